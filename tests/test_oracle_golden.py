@@ -1,0 +1,61 @@
+"""CPU: the oracle restatement reproduces the golden vectors that oracle/make_golden.py generated
+from the UNMODIFIED reference (trainers/rpo.py::CustomCLIP).  Same torch build -> bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.rpo_oracle import OracleModel, convert_state_dict
+from rpo_b200 import synth
+from tests.common import GOLDEN_CASES, class_tokens, load_golden, state_dict
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_oracle_matches_reference_golden(name):
+    g = load_golden(name)
+    prec = name.rsplit("_", 1)[1]
+    arch = synth.ARCHS["ViT-B/16"]
+    K, B = int(g["K"]), int(g["B"])
+    tokens = torch.from_numpy(g["tokens"].astype(np.int64))
+    # the committed token table agrees with what the reference tokenizer produced for this case
+    assert torch.equal(class_tokens(g["class_ids"].tolist()), tokens)
+    om = OracleModel(convert_state_dict(state_dict("ViT-B/16"), prec), tokens, K, prec)
+    image = synth.make_images(B, arch.image_resolution)
+    label = synth.make_labels(B, tokens.shape[0])
+    tp, ip = torch.from_numpy(g["text_prompt"]), torch.from_numpy(g["img_prompt"])
+    loss, gt, gi = om.step(image, tp, ip, label)
+    taps = {}
+    logits = om.logits(image, tp, ip, taps=taps)
+    # bit-exact on the same torch build; a tiny tolerance keeps the test meaningful on another
+    tol = 0.0 if torch.__version__.startswith("2.11.0") else 1e-5
+    assert abs(loss.item() - float(g["loss"])) <= tol
+    assert (logits - torch.from_numpy(g["logits"])).abs().max().item() <= tol * 100
+    assert (gt.float() - torch.from_numpy(g["grad_text_prompt"])).abs().max().item() <= tol
+    assert (gi.float() - torch.from_numpy(g["grad_img_prompt"])).abs().max().item() <= tol
+    tv = torch.stack([o[0, g["rows_v"].tolist(), :].float() for o in taps["img_layers"]])
+    tt = torch.stack([o[0, g["rows_t"].tolist(), :].float() for o in taps["text_layers"]])
+    assert (tv - torch.from_numpy(g["taps_v"])).abs().max().item() <= tol * 100
+    assert (tt - torch.from_numpy(g["taps_t"])).abs().max().item() <= tol * 100
+
+
+def test_structure_invariants_tiny():
+    """non-prompt rows do not depend on the prompts; the K-pair logit loop equals
+    one einsum.  Run on the tiny architecture (parameterised restatement)."""
+    arch = synth.ARCHS["tiny"]
+    sd = convert_state_dict(synth.make_state_dict(arch, 3), "fp32")
+    tokens = class_tokens([3, 77, 512])
+    K = 5
+    om = OracleModel(sd, tokens, K, "fp32")
+    img = synth.make_images(2, arch.image_resolution)
+    tp, ip = synth.make_prompt_init(sd, K)
+    t1, t2 = {}, {}
+    om.logits(img, tp, ip, taps=t1)
+    om.logits(img, tp + 1.0, ip - 0.5, taps=t2)
+    S = arch.n_patch + 1
+    for a, b in zip(t1["img_layers"], t2["img_layers"]):
+        assert torch.equal(a[:, :S], b[:, :S])
+    for a, b in zip(t1["text_layers"], t2["text_layers"]):
+        for c in range(tokens.shape[0]):
+            n = int(om.len_prompts[c])
+            assert torch.equal(a[c, :n], b[c, :n])
+    ein = torch.einsum("bkd,ckd->bc", t1["img_f"], t1["text_f"]) * om.sd["logit_scale"].exp() / K
+    assert (ein - t1["logits"]).abs().max().item() < 1e-4
