@@ -1,0 +1,187 @@
+/*
+ * rpo_b200 -- C ABI of the B200-native RPO hot path (CLIP ViT towers with K read-only prompts).
+ *
+ * The reference (mlvlab/RPO) has no FFI: its boundary is the Python class surface of
+ * trainers/rpo.py (CustomCLIP / PromptLearner, lines 41-232).  This header is what the host-side
+ * mirror of that surface (rpo_b200/model.py) binds through ctypes; each entry point names the
+ * reference code it replaces.  Plain C: pointers, sizes, an explicit cudaStream_t (passed as
+ * void*), int status returns (0 = ok, negative = error; rpo_last_error() gives the message).
+ * All device pointers are caller-owned unless stated; no entry point below allocates or
+ * synchronises on the hot path (rpo_forward / rpo_backward / rpo_sgd_step / the unit kernels),
+ * so the whole step can be captured into a CUDA graph by the caller.
+ *
+ * One handle per process/GPU, used from one host thread (same contract as the reference's single
+ * Python training thread, trainers/rpo.py:290-316).
+ */
+#ifndef RPO_B200_H
+#define RPO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RPO_OK 0
+#define RPO_ERR_INVALID (-1)
+#define RPO_ERR_CUDA (-2)
+#define RPO_ERR_STATE (-3)
+
+/* element type of activations and of the Linear/Conv/projection weights
+ * (clip/model.py:379-400 convert_weights; LayerNorm params, embeddings, logit_scale are always f32) */
+enum { RPO_F32 = 0, RPO_F16 = 1, RPO_BF16 = 2 };
+
+/* GEMM backends: tcgen05 (TMA + UMMA + TMEM, 16-bit types) or the generic SIMT kernel (any type,
+ * exact fp32 FMA; the only backend for RPO_F32).  AUTO picks tcgen05 whenever the shape allows. */
+enum { RPO_GEMM_AUTO = 0, RPO_GEMM_SIMT = 1, RPO_GEMM_TCGEN05 = 2 };
+
+/* epilogue activation */
+enum { RPO_ACT_NONE = 0, RPO_ACT_QUICKGELU = 1 };
+
+typedef struct RpoHandle RpoHandle;
+
+/* Model geometry.  Replaces the constants the reference hard-codes or reads off the CLIP module:
+ * trainers/rpo.py:52 (d_v), :142 (attn_head), :154 (1+14*14), :185 (512), clip/model.py:403-440. */
+typedef struct {
+  int32_t dtype;        /* RPO_F32 / RPO_F16 / RPO_BF16 */
+  int32_t K;            /* number of prompt pairs, cfg.TRAINER.RPO.K (trainers/rpo.py:49) */
+  int32_t n_cls;        /* C, number of class prompts */
+  int32_t ctx_len;      /* T = 77 */
+  int32_t embed_dim;    /* E */
+  int32_t v_width, v_layers, v_heads, v_patch, v_res;
+  int32_t t_width, t_layers, t_heads;
+  int32_t max_batch;    /* largest B rpo_forward will be called with (workspace is sized for it) */
+  int32_t gemm_backend; /* RPO_GEMM_* */
+  int32_t reserved[3];
+} RpoConfig;
+
+/* One ResidualAttentionBlock (clip/model.py:167-191).  ln_* are f32 [D]; the rest are `dtype`:
+ * in_w [3D,D], in_b [3D], out_w [D,D], out_b [D], fc_w [4D,D], fc_b [4D], proj_w [D,4D], proj_b [D]. */
+typedef struct {
+  const float *ln1_w, *ln1_b, *ln2_w, *ln2_b;
+  const void *in_w, *in_b, *out_w, *out_b, *fc_w, *fc_b, *proj_w, *proj_b;
+} RpoBlockWeights;
+
+/* Frozen CLIP weights on the path (trainers/rpo.py:104-120).  Device pointers, not owned; they
+ * must outlive the handle.  `*_blocks` are HOST arrays of v_layers / t_layers entries. */
+typedef struct {
+  const RpoBlockWeights *v_blocks;
+  const RpoBlockWeights *t_blocks;
+  const void *conv_w;       /* visual.conv1.weight [Dv, 3*p*p] dtype (clip/model.py:215) */
+  const float *cls_emb;     /* visual.class_embedding [Dv] f32 (:218) */
+  const float *v_pos;       /* visual.positional_embedding [S, Dv] f32 (:219) */
+  const float *ln_pre_w, *ln_pre_b, *ln_post_w, *ln_post_b; /* f32 [Dv] (:220,:224) */
+  const void *v_proj;       /* visual.proj [Dv, E] dtype (:225) */
+  const float *ln_final_w, *ln_final_b;                     /* f32 [Dt] */
+  const void *t_proj;       /* text_projection [Dt, E] dtype */
+  const float *logit_scale; /* f32 device scalar */
+} RpoWeights;
+
+const char *rpo_last_error(void);
+int rpo_version(void);
+
+/* lifetime ------------------------------------------------------------------------------------ */
+int rpo_create(const RpoConfig *cfg, RpoHandle **out);
+void rpo_destroy(RpoHandle *h);
+/* bytes of device memory the handle owns (workspace + transposed weight copies + context cache) */
+size_t rpo_device_bytes(const RpoHandle *h);
+
+/* Replaces CustomCLIP.__init__'s aliasing of the frozen sub-modules (trainers/rpo.py:104-120).
+ * Builds the K-major transposed copies the backward GEMMs read (weights are frozen, so this is a
+ * one-off).  Synchronises `stream` before returning. */
+int rpo_bind_weights(RpoHandle *h, const RpoWeights *w, void *stream);
+
+/* Replaces make_prompts' text_x/len_prompts (trainers/rpo.py:135-137), define_mask (:140-159) and
+ * the prompt-independent part of the text tower call (:180-181): runs the n_c = len_prompts[c]
+ * readable context tokens of every class through the text transformer once and caches their
+ * per-layer K/V.  text_x: device [C, T, Dt] dtype (token + positional embedding);
+ * len_prompts: HOST int32 [C], each in [1, T-K].  Synchronises `stream`. */
+int rpo_set_classes(RpoHandle *h, const void *text_x, const int32_t *len_prompts, void *stream);
+
+/* CustomCLIP.forward (trainers/rpo.py:161-232).  image: device [B,3,res,res], f32 (image_dtype =
+ * RPO_F32, cast to dtype inside like `image.type(self.dtype)`, :198) or already `dtype`.
+ * text_prompt [K,Dt], img_prompt [K,Dv]: device, dtype (PromptLearner.forward, :89-90).
+ * label: device int64 [B] or NULL.  logits: device f32 [B,C] or NULL.  loss: device f32 scalar or
+ * NULL (requires label).  Saves what rpo_backward needs inside the handle. */
+int rpo_forward(RpoHandle *h, const void *image, int32_t image_dtype, int32_t B, const void *text_prompt,
+                const void *img_prompt, const int64_t *label, float *logits, float *loss, void *stream);
+
+/* loss.backward() of trainers/rpo.py:308 restricted to what has a gradient (:258-260): writes
+ * d loss / d text_prompt into grad_flat[0 : K*Dt] and d loss / d img_prompt into
+ * grad_flat[K*Dt : K*Dt + K*Dv] (f32, contiguous: all-reduce ready).  Must follow an rpo_forward
+ * that was given a label. */
+int rpo_backward(RpoHandle *h, float *grad_flat, void *stream);
+
+/* optim.step() of trainers/rpo.py:309 for torch.optim.SGD semantics (momentum, dampening 0, L2
+ * weight decay, no nesterov) applied to one parameter in `dtype` with an f32 gradient:
+ *   g = scale*grad + wd*p ; buf = first ? g : mom*buf + g ; p -= lr*buf.
+ * `first_step` is a device int32 flag (non-zero before any momentum exists) so the call is
+ * graph-capturable; lr is a device f32 scalar for the same reason. */
+int rpo_sgd_step(void *param, int32_t dtype, const float *grad, float *momentum_buf, int64_t n, const float *lr,
+                 float momentum, float weight_decay, float grad_scale, const int32_t *first_step, void *stream);
+
+/* unit kernels (one per hot-path op; used by the parity tests) -------------------------------- */
+
+/* clip/model.py:153-159 LayerNorm.forward: y = LN_f32(x; w, b, eps=1e-5) cast to dtype. x,y [rows,D]. */
+int rpo_layernorm_fwd(const void *x, const float *w, const float *b, void *y, int64_t rows, int32_t D, int32_t dtype,
+                      void *stream);
+/* its input-gradient: dx = dres (nullable) + dLN/dx(dy; x, w).  All [rows,D] dtype. */
+int rpo_layernorm_bwd(const void *dy, const void *x, const float *w, const void *dres, void *dx, int64_t rows,
+                      int32_t D, int32_t dtype, void *stream);
+
+/* nn.Linear / `@` (clip/model.py:174-176,186; trainers/rpo.py:191,210): C[M,N] = A[M,Kd] . B[N,Kd]^T
+ * with fused epilogue: v = acc + bias[n]; aux_out (rows >= aux_row0) = v; v = act(v);
+ * v *= quickgelu'(gelu_grad_aux[m,n]); C = v + residual[m,n].  Row strides lda/ldb/ldc in elements;
+ * residual / aux use ldc.  Nullable: bias, residual, gelu_grad_aux, aux_out. */
+int rpo_gemm_bias_act(const void *A, int64_t lda, const void *B, int64_t ldb, void *C, int64_t ldc, int64_t M,
+                      int32_t N, int32_t Kd, const void *bias, int32_t act, const void *residual,
+                      const void *gelu_grad_aux, void *aux_out, int64_t aux_row0, int32_t dtype, int32_t backend,
+                      void *stream);
+
+/* Read-only masked multi-head attention (clip/model.py:186 with the masks of trainers/rpo.py:140-159).
+ * G groups (images / classes).  Group g has n_g = ctx_off[g+1]-ctx_off[g] context rows (its keys
+ * and values, and -- if do_ctx -- also queries) stored at rows ctx_off[g].. of qkv_ctx [Mc, 3D]
+ * (q | k | v, head-major inside each D), and K prompt rows (queries only) at rows g*K.. of
+ * q_prompt [G*K, D].  Context row r reads keys j<n_g (vision) or j<=r (causal, text); prompt rows
+ * read every key j<n_g.  Nothing reads a prompt row.  Output rows: out_ctx [Mc, D] (if do_ctx)
+ * and out_prompt [G*K, D].  head_dim is 64.  ctx_off: device int32 [G+1]. */
+int rpo_ro_attention_fwd(const void *qkv_ctx, const void *q_prompt, void *out_ctx, void *out_prompt,
+                         const int32_t *ctx_off, int32_t G, int32_t K, int32_t H, int32_t max_ctx, int32_t causal,
+                         int32_t do_ctx, int32_t dtype, void *stream);
+/* gradient w.r.t. the prompt queries only (keys/values come from rows that carry no gradient):
+ * dq_prompt [G*K, D] from d_out_prompt [G*K, D]. */
+int rpo_ro_attention_bwd(const void *qkv_ctx, const void *q_prompt, const void *d_out_prompt, void *dq_prompt,
+                         const int32_t *ctx_off, int32_t G, int32_t K, int32_t H, int32_t max_ctx, int32_t dtype,
+                         void *stream);
+
+/* trainers/rpo.py:215-230: L2-normalise img_feat [B,K,E] and text_feat [C,K,E] (dtype), K-pair
+ * logits with exp(logit_scale) folded into the image side in `dtype`, f32 accumulation over the K
+ * pairs, /K, and (label != NULL) mean cross-entropy.  Scratch is caller-provided:
+ * img_n, img_s [B,K,E], text_n [C,K,E], pair_logits [K,B,C] (dtype), inv norms f32 [B*K], [C*K].
+ * Outputs logits f32 [B,C], loss f32 scalar, dlogits f32 [B,C] (d loss / d logits; nullable). */
+int rpo_logits_ce_fwd(const void *img_feat, const void *text_feat, const float *logit_scale, const int64_t *label,
+                      int32_t B, int32_t C, int32_t K, int32_t E, void *img_n, void *img_s, void *text_n,
+                      float *img_rnorm, float *text_rnorm, void *pair_logits, float *logits, float *loss,
+                      float *dlogits, int32_t dtype, void *stream);
+/* backward of the above to d img_feat [B,K,E] and d text_feat [C,K,E] (dtype).
+ * Scratch: dl_t [B,C] dtype, d_img_s [B,K,E], d_text_n [C,K,E] dtype. */
+int rpo_logits_ce_bwd(const float *dlogits, const void *img_feat, const void *text_feat, const void *img_n,
+                      const void *img_s, const void *text_n, const float *img_rnorm, const float *text_rnorm,
+                      const float *logit_scale, int32_t B, int32_t C, int32_t K, int32_t E, void *dl_t, void *d_img_s,
+                      void *d_text_n, void *d_img_feat, void *d_text_feat, int32_t dtype, void *stream);
+
+/* introspection for tests: copies of internal activations after rpo_forward.
+ * which: 0 = vision residual stream after block `layer` ([B*(S+K), Dv]: context rows image-major,
+ * then prompt rows image-major), 1 = text residual stream after block `layer` ([Mc + C*K, Dt]),
+ * 2 = img_feat [B,K,E], 3 = text_feat [C,K,E].  Returns the number of elements, copies at most
+ * `cap` elements (dtype) to `dst` (device).  layer = -1 means the tower input. */
+int64_t rpo_debug_fetch(RpoHandle *h, int32_t which, int32_t layer, void *dst, int64_t cap, void *stream);
+
+/* number of kernel launches issued by the last rpo_forward + rpo_backward pair */
+int64_t rpo_launch_count(const RpoHandle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RPO_B200_H */

@@ -1,0 +1,412 @@
+// HBM-streaming kernels of the path: LayerNorm fwd/bwd (clip/model.py:153-159), patch extraction,
+// embedding assembly (trainers/rpo.py:198-204), prompt broadcast / gradient reduction, SGD.
+// All are bandwidth-bound: one warp per row, 16-byte vector loads, warp-shuffle reductions.
+#include "common.cuh"
+
+namespace rpo {
+
+static constexpr int LN_WARPS = 8;
+static constexpr float LN_EPS = 1e-5f;
+
+// Loads one row (D elements of T) spread over a warp into registers as f32.
+// Lane l owns vectors l, l+32, ... ; MAXV vectors of VEC elements each (D <= 32*MAXV*VEC = 1024).
+template <typename T, int MAXV>
+__device__ __forceinline__ void load_row(const T *row, int nv, int lane, float (&vals)[MAXV * Vec16<T>::N]) {
+  constexpr int VEC = Vec16<T>::N;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int vi = lane + 32 * i;
+    if (vi < nv) {
+      Vec16<T> v = ld16(row + (size_t)vi * VEC);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) vals[i * VEC + e] = tof<T>(v.v[e]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) vals[i * VEC + e] = 0.f;
+    }
+  }
+}
+
+template <typename T, int MAXV>
+__device__ __forceinline__ void row_stats(const float (&vals)[MAXV * Vec16<T>::N], int nv, int lane, int D,
+                                          float &mean, float &rstd) {
+  constexpr int VEC = Vec16<T>::N;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV * VEC; ++i) s += vals[i];  // padding entries are zero
+  mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (lane + 32 * i < nv) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        float d = vals[i * VEC + e] - mean;
+        q += d * d;
+      }
+    }
+  }
+  float var = warp_sum(q) / (float)D;
+  rstd = 1.0f / sqrtf(var + LN_EPS);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const T *__restrict__ x, const float *__restrict__ w,
+                                                               const float *__restrict__ b, T *__restrict__ y,
+                                                               long long rows, int D) {
+  constexpr int VEC = Vec16<T>::N;
+  constexpr int MAXV = 32 / VEC;
+  long long row = (long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  int nv = D / VEC;
+  float vals[MAXV * VEC];
+  load_row<T, MAXV>(x + row * D, nv, lane, vals);
+  float mean, rstd;
+  row_stats<T, MAXV>(vals, nv, lane, D, mean, rstd);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int vi = lane + 32 * i;
+    if (vi < nv) {
+      Vec16<T> o;
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        int c = vi * VEC + e;
+        o.v[e] = fromf<T>((vals[i * VEC + e] - mean) * rstd * __ldg(w + c) + __ldg(b + c));
+      }
+      st16(y + row * D + (size_t)vi * VEC, o);
+    }
+  }
+}
+
+// dx = dres + rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy * w,  xhat = (x-mean)*rstd
+template <typename T>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const T *__restrict__ dy, const T *__restrict__ x,
+                                                               const float *__restrict__ w, const T *__restrict__ dres,
+                                                               T *__restrict__ dx, long long rows, int D) {
+  constexpr int VEC = Vec16<T>::N;
+  constexpr int MAXV = 32 / VEC;
+  long long row = (long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  int nv = D / VEC;
+  float xv[MAXV * VEC], gv[MAXV * VEC];
+  load_row<T, MAXV>(x + row * D, nv, lane, xv);
+  load_row<T, MAXV>(dy + row * D, nv, lane, gv);
+  float mean, rstd;
+  row_stats<T, MAXV>(xv, nv, lane, D, mean, rstd);
+  float sg = 0.f, sgx = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int vi = lane + 32 * i;
+    if (vi < nv) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        int c = vi * VEC + e;
+        float g = gv[i * VEC + e] * __ldg(w + c);
+        float xh = (xv[i * VEC + e] - mean) * rstd;
+        gv[i * VEC + e] = g;
+        xv[i * VEC + e] = xh;
+        sg += g;
+        sgx += g * xh;
+      }
+    }
+  }
+  sg = warp_sum(sg) / (float)D;
+  sgx = warp_sum(sgx) / (float)D;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int vi = lane + 32 * i;
+    if (vi < nv) {
+      Vec16<T> o, r;
+      if (dres) r = ld16(dres + row * D + (size_t)vi * VEC);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        float v = rstd * (gv[i * VEC + e] - sg - xv[i * VEC + e] * sgx);
+        if (dres) v += tof<T>(r.v[e]);
+        o.v[e] = fromf<T>(v);
+      }
+      st16(dx + row * D + (size_t)vi * VEC, o);
+    }
+  }
+}
+
+static bool ln_shape_ok(int D, size_t esz) { return D > 0 && D <= 1024 && (D * esz) % 16 == 0; }
+
+template <typename T>
+int layernorm_fwd(const T *x, const float *w, const float *b, T *y, long long rows, int D, cudaStream_t st) {
+  RPO_REQUIRE(ln_shape_ok(D, sizeof(T)), "LayerNorm width must be <= 1024 and a multiple of 16 bytes");
+  if (rows <= 0) return RPO_OK;
+  unsigned grid = (unsigned)((rows + LN_WARPS - 1) / LN_WARPS);
+  ln_fwd_kernel<T><<<grid, LN_WARPS * 32, 0, st>>>(x, w, b, y, rows, D);
+  RPO_LAUNCH_CHECK();
+  return RPO_OK;
+}
+template <typename T>
+int layernorm_bwd(const T *dy, const T *x, const float *w, const T *dres, T *dx, long long rows, int D,
+                  cudaStream_t st) {
+  RPO_REQUIRE(ln_shape_ok(D, sizeof(T)), "LayerNorm width must be <= 1024 and a multiple of 16 bytes");
+  if (rows <= 0) return RPO_OK;
+  unsigned grid = (unsigned)((rows + LN_WARPS - 1) / LN_WARPS);
+  ln_bwd_kernel<T><<<grid, LN_WARPS * 32, 0, st>>>(dy, x, w, dres, dx, rows, D);
+  RPO_LAUNCH_CHECK();
+  return RPO_OK;
+}
+
+// ---- patch extraction: conv1 with stride == kernel (clip/model.py:215) is a GEMM over patches ----
+// out[(b*NP + py*G + px), c*P*P + ky*P + kx] = T(image[b, c, py*P+ky, px*P+kx])
+template <typename T, typename TI>
+__global__ void im2col_kernel(const TI *__restrict__ img, T *__restrict__ out, int B, int res, int P, int ld,
+                              long long total) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int G = res / P;
+  int col = (int)(idx % ld);
+  long long row = idx / ld;
+  if (col >= 3 * P * P) {  // zero padding up to the GEMM K tile
+    out[idx] = fromf<T>(0.f);
+    return;
+  }
+  int kx = col % P, ky = (col / P) % P, c = col / (P * P);
+  int p = (int)(row % (G * G));
+  int b = (int)(row / (G * G));
+  int py = p / G, px = p % G;
+  float v = Num<TI>::to_f(img[(((size_t)b * 3 + c) * res + (py * P + ky)) * res + (px * P + kx)]);
+  out[idx] = fromf<T>(v);
+}
+
+template <typename T>
+int im2col_patches(const void *image, int image_dtype, T *out, int B, int res, int patch, int ld, cudaStream_t st) {
+  int G = res / patch;
+  long long total = (long long)B * G * G * ld;
+  if (total == 0) return RPO_OK;
+  unsigned grid = (unsigned)((total + 255) / 256);
+  if (image_dtype == RPO_F32) {
+    im2col_kernel<T, float><<<grid, 256, 0, st>>>((const float *)image, out, B, res, patch, ld, total);
+  } else {
+    RPO_REQUIRE(image_dtype == Num<T>::dtype, "image must be f32 or the model dtype");
+    im2col_kernel<T, T><<<grid, 256, 0, st>>>((const T *)image, out, B, res, patch, ld, total);
+  }
+  RPO_LAUNCH_CHECK();
+  return RPO_OK;
+}
+
+// trainers/rpo.py:199-204: [cls ; patches] + pos (dtype add), then the K image prompts appended
+// (prompts get no positional embedding).  Context rows are image-major [B*S, D]; prompt rows
+// [B*K, D].  ln_pre (:206) is applied afterwards by layernorm_fwd over both row sets.
+template <typename T>
+__global__ void vision_assemble_kernel(const T *__restrict__ patch_emb, const float *__restrict__ cls,
+                                       const float *__restrict__ pos, const T *__restrict__ img_prompt,
+                                       T *__restrict__ x_ctx, T *__restrict__ x_prompt, int B, int S, int K, int D) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long n_ctx = (long long)B * S * D;
+  long long total = n_ctx + (long long)B * K * D;
+  if (idx >= total) return;
+  if (idx < n_ctx) {
+    int d = (int)(idx % D);
+    long long r = idx / D;
+    int s = (int)(r % S);
+    int b = (int)(r / S);
+    float e = (s == 0) ? rnd<T>(cls[d]) : tof<T>(patch_emb[((size_t)b * (S - 1) + (s - 1)) * D + d]);
+    x_ctx[idx] = fromf<T>(e + rnd<T>(pos[(size_t)s * D + d]));
+  } else {
+    long long j = idx - n_ctx;
+    int d = (int)(j % D);
+    int i = (int)((j / D) % K);
+    x_prompt[j] = img_prompt[(size_t)i * D + d];
+  }
+}
+
+template <typename T>
+int vision_assemble_lnpre(const T *patch_emb, const float *cls, const float *pos, const float *, const float *,
+                          const T *img_prompt, T *x_ctx, T *x_prompt, int B, int S, int K, int D, cudaStream_t st) {
+  long long total = (long long)B * (S + K) * D;
+  if (total == 0) return RPO_OK;
+  vision_assemble_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(patch_emb, cls, pos, img_prompt, x_ctx,
+                                                                            x_prompt, B, S, K, D);
+  RPO_LAUNCH_CHECK();
+  return RPO_OK;
+}
+
+// context rows of the text tower: x_ctx[r, :] = text_x[row_cls[r], row_pos[r], :]
+template <typename T>
+__global__ void text_gather_kernel(const T *__restrict__ text_x, const int *__restrict__ row_cls,
+                                   const int *__restrict__ row_pos, T *__restrict__ x_ctx, long long Mc, int T_len,
+                                   int D) {
+  constexpr int VEC = Vec16<T>::N;
+  int nv = D / VEC;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Mc * nv) return;
+  long long r = idx / nv;
+  int v = (int)(idx % nv);
+  const T *src = text_x + ((size_t)row_cls[r] * T_len + row_pos[r]) * D + (size_t)v * VEC;
+  st16(x_ctx + r * D + (size_t)v * VEC, ld16(src));
+}
+template <typename T>
+int text_gather_ctx(const T *text_x, const int *, const int *row_cls, const int *row_pos, T *x_ctx, long long Mc,
+                    int T_len, int D, cudaStream_t st) {
+  constexpr int VEC = Vec16<T>::N;
+  long long total = Mc * (D / VEC);
+  if (total == 0) return RPO_OK;
+  text_gather_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(text_x, row_cls, row_pos, x_ctx, Mc, T_len, D);
+  RPO_LAUNCH_CHECK();
+  return RPO_OK;
+}
+
+// dst[g*K + i, :] = src[i, :]   (the shared text prompt spliced into every class, trainers/rpo.py:176-177)
+template <typename T>
+__global__ void broadcast_rows_kernel(const T *__restrict__ src, T *__restrict__ dst, int G, int K, int D) {
+  constexpr int VEC = Vec16<T>::N;
+  int nv = D / VEC;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)G * K * nv;
+  if (idx >= total) return;
+  int v = (int)(idx % nv);
+  int i = (int)((idx / nv) % K);
+  st16(dst + idx * VEC, ld16(src + ((size_t)i * nv + v) * VEC));
+}
+template <typename T>
+int broadcast_rows(const T *src, T *dst, int G, int K, int D, cudaStream_t st) {
+  constexpr int VEC = Vec16<T>::N;
+  long long total = (long long)G * K * (D / VEC);
+  if (total == 0) return RPO_OK;
+  broadcast_rows_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, dst, G, K, D);
+  RPO_LAUNCH_CHECK();
+  return RPO_OK;
+}
+
+// dst[i, d] = sum_g src[g*K + i, d]   (backward of the broadcast; f32 accumulation).
+// grid.y splits the groups; partial sums are combined with atomics into a zeroed dst.
+template <typename T>
+__global__ void reduce_groups_kernel(const T *__restrict__ src, float *__restrict__ dst, int G, int K, int D,
+                                     int g_per_block) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= K * D) return;
+  int g0 = blockIdx.y * g_per_block;
+  int g1 = min(G, g0 + g_per_block);
+  float acc = 0.f;
+  for (int g = g0; g < g1; ++g) acc += tof<T>(src[(size_t)g * K * D + idx]);
+  atomicAdd(dst + idx, acc);
+}
+template <typename T>
+int reduce_groups_f32(const T *src, float *dst, int G, int K, int D, cudaStream_t st) {
+  RPO_CHECK_CUDA(cudaMemsetAsync(dst, 0, sizeof(float) * K * D, st));
+  if (G == 0) return RPO_OK;
+  int g_per_block = 16;
+  dim3 grid((K * D + 255) / 256, (G + g_per_block - 1) / g_per_block);
+  reduce_groups_kernel<T><<<grid, 256, 0, st>>>(src, dst, G, K, D, g_per_block);
+  RPO_LAUNCH_CHECK();
+  return RPO_OK;
+}
+
+// gradient of ln_pre w.r.t. the image prompts: every image sees the same prompt row, so
+// d img_prompt[i] = dLN/dx(sum_b dy[b,i]; x = img_prompt[i]).  One warp per prompt row, D <= 1024.
+template <typename T>
+__global__ void lnpre_prompt_bwd_kernel(const float *__restrict__ dsum, const T *__restrict__ xp,
+                                        const float *__restrict__ w, float *__restrict__ grad, int K, int D) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= K) return;
+  const T *x = xp + (size_t)row * D;
+  const float *dy = dsum + (size_t)row * D;
+  float s = 0.f;
+  for (int c = lane; c < D; c += 32) s += tof<T>(x[c]);
+  float mean = warp_sum(s) / D;
+  float q = 0.f;
+  for (int c = lane; c < D; c += 32) {
+    float d = tof<T>(x[c]) - mean;
+    q += d * d;
+  }
+  float rstd = 1.0f / sqrtf(warp_sum(q) / D + LN_EPS);
+  float sg = 0.f, sgx = 0.f;
+  for (int c = lane; c < D; c += 32) {
+    float g = dy[c] * w[c];
+    float xh = (tof<T>(x[c]) - mean) * rstd;
+    sg += g;
+    sgx += g * xh;
+  }
+  sg = warp_sum(sg) / D;
+  sgx = warp_sum(sgx) / D;
+  for (int c = lane; c < D; c += 32) {
+    float g = dy[c] * w[c];
+    float xh = (tof<T>(x[c]) - mean) * rstd;
+    grad[(size_t)row * D + c] = rstd * (g - sg - xh * sgx);
+  }
+}
+template <typename T>
+int lnpre_prompt_bwd(const float *dsum, const T *img_prompt, const float *w, float *grad, int K, int D,
+                     cudaStream_t st) {
+  if (K == 0) return RPO_OK;
+  lnpre_prompt_bwd_kernel<T><<<(K + 3) / 4, 128, 0, st>>>(dsum, img_prompt, w, grad, K, D);
+  RPO_LAUNCH_CHECK();
+  return RPO_OK;
+}
+
+// dst[c, r] = src[r, c]  (one-off at weight-bind time: K-major copies for the backward GEMMs)
+template <typename T>
+__global__ void transpose_kernel(const T *__restrict__ src, T *__restrict__ dst, int rows, int cols) {
+  __shared__ T tile[32][33];
+  int c = blockIdx.x * 32 + threadIdx.x;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int r = blockIdx.y * 32 + j;
+    if (r < rows && c < cols) tile[j][threadIdx.x] = src[(size_t)r * cols + c];
+  }
+  __syncthreads();
+  int r2 = blockIdx.y * 32 + threadIdx.x;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int c2 = blockIdx.x * 32 + j;
+    if (r2 < rows && c2 < cols) dst[(size_t)c2 * rows + r2] = tile[threadIdx.x][j];
+  }
+}
+template <typename T>
+int transpose_2d(const T *src, T *dst, int rows, int cols, cudaStream_t st) {
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  transpose_kernel<T><<<grid, block, 0, st>>>(src, dst, rows, cols);
+  RPO_LAUNCH_CHECK();
+  return RPO_OK;
+}
+
+// torch.optim.SGD step (momentum, dampening 0, L2 weight decay), parameter stored in T
+template <typename T>
+__global__ void sgd_kernel(T *__restrict__ p, const float *__restrict__ g, float *__restrict__ buf, long long n,
+                           const float *__restrict__ lr, float mom, float wd, float gscale,
+                           const int *__restrict__ first) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float pv = tof<T>(p[i]);
+  float gv = gscale * g[i] + wd * pv;
+  float b = gv;
+  if (mom != 0.f) {
+    b = (first && *first) ? gv : mom * buf[i] + gv;
+    buf[i] = b;
+  }
+  p[i] = fromf<T>(pv - (*lr) * b);
+}
+template <typename T>
+int sgd_step(T *p, const float *g, float *buf, long long n, const float *lr, float mom, float wd, float gscale,
+             const int *first, cudaStream_t st) {
+  if (n == 0) return RPO_OK;
+  sgd_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, g, buf, n, lr, mom, wd, gscale, first);
+  RPO_LAUNCH_CHECK();
+  return RPO_OK;
+}
+
+#define INSTANTIATE(T)                                                                                              \
+  template int layernorm_fwd<T>(const T *, const float *, const float *, T *, long long, int, cudaStream_t);        \
+  template int layernorm_bwd<T>(const T *, const T *, const float *, const T *, T *, long long, int, cudaStream_t); \
+  template int im2col_patches<T>(const void *, int, T *, int, int, int, int, cudaStream_t);                              \
+  template int vision_assemble_lnpre<T>(const T *, const float *, const float *, const float *, const float *,      \
+                                        const T *, T *, T *, int, int, int, int, cudaStream_t);                     \
+  template int text_gather_ctx<T>(const T *, const int *, const int *, const int *, T *, long long, int, int,       \
+                                  cudaStream_t);                                                                    \
+  template int broadcast_rows<T>(const T *, T *, int, int, int, cudaStream_t);                                      \
+  template int reduce_groups_f32<T>(const T *, float *, int, int, int, cudaStream_t);                               \
+  template int lnpre_prompt_bwd<T>(const float *, const T *, const float *, float *, int, int, cudaStream_t);       \
+  template int transpose_2d<T>(const T *, T *, int, int, cudaStream_t);                                             \
+  template int sgd_step<T>(T *, const float *, float *, long long, const float *, float, float, float, const int *, \
+                           cudaStream_t);
+INSTANTIATE(float)
+INSTANTIATE(__half)
+INSTANTIATE(__nv_bfloat16)
+
+}  // namespace rpo

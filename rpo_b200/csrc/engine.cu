@@ -1,0 +1,694 @@
+// Host-side orchestration of the RPO hot path and the C ABI (include/rpo_b200.h).
+//
+// Data layout in HBM ("row sets").  A tower (vision / text) processes G groups (images / classes).
+// Group g owns n_g context rows (patch+cls tokens / readable word tokens) and K prompt rows.  All
+// activations of a tower are 2-D row-major [rows, D] matrices with the context rows of all groups
+// first (group-major, offsets ctx_off[g]) and the prompt rows of all groups after them
+// ([Mc, Mc + G*K), group-major).  Every GEMM / LayerNorm therefore runs over one contiguous row
+// range, the prompt-only passes (text tower per step, the whole backward) are a pointer offset, and
+// the read-only mask (trainers/rpo.py:140-159) is never materialised: it is the split itself.
+//
+// Per block l the handle keeps x_in[l] (block input), qkv[l] (context q|k|v), qp[l] (prompt q),
+// x_mid[l] (after the attention residual) and fcpre[l] (MLP pre-activation of the prompt rows);
+// that is everything the prompt-row backward needs, so nothing is recomputed.
+#include <vector>
+
+#include "common.cuh"
+
+namespace rpo {
+
+thread_local std::string g_last_error;
+thread_local int64_t g_launch_count = 0;
+void set_error(const std::string &msg) { g_last_error = msg; }
+
+struct Arena {
+  char *base = nullptr;
+  size_t cap = 0, off = 0;
+  void *take(size_t bytes) {
+    size_t a = (off + 255) & ~(size_t)255;
+    if (a + bytes > cap) return nullptr;
+    off = a + bytes;
+    return base + a;
+  }
+};
+
+struct Tower {
+  int D = 0, H = 0, layers = 0, K = 0, causal = 0;
+  int G = 0, Gmax = 0, max_ctx = 0;
+  long long Mc = 0, Mc_max = 0, Mp_max = 0, Mtot_max = 0;
+  int *ctx_off = nullptr;  // device [Gmax+1]
+  // per-layer saved activations
+  char *x_in = nullptr, *qkv = nullptr, *qp = nullptr, *x_mid = nullptr, *fcpre = nullptr;
+  // transients
+  char *h = nullptr, *o = nullptr, *fc = nullptr;
+  // backward scratch (prompt rows)
+  char *dx = nullptr, *dx_mid = nullptr, *dh = nullptr, *dpre = nullptr, *dao = nullptr, *dq = nullptr;
+  std::vector<RpoBlockWeights> blocks;
+  std::vector<char *> proj_wT, fc_wT, out_wT, q_wT;  // K-major operands of the input-gradient GEMMs
+};
+
+}  // namespace rpo
+
+using namespace rpo;
+
+struct RpoHandle {
+  RpoConfig cfg;
+  size_t esz = 2;
+  int S = 0, NP = 0;  // vision context rows per image (1 + patches), patches
+  int pk = 0, pk_pad = 0;  // 3*p*p and its zero-padded extent
+  const void *conv_w_eff = nullptr;  // conv weight as [Dv, pk_pad]
+  Tower vis, txt;
+  Arena arena;
+  size_t device_bytes = 0;
+  std::vector<void *> owned;  // separately cudaMalloc'ed blocks
+  RpoWeights w{};
+  bool bound = false, classes_set = false, fwd_has_grad = false;
+  int B = 0;
+  // vision front end
+  char *patches = nullptr, *patch_emb = nullptr, *x_raw = nullptr;
+  // heads
+  char *hp_v = nullptr, *hp_t = nullptr, *img_feat = nullptr, *text_feat = nullptr;
+  char *v_projT = nullptr, *t_projT = nullptr;
+  // logit block
+  char *img_n = nullptr, *img_s = nullptr, *text_n = nullptr, *pair = nullptr, *dl_t = nullptr;
+  char *d_img_s = nullptr, *d_text_n = nullptr, *d_img_feat = nullptr, *d_text_feat = nullptr;
+  float *img_norm = nullptr, *text_norm = nullptr, *logits_f = nullptr, *dlogits = nullptr, *loss_f = nullptr;
+  float *dsum_v = nullptr;  // [K, Dv] f32: sum over images of d(ln_pre output) at the prompt rows
+  // text context gather maps
+  int *row_cls = nullptr, *row_pos = nullptr;
+  const void *img_prompt = nullptr;  // from the last forward (needed by the ln_pre backward)
+  int64_t launches_fwd = 0, launches_bwd = 0;
+};
+
+namespace rpo {
+
+template <typename T>
+static T *at(char *base, long long elem_off) {
+  return reinterpret_cast<T *>(base) + elem_off;
+}
+
+template <typename T>
+static int tower_forward(RpoHandle *hd, Tower &tw, bool do_ctx, bool do_prompt, cudaStream_t st) {
+  const int D = tw.D, backend = hd->cfg.gemm_backend;
+  const long long Mc = tw.Mc, Mp = (long long)tw.G * tw.K;
+  const long long r0 = do_ctx ? 0 : Mc;
+  const long long r1 = do_prompt ? Mc + Mp : Mc;
+  const long long rows = r1 - r0;
+  if (rows <= 0) return RPO_OK;
+  const long long xs = tw.Mtot_max * D;  // per-layer stride of x_in / x_mid
+  for (int l = 0; l < tw.layers; ++l) {
+    const RpoBlockWeights &bw = tw.blocks[l];
+    T *x_in = at<T>(tw.x_in, l * xs), *x_out = at<T>(tw.x_in, (l + 1) * xs), *x_mid = at<T>(tw.x_mid, l * xs);
+    T *h = (T *)tw.h, *o = (T *)tw.o, *fc = (T *)tw.fc;
+    T *qkv = at<T>(tw.qkv, (long long)l * tw.Mc_max * 3 * D);
+    T *qp = at<T>(tw.qp, (long long)l * tw.Mp_max * D);
+    T *fcpre = at<T>(tw.fcpre, (long long)l * tw.Mp_max * 4 * D);
+    // x = x + attn(ln_1(x))                                             clip/model.py:189
+    RPO_TRY(layernorm_fwd<T>(x_in + r0 * D, bw.ln1_w, bw.ln1_b, h + r0 * D, rows, D, st));
+    Epilogue<T> ep{};
+    if (do_ctx) {
+      ep = Epilogue<T>{};
+      ep.bias = (const T *)bw.in_b;
+      RPO_TRY(gemm_dispatch<T>(backend, h, D, (const T *)bw.in_w, D, qkv, 3 * D, Mc, 3 * D, D, ep, st));
+    }
+    if (do_prompt) {
+      // prompts are queries only: project with the q third of in_proj (rows 0..D-1)
+      ep = Epilogue<T>{};
+      ep.bias = (const T *)bw.in_b;
+      RPO_TRY(gemm_dispatch<T>(backend, h + Mc * D, D, (const T *)bw.in_w, D, qp, D, Mp, D, D, ep, st));
+    }
+    RPO_TRY(ro_attention_fwd<T>(qkv, qp, o, o + Mc * D, tw.ctx_off, tw.G, do_prompt ? tw.K : 0, tw.H, tw.max_ctx,
+                                tw.causal, do_ctx ? 1 : 0, st));
+    ep = Epilogue<T>{};
+    ep.bias = (const T *)bw.out_b;
+    ep.residual = x_in + r0 * D;
+    RPO_TRY(gemm_dispatch<T>(backend, o + r0 * D, D, (const T *)bw.out_w, D, x_mid + r0 * D, D, rows, D, D, ep, st));
+    // x = x + mlp(ln_2(x))                                              clip/model.py:190
+    RPO_TRY(layernorm_fwd<T>(x_mid + r0 * D, bw.ln2_w, bw.ln2_b, h + r0 * D, rows, D, st));
+    ep = Epilogue<T>{};
+    ep.bias = (const T *)bw.fc_b;
+    ep.act = RPO_ACT_QUICKGELU;
+    if (do_prompt) {
+      ep.aux_out = fcpre;
+      ep.aux_row0 = Mc - r0;  // row index inside this launch where the prompt rows begin
+    }
+    RPO_TRY(gemm_dispatch<T>(backend, h + r0 * D, D, (const T *)bw.fc_w, D, fc + r0 * 4 * D, 4 * D, rows, 4 * D, D, ep,
+                             st));
+    ep = Epilogue<T>{};
+    ep.bias = (const T *)bw.proj_b;
+    ep.residual = x_mid + r0 * D;
+    RPO_TRY(gemm_dispatch<T>(backend, fc + r0 * 4 * D, 4 * D, (const T *)bw.proj_w, 4 * D, x_out + r0 * D, D, rows, D,
+                             4 * D, ep, st));
+  }
+  return RPO_OK;
+}
+
+// Input-gradient of the tower restricted to the prompt rows (the only rows on a path from the
+// learnable prompts to the loss).  dx: [Mp, D] gradient w.r.t. the tower output, overwritten with
+// the gradient w.r.t. the tower input.
+template <typename T>
+static int tower_backward(RpoHandle *hd, Tower &tw, cudaStream_t st) {
+  const int D = tw.D, backend = hd->cfg.gemm_backend;
+  const long long Mc = tw.Mc, Mp = (long long)tw.G * tw.K;
+  const long long xs = tw.Mtot_max * D;
+  T *dx = (T *)tw.dx, *dx_mid = (T *)tw.dx_mid, *dh = (T *)tw.dh, *dpre = (T *)tw.dpre, *dao = (T *)tw.dao,
+    *dq = (T *)tw.dq;
+  for (int l = tw.layers - 1; l >= 0; --l) {
+    const RpoBlockWeights &bw = tw.blocks[l];
+    T *x_in = at<T>(tw.x_in, l * xs) + Mc * D, *x_mid = at<T>(tw.x_mid, l * xs) + Mc * D;
+    T *qkv = at<T>(tw.qkv, (long long)l * tw.Mc_max * 3 * D);
+    T *qp = at<T>(tw.qp, (long long)l * tw.Mp_max * D);
+    T *fcpre = at<T>(tw.fcpre, (long long)l * tw.Mp_max * 4 * D);
+    Epilogue<T> ep{};
+    // MLP: d gelu-input = (dx . W2) * quickgelu'(pre);  d ln2-out = that . W1
+    ep.gelu_grad_aux = fcpre;
+    RPO_TRY(gemm_dispatch<T>(backend, dx, D, (const T *)tw.proj_wT[l], D, dpre, 4 * D, Mp, 4 * D, D, ep, st));
+    ep = Epilogue<T>{};
+    RPO_TRY(gemm_dispatch<T>(backend, dpre, 4 * D, (const T *)tw.fc_wT[l], 4 * D, dh, D, Mp, D, 4 * D, ep, st));
+    RPO_TRY(layernorm_bwd<T>(dh, x_mid, bw.ln2_w, dx, dx_mid, Mp, D, st));
+    // attention: d attn-out = dx_mid . Wo ; dq ; d ln1-out = dq . Wq
+    RPO_TRY(gemm_dispatch<T>(backend, dx_mid, D, (const T *)tw.out_wT[l], D, dao, D, Mp, D, D, ep, st));
+    RPO_TRY(ro_attention_bwd<T>(qkv, qp, dao, dq, tw.ctx_off, tw.G, tw.K, tw.H, tw.max_ctx, st));
+    RPO_TRY(gemm_dispatch<T>(backend, dq, D, (const T *)tw.q_wT[l], D, dh, D, Mp, D, D, ep, st));
+    RPO_TRY(layernorm_bwd<T>(dh, x_in, bw.ln1_w, dx_mid, dx, Mp, D, st));
+  }
+  return RPO_OK;
+}
+
+template <typename T>
+static int forward_impl(RpoHandle *hd, const void *image, int image_dtype, int B, const void *text_prompt,
+                        const void *img_prompt, const int64_t *label, float *logits, float *loss, cudaStream_t st) {
+  const RpoConfig &c = hd->cfg;
+  Tower &v = hd->vis, &t = hd->txt;
+  const int K = c.K, C = c.n_cls, E = c.embed_dim, Dv = c.v_width, Dt = c.t_width, S = hd->S;
+  const int backend = c.gemm_backend;
+  g_launch_count = 0;
+  // ---- vision front end (trainers/rpo.py:198-206) ----
+  v.G = B;
+  v.Mc = (long long)B * S;
+  const long long Mp_v = (long long)B * K;
+  RPO_TRY(im2col_patches<T>(image, image_dtype, (T *)hd->patches, B, c.v_res, c.v_patch, hd->pk_pad, st));
+  Epilogue<T> ep{};
+  const int pk = hd->pk_pad;
+  RPO_TRY(gemm_dispatch<T>(backend, (const T *)hd->patches, pk, (const T *)hd->conv_w_eff, pk, (T *)hd->patch_emb, Dv,
+                           (long long)B * hd->NP, Dv, pk, ep, st));
+  T *x_raw = (T *)hd->x_raw;
+  RPO_TRY(vision_assemble_lnpre<T>((const T *)hd->patch_emb, hd->w.cls_emb, hd->w.v_pos, nullptr, nullptr,
+                                   (const T *)img_prompt, x_raw, x_raw + v.Mc * Dv, B, S, K, Dv, st));
+  RPO_TRY(layernorm_fwd<T>(x_raw, hd->w.ln_pre_w, hd->w.ln_pre_b, (T *)v.x_in, v.Mc + Mp_v, Dv, st));
+  RPO_TRY(tower_forward<T>(hd, v, true, true, st));
+  // img_f = ln_post(x[:, -K:, :]) @ proj                                 (:210)
+  T *xv_out = at<T>(v.x_in, (long long)v.layers * v.Mtot_max * Dv) + v.Mc * Dv;
+  RPO_TRY(layernorm_fwd<T>(xv_out, hd->w.ln_post_w, hd->w.ln_post_b, (T *)hd->hp_v, Mp_v, Dv, st));
+  RPO_TRY(gemm_dispatch<T>(backend, (const T *)hd->hp_v, Dv, (const T *)hd->v_projT, Dv, (T *)hd->img_feat, E, Mp_v, E,
+                           Dv, ep, st));
+  // ---- text tower, prompt rows only (context K/V cached by rpo_set_classes) (:173-191) ----
+  const long long Mp_t = (long long)C * K;
+  RPO_TRY(broadcast_rows<T>((const T *)text_prompt, (T *)t.x_in + t.Mc * Dt, C, K, Dt, st));
+  RPO_TRY(tower_forward<T>(hd, t, false, true, st));
+  T *xt_out = at<T>(t.x_in, (long long)t.layers * t.Mtot_max * Dt) + t.Mc * Dt;
+  RPO_TRY(layernorm_fwd<T>(xt_out, hd->w.ln_final_w, hd->w.ln_final_b, (T *)hd->hp_t, Mp_t, Dt, st));
+  RPO_TRY(gemm_dispatch<T>(backend, (const T *)hd->hp_t, Dt, (const T *)hd->t_projT, Dt, (T *)hd->text_feat, E, Mp_t,
+                           E, Dt, ep, st));
+  // ---- logits + CE (:215-230) ----
+  float *lg = logits ? logits : hd->logits_f;
+  RPO_TRY(logits_ce_fwd<T>((const T *)hd->img_feat, (const T *)hd->text_feat, hd->w.logit_scale, label, B, C, K, E,
+                           (T *)hd->img_n, (T *)hd->img_s, (T *)hd->text_n, hd->img_norm, hd->text_norm, (T *)hd->pair,
+                           lg, label ? (loss ? loss : hd->loss_f) : nullptr, hd->dlogits, st));
+  hd->B = B;
+  hd->fwd_has_grad = label != nullptr;
+  hd->img_prompt = img_prompt;
+  hd->launches_fwd = g_launch_count;
+  return RPO_OK;
+}
+
+template <typename T>
+static int backward_impl(RpoHandle *hd, float *grad_flat, cudaStream_t st) {
+  const RpoConfig &c = hd->cfg;
+  Tower &v = hd->vis, &t = hd->txt;
+  const int K = c.K, C = c.n_cls, E = c.embed_dim, Dv = c.v_width, Dt = c.t_width, B = hd->B;
+  const int backend = c.gemm_backend;
+  g_launch_count = 0;
+  RPO_TRY(logits_ce_bwd<T>(hd->dlogits, (const T *)hd->img_feat, (const T *)hd->text_feat, (const T *)hd->img_n,
+                           (const T *)hd->img_s, (const T *)hd->text_n, hd->img_norm, hd->text_norm, hd->w.logit_scale,
+                           B, C, K, E, (T *)hd->dl_t, (T *)hd->d_img_s, (T *)hd->d_text_n, (T *)hd->d_img_feat,
+                           (T *)hd->d_text_feat, st));
+  Epilogue<T> ep{};
+  // vision head: d ln_post-out = d img_feat . proj^T  (B operand = proj [Dv,E] itself, K-major in E)
+  const long long Mp_v = (long long)B * K, Mp_t = (long long)C * K;
+  RPO_TRY(gemm_dispatch<T>(backend, (const T *)hd->d_img_feat, E, (const T *)hd->w.v_proj, E, (T *)v.dh, Dv, Mp_v, Dv,
+                           E, ep, st));
+  T *xv_out = at<T>(v.x_in, (long long)v.layers * v.Mtot_max * Dv) + v.Mc * Dv;
+  RPO_TRY(layernorm_bwd<T>((const T *)v.dh, xv_out, hd->w.ln_post_w, nullptr, (T *)v.dx, Mp_v, Dv, st));
+  RPO_TRY(tower_backward<T>(hd, v, st));
+  // d img_prompt: sum over images, then through ln_pre (trainers/rpo.py:204-206)
+  RPO_TRY(reduce_groups_f32<T>((const T *)v.dx, hd->dsum_v, B, K, Dv, st));
+  RPO_TRY(lnpre_prompt_bwd<T>(hd->dsum_v, (const T *)hd->img_prompt, hd->w.ln_pre_w, grad_flat + (size_t)K * Dt, K, Dv,
+                              st));
+  // text head
+  RPO_TRY(gemm_dispatch<T>(backend, (const T *)hd->d_text_feat, E, (const T *)hd->w.t_proj, E, (T *)t.dh, Dt, Mp_t, Dt,
+                           E, ep, st));
+  T *xt_out = at<T>(t.x_in, (long long)t.layers * t.Mtot_max * Dt) + t.Mc * Dt;
+  RPO_TRY(layernorm_bwd<T>((const T *)t.dh, xt_out, hd->w.ln_final_w, nullptr, (T *)t.dx, Mp_t, Dt, st));
+  RPO_TRY(tower_backward<T>(hd, t, st));
+  // d text_prompt: the prompt is shared by all classes (trainers/rpo.py:176-177)
+  RPO_TRY(reduce_groups_f32<T>((const T *)t.dx, grad_flat, C, K, Dt, st));
+  hd->launches_bwd = g_launch_count;
+  return RPO_OK;
+}
+
+template <typename T>
+static int bind_impl(RpoHandle *hd, cudaStream_t st) {
+  auto make_T = [&](const void *src, int rows, int cols, char **dst) -> int {
+    void *p = nullptr;
+    RPO_CHECK_CUDA(cudaMalloc(&p, (size_t)rows * cols * sizeof(T)));
+    hd->owned.push_back(p);
+    hd->device_bytes += (size_t)rows * cols * sizeof(T);
+    *dst = (char *)p;
+    return transpose_2d<T>((const T *)src, (T *)p, rows, cols, st);
+  };
+  for (Tower *tw : {&hd->vis, &hd->txt}) {
+    const int D = tw->D;
+    tw->proj_wT.assign(tw->layers, nullptr);
+    tw->fc_wT.assign(tw->layers, nullptr);
+    tw->out_wT.assign(tw->layers, nullptr);
+    tw->q_wT.assign(tw->layers, nullptr);
+    for (int l = 0; l < tw->layers; ++l) {
+      const RpoBlockWeights &bw = tw->blocks[l];
+      RPO_TRY(make_T(bw.proj_w, D, 4 * D, &tw->proj_wT[l]));  // [D,4D] -> [4D,D]
+      RPO_TRY(make_T(bw.fc_w, 4 * D, D, &tw->fc_wT[l]));      // [4D,D] -> [D,4D]
+      RPO_TRY(make_T(bw.out_w, D, D, &tw->out_wT[l]));
+      RPO_TRY(make_T(bw.in_w, D, D, &tw->q_wT[l]));  // q third of in_proj
+    }
+  }
+  if (hd->pk_pad != hd->pk) {
+    void *p = nullptr;
+    size_t bytes = (size_t)hd->cfg.v_width * hd->pk_pad * sizeof(T);
+    RPO_CHECK_CUDA(cudaMalloc(&p, bytes));
+    hd->owned.push_back(p);
+    hd->device_bytes += bytes;
+    RPO_CHECK_CUDA(cudaMemsetAsync(p, 0, bytes, st));
+    RPO_CHECK_CUDA(cudaMemcpy2DAsync(p, (size_t)hd->pk_pad * sizeof(T), hd->w.conv_w, (size_t)hd->pk * sizeof(T),
+                                     (size_t)hd->pk * sizeof(T), hd->cfg.v_width, cudaMemcpyDeviceToDevice, st));
+    hd->conv_w_eff = p;
+  } else {
+    hd->conv_w_eff = hd->w.conv_w;
+  }
+  RPO_TRY(make_T(hd->w.v_proj, hd->cfg.v_width, hd->cfg.embed_dim, &hd->v_projT));
+  RPO_TRY(make_T(hd->w.t_proj, hd->cfg.t_width, hd->cfg.embed_dim, &hd->t_projT));
+  RPO_CHECK_CUDA(cudaStreamSynchronize(st));
+  return RPO_OK;
+}
+
+template <typename T>
+static int set_classes_impl(RpoHandle *hd, const void *text_x, cudaStream_t st) {
+  Tower &t = hd->txt;
+  RPO_TRY(text_gather_ctx<T>((const T *)text_x, t.ctx_off, hd->row_cls, hd->row_pos, (T *)t.x_in, t.Mc, hd->cfg.ctx_len,
+                             t.D, st));
+  RPO_TRY(tower_forward<T>(hd, t, true, false, st));
+  RPO_CHECK_CUDA(cudaStreamSynchronize(st));
+  return RPO_OK;
+}
+
+static int alloc_tower(RpoHandle *hd, Tower &tw, bool with_ctx_transients) {
+  (void)with_ctx_transients;
+  Arena &a = hd->arena;
+  const size_t e = hd->esz;
+  const long long D = tw.D, Mt = tw.Mtot_max, Mp = tw.Mp_max, Mc = tw.Mc_max;
+#define TAKE(field, bytes)                                         \
+  do {                                                             \
+    tw.field = (decltype(tw.field))a.take((size_t)(bytes));        \
+    if (!tw.field) {                                               \
+      set_error("internal: arena too small for " #field);          \
+      return RPO_ERR_STATE;                                        \
+    }                                                              \
+  } while (0)
+  TAKE(ctx_off, sizeof(int) * (tw.Gmax + 1));
+  TAKE(x_in, e * (tw.layers + 1) * Mt * D);
+  TAKE(qkv, e * tw.layers * Mc * 3 * D);
+  TAKE(qp, e * tw.layers * Mp * D);
+  TAKE(x_mid, e * tw.layers * Mt * D);
+  TAKE(fcpre, e * tw.layers * Mp * 4 * D);
+  TAKE(h, e * Mt * D);
+  TAKE(o, e * Mt * D);
+  TAKE(fc, e * Mt * 4 * D);
+  TAKE(dx, e * Mp * D);
+  TAKE(dx_mid, e * Mp * D);
+  TAKE(dh, e * Mp * D);
+  TAKE(dpre, e * Mp * 4 * D);
+  TAKE(dao, e * Mp * D);
+  TAKE(dq, e * Mp * D);
+#undef TAKE
+  return RPO_OK;
+}
+
+static size_t tower_bytes(const Tower &tw, size_t e) {
+  const long long D = tw.D, Mt = tw.Mtot_max, Mp = tw.Mp_max, Mc = tw.Mc_max;
+  size_t b = sizeof(int) * (tw.Gmax + 1);
+  b += e * ((size_t)(tw.layers + 1) * Mt * D + (size_t)tw.layers * Mc * 3 * D + (size_t)tw.layers * Mp * D +
+            (size_t)tw.layers * Mt * D + (size_t)tw.layers * Mp * 4 * D + 2 * (size_t)Mt * D + (size_t)Mt * 4 * D +
+            5 * (size_t)Mp * D + (size_t)Mp * 4 * D);
+  return b + 16 * 256;
+}
+
+}  // namespace rpo
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+const char *rpo_last_error(void) { return g_last_error.c_str(); }
+int rpo_version(void) { return 100; }
+
+int rpo_create(const RpoConfig *cfg, RpoHandle **out) {
+  RPO_REQUIRE(cfg && out, "null argument");
+  const RpoConfig &c = *cfg;
+  RPO_REQUIRE(c.dtype == RPO_F32 || c.dtype == RPO_F16 || c.dtype == RPO_BF16, "dtype");
+  RPO_REQUIRE(c.K >= 1, "K should be bigger than 0");  // trainers/rpo.py:47
+  RPO_REQUIRE(c.n_cls >= 1 && c.max_batch >= 1 && c.ctx_len >= 2, "n_cls / max_batch / ctx_len");
+  RPO_REQUIRE(c.v_width == c.v_heads * 64 && c.t_width == c.t_heads * 64, "head dim must be 64");
+  RPO_REQUIRE(c.v_width <= 1024 && c.t_width <= 1024, "tower width must be <= 1024");
+  RPO_REQUIRE(c.v_patch > 0 && c.v_res % c.v_patch == 0, "patch size must divide the resolution");
+  RPO_REQUIRE(c.embed_dim % 8 == 0 && c.v_width % 8 == 0 && c.t_width % 8 == 0, "widths must be multiples of 8");
+  RPO_REQUIRE(c.gemm_backend >= RPO_GEMM_AUTO && c.gemm_backend <= RPO_GEMM_TCGEN05, "gemm_backend");
+  RPO_REQUIRE(!(c.dtype == RPO_F32 && c.gemm_backend == RPO_GEMM_TCGEN05), "tcgen05 backend needs a 16-bit dtype");
+  const int grid = c.v_res / c.v_patch;
+  RPO_REQUIRE(grid * grid + 1 <= 320 && c.ctx_len <= 320, "at most 320 context rows per group");
+  RpoHandle *h = new RpoHandle();
+  h->cfg = c;
+  h->esz = dtype_size(c.dtype);
+  h->NP = grid * grid;
+  h->S = h->NP + 1;
+  h->pk = 3 * c.v_patch * c.v_patch;
+  // K extent of the patch GEMM padded to the tcgen05 K tile (ViT-L/14: 588 -> 640, zero filled)
+  h->pk_pad = (c.dtype == RPO_F32) ? h->pk : (h->pk + 63) / 64 * 64;
+  Tower &v = h->vis, &t = h->txt;
+  v.D = c.v_width; v.H = c.v_heads; v.layers = c.v_layers; v.K = c.K; v.causal = 0;
+  v.Gmax = c.max_batch; v.max_ctx = h->S;
+  v.Mc_max = (long long)c.max_batch * h->S; v.Mp_max = (long long)c.max_batch * c.K; v.Mtot_max = v.Mc_max + v.Mp_max;
+  t.D = c.t_width; t.H = c.t_heads; t.layers = c.t_layers; t.K = c.K; t.causal = 1;
+  t.Gmax = c.n_cls; t.G = c.n_cls; t.max_ctx = c.ctx_len;
+  t.Mc_max = (long long)c.n_cls * (c.ctx_len - c.K > 0 ? c.ctx_len - c.K : 1);
+  t.Mp_max = (long long)c.n_cls * c.K; t.Mtot_max = t.Mc_max + t.Mp_max;
+
+  const size_t e = h->esz;
+  const long long Bm = c.max_batch, K = c.K, C = c.n_cls, E = c.embed_dim;
+  const long long pk = h->pk_pad;
+  size_t total = tower_bytes(v, e) + tower_bytes(t, e);
+  total += e * (Bm * h->NP * pk + Bm * h->NP * v.D + v.Mtot_max * v.D);                 // patches, patch_emb, x_raw
+  total += e * (v.Mp_max * v.D + t.Mp_max * t.D + Bm * K * E + C * K * E);              // hp_v, hp_t, feats
+  total += e * (2 * Bm * K * E + C * K * E + K * Bm * C + Bm * C);                      // img_n, img_s, text_n, pair, dl_t
+  total += e * (2 * Bm * K * E + 2 * C * K * E);                                        // d_img_s, d_img_feat, d_text_n, d_text_feat
+  total += sizeof(float) * (Bm * K + Bm + C * K + 2 * Bm * C + 1 + K * v.D);
+  total += sizeof(int) * 2 * t.Mc_max;
+  total += 64 * 256;
+  void *base = nullptr;
+  cudaError_t err = cudaMalloc(&base, total);
+  if (err != cudaSuccess) {
+    set_error(std::string("cudaMalloc of the workspace failed: ") + cudaGetErrorString(err));
+    delete h;
+    return RPO_ERR_CUDA;
+  }
+  h->arena.base = (char *)base;
+  h->arena.cap = total;
+  h->device_bytes = total;
+  int s = alloc_tower(h, v, true);
+  if (s == RPO_OK) s = alloc_tower(h, t, true);
+  Arena &a = h->arena;
+  bool ok = s == RPO_OK;
+#define TAKE(field, bytes)                                   \
+  do {                                                       \
+    h->field = (decltype(h->field))a.take((size_t)(bytes));  \
+    ok = ok && h->field != nullptr;                          \
+  } while (0)
+  TAKE(patches, e * Bm * h->NP * pk);
+  TAKE(patch_emb, e * Bm * h->NP * v.D);
+  TAKE(x_raw, e * v.Mtot_max * v.D);
+  TAKE(hp_v, e * v.Mp_max * v.D);
+  TAKE(hp_t, e * t.Mp_max * t.D);
+  TAKE(img_feat, e * Bm * K * E);
+  TAKE(text_feat, e * C * K * E);
+  TAKE(img_n, e * Bm * K * E);
+  TAKE(img_s, e * Bm * K * E);
+  TAKE(text_n, e * C * K * E);
+  TAKE(pair, e * K * Bm * C);
+  TAKE(dl_t, e * Bm * C);
+  TAKE(d_img_s, e * Bm * K * E);
+  TAKE(d_img_feat, e * Bm * K * E);
+  TAKE(d_text_n, e * C * K * E);
+  TAKE(d_text_feat, e * C * K * E);
+  TAKE(img_norm, sizeof(float) * (Bm * K + Bm));
+  TAKE(text_norm, sizeof(float) * C * K);
+  TAKE(logits_f, sizeof(float) * Bm * C);
+  TAKE(dlogits, sizeof(float) * Bm * C);
+  TAKE(loss_f, sizeof(float));
+  TAKE(dsum_v, sizeof(float) * K * v.D);
+  TAKE(row_cls, sizeof(int) * t.Mc_max);
+  TAKE(row_pos, sizeof(int) * t.Mc_max);
+#undef TAKE
+  if (!ok) {
+    if (s == RPO_OK) set_error("internal: arena too small");
+    cudaFree(base);
+    delete h;
+    return RPO_ERR_STATE;
+  }
+  // vision context offsets are static: image b owns rows [b*S, (b+1)*S)
+  std::vector<int> off(c.max_batch + 1);
+  for (int b = 0; b <= c.max_batch; ++b) off[b] = b * h->S;
+  err = cudaMemcpy(v.ctx_off, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) {
+    set_error(std::string("cudaMemcpy failed: ") + cudaGetErrorString(err));
+    cudaFree(base);
+    delete h;
+    return RPO_ERR_CUDA;
+  }
+  *out = h;
+  return RPO_OK;
+}
+
+void rpo_destroy(RpoHandle *h) {
+  if (!h) return;
+  for (void *p : h->owned) cudaFree(p);
+  if (h->arena.base) cudaFree(h->arena.base);
+  delete h;
+}
+
+size_t rpo_device_bytes(const RpoHandle *h) { return h ? h->device_bytes : 0; }
+
+int rpo_bind_weights(RpoHandle *h, const RpoWeights *w, void *stream) {
+  RPO_REQUIRE(h && w, "null argument");
+  RPO_REQUIRE(!h->bound, "weights are already bound");
+  RPO_REQUIRE(w->v_blocks && w->t_blocks && w->conv_w && w->cls_emb && w->v_pos && w->ln_pre_w && w->ln_pre_b &&
+                  w->ln_post_w && w->ln_post_b && w->v_proj && w->ln_final_w && w->ln_final_b && w->t_proj &&
+                  w->logit_scale,
+              "null weight pointer");
+  h->w = *w;
+  h->vis.blocks.assign(w->v_blocks, w->v_blocks + h->cfg.v_layers);
+  h->txt.blocks.assign(w->t_blocks, w->t_blocks + h->cfg.t_layers);
+  for (Tower *tw : {&h->vis, &h->txt})
+    for (const RpoBlockWeights &b : tw->blocks)
+      RPO_REQUIRE(b.ln1_w && b.ln1_b && b.ln2_w && b.ln2_b && b.in_w && b.in_b && b.out_w && b.out_b && b.fc_w &&
+                      b.fc_b && b.proj_w && b.proj_b,
+                  "null block weight pointer");
+  h->w.v_blocks = nullptr;
+  h->w.t_blocks = nullptr;
+  cudaStream_t st = (cudaStream_t)stream;
+  int s;
+  switch (h->cfg.dtype) {
+    case RPO_F32: s = bind_impl<float>(h, st); break;
+    case RPO_F16: s = bind_impl<__half>(h, st); break;
+    default: s = bind_impl<__nv_bfloat16>(h, st); break;
+  }
+  if (s == RPO_OK) h->bound = true;
+  return s;
+}
+
+int rpo_set_classes(RpoHandle *h, const void *text_x, const int32_t *len_prompts, void *stream) {
+  RPO_REQUIRE(h && text_x && len_prompts, "null argument");
+  RPO_REQUIRE(h->bound, "rpo_bind_weights must be called first");
+  const RpoConfig &c = h->cfg;
+  Tower &t = h->txt;
+  std::vector<int> off(c.n_cls + 1, 0), rc, rp;
+  int mx = 0;
+  for (int i = 0; i < c.n_cls; ++i) {
+    int n = len_prompts[i];
+    // the reference indexes position len_prompts+K-1 of a 77-token sequence (trainers/rpo.py:177)
+    RPO_REQUIRE(n >= 1 && n + c.K <= c.ctx_len, "len_prompts[c] + K must fit in the context length");
+    off[i + 1] = off[i] + n;
+    mx = n > mx ? n : mx;
+    for (int j = 0; j < n; ++j) {
+      rc.push_back(i);
+      rp.push_back(j);
+    }
+  }
+  t.Mc = off[c.n_cls];
+  t.max_ctx = mx;
+  t.G = c.n_cls;
+  RPO_REQUIRE(t.Mc <= t.Mc_max, "internal: context rows exceed the workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  RPO_CHECK_CUDA(cudaMemcpyAsync(t.ctx_off, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice, st));
+  RPO_CHECK_CUDA(cudaMemcpyAsync(h->row_cls, rc.data(), sizeof(int) * rc.size(), cudaMemcpyHostToDevice, st));
+  RPO_CHECK_CUDA(cudaMemcpyAsync(h->row_pos, rp.data(), sizeof(int) * rp.size(), cudaMemcpyHostToDevice, st));
+  RPO_CHECK_CUDA(cudaStreamSynchronize(st));  // host vectors go out of scope
+  int s;
+  switch (c.dtype) {
+    case RPO_F32: s = set_classes_impl<float>(h, text_x, st); break;
+    case RPO_F16: s = set_classes_impl<__half>(h, text_x, st); break;
+    default: s = set_classes_impl<__nv_bfloat16>(h, text_x, st); break;
+  }
+  if (s == RPO_OK) h->classes_set = true;
+  return s;
+}
+
+int rpo_forward(RpoHandle *h, const void *image, int32_t image_dtype, int32_t B, const void *text_prompt,
+                const void *img_prompt, const int64_t *label, float *logits, float *loss, void *stream) {
+  RPO_REQUIRE(h && image && text_prompt && img_prompt, "null argument");
+  RPO_REQUIRE(h->bound && h->classes_set, "rpo_bind_weights and rpo_set_classes must be called first");
+  RPO_REQUIRE(B >= 1 && B <= h->cfg.max_batch, "batch size exceeds max_batch");
+  RPO_REQUIRE(!loss || label, "loss requires labels");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (h->cfg.dtype) {
+    case RPO_F32: return forward_impl<float>(h, image, image_dtype, B, text_prompt, img_prompt, label, logits, loss, st);
+    case RPO_F16: return forward_impl<__half>(h, image, image_dtype, B, text_prompt, img_prompt, label, logits, loss, st);
+    default: return forward_impl<__nv_bfloat16>(h, image, image_dtype, B, text_prompt, img_prompt, label, logits, loss, st);
+  }
+}
+
+int rpo_backward(RpoHandle *h, float *grad_flat, void *stream) {
+  RPO_REQUIRE(h && grad_flat, "null argument");
+  RPO_REQUIRE(h->fwd_has_grad, "rpo_backward must follow an rpo_forward that was given labels");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (h->cfg.dtype) {
+    case RPO_F32: return backward_impl<float>(h, grad_flat, st);
+    case RPO_F16: return backward_impl<__half>(h, grad_flat, st);
+    default: return backward_impl<__nv_bfloat16>(h, grad_flat, st);
+  }
+}
+
+int64_t rpo_launch_count(const RpoHandle *h) { return h ? h->launches_fwd + h->launches_bwd : 0; }
+
+int rpo_sgd_step(void *param, int32_t dtype, const float *grad, float *momentum_buf, int64_t n, const float *lr,
+                 float momentum, float weight_decay, float grad_scale, const int32_t *first_step, void *stream) {
+  RPO_REQUIRE(param && grad && lr, "null argument");
+  RPO_REQUIRE(momentum == 0.f || momentum_buf, "momentum needs a buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case RPO_F32: return sgd_step<float>((float *)param, grad, momentum_buf, n, lr, momentum, weight_decay, grad_scale, first_step, st);
+    case RPO_F16: return sgd_step<__half>((__half *)param, grad, momentum_buf, n, lr, momentum, weight_decay, grad_scale, first_step, st);
+    case RPO_BF16: return sgd_step<__nv_bfloat16>((__nv_bfloat16 *)param, grad, momentum_buf, n, lr, momentum, weight_decay, grad_scale, first_step, st);
+  }
+  set_error("invalid dtype");
+  return RPO_ERR_INVALID;
+}
+
+int64_t rpo_debug_fetch(RpoHandle *h, int32_t which, int32_t layer, void *dst, int64_t cap, void *stream) {
+  if (!h || !dst) return -1;
+  const RpoConfig &c = h->cfg;
+  const char *src = nullptr;
+  int64_t n = 0;
+  if (which == 0 || which == 1) {
+    Tower &tw = which == 0 ? h->vis : h->txt;
+    if (layer < -1 || layer >= tw.layers) return -1;
+    src = tw.x_in + (size_t)(layer + 1) * tw.Mtot_max * tw.D * h->esz;
+    n = (tw.Mc + (int64_t)tw.G * tw.K) * tw.D;
+  } else if (which == 2) {
+    src = h->img_feat;
+    n = (int64_t)h->B * c.K * c.embed_dim;
+  } else if (which == 3) {
+    src = h->text_feat;
+    n = (int64_t)c.n_cls * c.K * c.embed_dim;
+  } else {
+    return -1;
+  }
+  int64_t m = n < cap ? n : cap;
+  if (cudaMemcpyAsync(dst, src, (size_t)m * h->esz, cudaMemcpyDeviceToDevice, (cudaStream_t)stream) != cudaSuccess)
+    return -1;
+  return n;
+}
+
+// ---- unit kernels --------------------------------------------------------------------------------
+#define DISPATCH(dtype, CALL)                                \
+  switch (dtype) {                                           \
+    case RPO_F32: { using T = float; return CALL; }          \
+    case RPO_F16: { using T = __half; return CALL; }         \
+    case RPO_BF16: { using T = __nv_bfloat16; return CALL; } \
+    default: set_error("invalid dtype"); return RPO_ERR_INVALID; \
+  }
+
+int rpo_layernorm_fwd(const void *x, const float *w, const float *b, void *y, int64_t rows, int32_t D, int32_t dtype,
+                      void *stream) {
+  RPO_REQUIRE(x && w && b && y, "null argument");
+  DISPATCH(dtype, (layernorm_fwd<T>((const T *)x, w, b, (T *)y, rows, D, (cudaStream_t)stream)));
+}
+
+int rpo_layernorm_bwd(const void *dy, const void *x, const float *w, const void *dres, void *dx, int64_t rows,
+                      int32_t D, int32_t dtype, void *stream) {
+  RPO_REQUIRE(dy && x && w && dx, "null argument");
+  DISPATCH(dtype, (layernorm_bwd<T>((const T *)dy, (const T *)x, w, (const T *)dres, (T *)dx, rows, D,
+                                    (cudaStream_t)stream)));
+}
+
+int rpo_gemm_bias_act(const void *A, int64_t lda, const void *B, int64_t ldb, void *C, int64_t ldc, int64_t M,
+                      int32_t N, int32_t Kd, const void *bias, int32_t act, const void *residual,
+                      const void *gelu_grad_aux, void *aux_out, int64_t aux_row0, int32_t dtype, int32_t backend,
+                      void *stream) {
+  RPO_REQUIRE(A && B && C, "null argument");
+  RPO_REQUIRE(backend >= RPO_GEMM_AUTO && backend <= RPO_GEMM_TCGEN05, "backend");
+  DISPATCH(dtype, ([&]() -> int {
+             Epilogue<T> ep{};
+             ep.bias = (const T *)bias;
+             ep.residual = (const T *)residual;
+             ep.gelu_grad_aux = (const T *)gelu_grad_aux;
+             ep.aux_out = (T *)aux_out;
+             ep.aux_row0 = aux_row0;
+             ep.act = act;
+             return gemm_dispatch<T>(backend, (const T *)A, lda, (const T *)B, ldb, (T *)C, ldc, M, N, Kd, ep,
+                                     (cudaStream_t)stream);
+           }()));
+}
+
+int rpo_ro_attention_fwd(const void *qkv_ctx, const void *q_prompt, void *out_ctx, void *out_prompt,
+                         const int32_t *ctx_off, int32_t G, int32_t K, int32_t H, int32_t max_ctx, int32_t causal,
+                         int32_t do_ctx, int32_t dtype, void *stream) {
+  RPO_REQUIRE(qkv_ctx && ctx_off, "null argument");
+  RPO_REQUIRE(K == 0 || (q_prompt && out_prompt), "prompt buffers");
+  RPO_REQUIRE(!do_ctx || out_ctx, "context output buffer");
+  DISPATCH(dtype, (ro_attention_fwd<T>((const T *)qkv_ctx, (const T *)q_prompt, (T *)out_ctx, (T *)out_prompt, ctx_off,
+                                       G, K, H, max_ctx, causal, do_ctx, (cudaStream_t)stream)));
+}
+
+int rpo_ro_attention_bwd(const void *qkv_ctx, const void *q_prompt, const void *d_out_prompt, void *dq_prompt,
+                         const int32_t *ctx_off, int32_t G, int32_t K, int32_t H, int32_t max_ctx, int32_t dtype,
+                         void *stream) {
+  RPO_REQUIRE(qkv_ctx && q_prompt && d_out_prompt && dq_prompt && ctx_off, "null argument");
+  DISPATCH(dtype, (ro_attention_bwd<T>((const T *)qkv_ctx, (const T *)q_prompt, (const T *)d_out_prompt,
+                                       (T *)dq_prompt, ctx_off, G, K, H, max_ctx, (cudaStream_t)stream)));
+}
+
+int rpo_logits_ce_fwd(const void *img_feat, const void *text_feat, const float *logit_scale, const int64_t *label,
+                      int32_t B, int32_t C, int32_t K, int32_t E, void *img_n, void *img_s, void *text_n,
+                      float *img_rnorm, float *text_rnorm, void *pair_logits, float *logits, float *loss,
+                      float *dlogits, int32_t dtype, void *stream) {
+  RPO_REQUIRE(img_feat && text_feat && logit_scale && img_n && img_s && text_n && img_rnorm && text_rnorm &&
+                  pair_logits,
+              "null argument");
+  DISPATCH(dtype, (logits_ce_fwd<T>((const T *)img_feat, (const T *)text_feat, logit_scale, label, B, C, K, E,
+                                    (T *)img_n, (T *)img_s, (T *)text_n, img_rnorm, text_rnorm, (T *)pair_logits,
+                                    logits, loss, dlogits, (cudaStream_t)stream)));
+}
+
+int rpo_logits_ce_bwd(const float *dlogits, const void *img_feat, const void *text_feat, const void *img_n,
+                      const void *img_s, const void *text_n, const float *img_rnorm, const float *text_rnorm,
+                      const float *logit_scale, int32_t B, int32_t C, int32_t K, int32_t E, void *dl_t, void *d_img_s,
+                      void *d_text_n, void *d_img_feat, void *d_text_feat, int32_t dtype, void *stream) {
+  RPO_REQUIRE(dlogits && img_n && img_s && text_n && img_rnorm && text_rnorm && logit_scale && dl_t && d_img_s &&
+                  d_text_n && d_img_feat && d_text_feat,
+              "null argument");
+  DISPATCH(dtype, (logits_ce_bwd<T>(dlogits, (const T *)img_feat, (const T *)text_feat, (const T *)img_n,
+                                    (const T *)img_s, (const T *)text_n, img_rnorm, text_rnorm, logit_scale, B, C, K,
+                                    E, (T *)dl_t, (T *)d_img_s, (T *)d_text_n, (T *)d_img_feat, (T *)d_text_feat,
+                                    (cudaStream_t)stream)));
+}
+
+}  // extern "C"

