@@ -1,0 +1,92 @@
+"""One training step of the RPO hot path as the reference trainer performs it
+(trainers/rpo.py:290-316: forward, zero_grad, backward, optimizer step) but enqueued as one CUDA
+graph: forward + CE + prompt-gradient backward (librpo_b200), an NCCL all-reduce of the flat
+[K*Dt + K*Dv] f32 gradient when data-parallel, and the fused SGD update of the two prompt tensors.
+
+Used by bench.py and by rpo_b200.trainer.RPO.forward_backward.  Host code is plumbing only.
+"""
+import torch
+
+from . import _lib
+
+
+class StepRunner:
+    def __init__(self, model, batch, lr=0.01, momentum=0.9, weight_decay=5e-4, use_graph=True, process_group=None,
+                 world_size=1):
+        self.model = model
+        self.B = int(batch)
+        self.device = model.w_mm.device
+        self.world = int(world_size)
+        self.pg = process_group
+        self.momentum, self.wd = float(momentum), float(weight_decay)
+        self.eng = model.engine(self.B)
+        res = model.arch.v_res
+        self.image = torch.zeros(self.B, 3, res, res, dtype=torch.float32, device=self.device)
+        self.label = torch.zeros(self.B, dtype=torch.int64, device=self.device)
+        self.lr = torch.tensor(float(lr), dtype=torch.float32, device=self.device)
+        self.first = torch.ones(1, dtype=torch.int32, device=self.device)
+        n = self.eng.grad_flat.numel()
+        self.mom_buf = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.graph = None
+        self.use_graph = use_graph
+        self.launches_per_step = 0
+
+    # -- enqueue helpers (no host sync) ----------------------------------------------------------
+    def _fwd_bwd(self):
+        pl = self.model.prompt_learner
+        self.eng.forward(self.image, pl.text_prompt.data, pl.img_prompt.data, self.label)
+        self.eng.backward()
+
+    def _update(self):
+        eng, pl, lib = self.eng, self.model.prompt_learner, self.eng.lib
+        g = eng.grad_flat
+        if self.world > 1:
+            torch.distributed.all_reduce(g, group=self.pg)  # sum; the mean is folded into grad_scale
+        st = _lib.stream_ptr(self.device)
+        code = _lib.dtype_code(self.model.dtype)
+        scale = 1.0 / self.world
+        nt = eng.n_text
+        _lib.check(lib.rpo_sgd_step(pl.text_prompt.data.data_ptr(), code, g.data_ptr(), self.mom_buf.data_ptr(), nt,
+                                    self.lr.data_ptr(), self.momentum, self.wd, scale, self.first.data_ptr(), st))
+        _lib.check(lib.rpo_sgd_step(pl.img_prompt.data.data_ptr(), code, g.data_ptr() + 4 * nt,
+                                    self.mom_buf.data_ptr() + 4 * nt, g.numel() - nt, self.lr.data_ptr(), self.momentum,
+                                    self.wd, scale, self.first.data_ptr(), st))
+        self.first.zero_()
+
+    def _enqueue(self):
+        self._fwd_bwd()
+        self._update()
+
+    def prepare(self, warmup=3):
+        """Warm-up (sets kernel attributes, loads modules) and CUDA-graph capture of the step."""
+        with torch.cuda.device(self.device):
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(max(1, warmup)):
+                    self._enqueue()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self.launches_per_step = self.eng.launch_count() + 2  # + two SGD kernels
+            if self.use_graph:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    if self.world > 1:
+                        self._fwd_bwd()
+                    else:
+                        self._enqueue()
+                self.graph = g
+        return self
+
+    def step(self):
+        """Enqueues one step on the current stream.  Inputs are whatever self.image / self.label hold."""
+        if self.graph is not None:
+            self.graph.replay()
+            if self.world > 1:
+                self._update()
+        else:
+            self._enqueue()
+
+    @property
+    def loss(self):
+        return self.eng.loss

@@ -20,9 +20,23 @@ from tests.common import GOLDEN_CASES, class_tokens, load_golden, rel_err, state
 pytestmark = pytest.mark.gpu
 
 TOL = {"fp32": 1e-5, "fp16": 1e-3, "bf16": 1e-2}
-# gradients travel through ~25 more 16-bit tensors than the loss; the reference's own fp16 gradient
-# differs from its fp32 gradient by ~1e-2 relative, so the fp16 bar for gradients is 5e-3 of max
-GRAD_TOL = {"fp32": 2e-5, "fp16": 5e-3, "bf16": 5e-2}
+# Gradients.  fp32: 3e-5 of the max magnitude (measured against an fp64 evaluation both this path and
+# torch's fp32 sit ~2e-6 from the truth; the CPU golden itself carries ~1e-5).  16-bit: the
+# reference's OWN fp16 gradients differ from its fp32 gradients by 0.7e-2 .. 2.4e-2 of max (compare
+# tests/golden/*_fp16.npz with *_fp32.npz), so the bar is "as close to the fp32 reference as the
+# reference's own 16-bit run": err(ours_16, ref_32) <= 2 * err(ref_16, ref_32) + 2e-3, plus a loose
+# direct bound against the 16-bit reference.
+GRAD_TOL = {"fp32": 3e-5, "fp16": 6e-2, "bf16": 2.5e-1}
+
+
+def check_grads(prec, ours, ref_same_prec, ref_fp32, what):
+    direct = rel_err(ours, ref_same_prec)
+    assert direct <= GRAD_TOL[prec], f"{what}: {direct:.3e} vs the {prec} reference"
+    if prec != "fp32":
+        floor = rel_err(ref_same_prec, ref_fp32)
+        mine = rel_err(ours, ref_fp32)
+        assert mine <= 2.0 * floor + 2e-3, f"{what}: {mine:.3e} from the fp32 reference; the reference's own " \
+                                           f"{prec} run is {floor:.3e} away"
 
 
 def make_cfg(K, res):
@@ -79,7 +93,7 @@ def test_matches_reference_golden(name):
     label = synth.make_labels(B, tokens.shape[0]).cuda()
     loss, gt, gi = step(model, image, label)
     logits = eval_logits(model, image)
-    tol, gtol = TOL[prec], GRAD_TOL[prec]
+    tol = TOL[prec]
     scale = float(np.exp(2.6592600369327783))  # logits are exp(logit_scale) * cosine
     print(f"{name}: dloss={abs(loss.item() - float(g['loss'])):.3e} "
           f"dlogits={(logits - torch.from_numpy(g['logits'])).abs().max().item():.3e} "
@@ -87,8 +101,9 @@ def test_matches_reference_golden(name):
           f"gi={rel_err(gi, torch.from_numpy(g['grad_img_prompt'])):.3e}")
     assert abs(loss.item() - float(g["loss"])) <= tol * max(1.0, abs(float(g["loss"])))
     assert (logits - torch.from_numpy(g["logits"])).abs().max().item() <= tol * scale
-    assert rel_err(gt, torch.from_numpy(g["grad_text_prompt"])) <= gtol
-    assert rel_err(gi, torch.from_numpy(g["grad_img_prompt"])) <= gtol
+    g32 = load_golden(name.replace("fp16", "fp32"))
+    check_grads(prec, gt, torch.from_numpy(g["grad_text_prompt"]), torch.from_numpy(g32["grad_text_prompt"]), "text")
+    check_grads(prec, gi, torch.from_numpy(g["grad_img_prompt"]), torch.from_numpy(g32["grad_img_prompt"]), "image")
     # residual-stream rows after every block (forward hooks in the reference)
     eng = model._engine
     S = arch.n_patch + 1
@@ -142,15 +157,19 @@ def test_matches_oracle(arch_name, prec, K, class_ids, B, backend):
     ipd = model.prompt_learner.img_prompt.detach()
     oloss, ogt, ogi = om.step(image, tpd, ipd, label)
     ologits = om.logits(image, tpd, ipd)
-    tol, gtol = TOL[prec], GRAD_TOL[prec]
+    tol = TOL[prec]
     scale = float(np.exp(2.6592600369327783))
     print(f"{arch_name}/{prec}: dloss={abs(loss.item() - oloss.item()):.3e} "
           f"dlogits={(logits - ologits.cpu()).abs().max().item():.3e} gt={rel_err(gt, ogt):.3e} "
           f"gi={rel_err(gi, ogi):.3e}")
     assert abs(loss.item() - oloss.item()) <= tol * max(1.0, abs(oloss.item()))
     assert (logits - ologits.cpu()).abs().max().item() <= tol * scale
-    assert rel_err(gt, ogt) <= gtol
-    assert rel_err(gi, ogi) <= gtol
+    ogt32, ogi32 = ogt, ogi
+    if prec != "fp32":
+        om32 = OracleModel(convert_state_dict(sd, "fp32"), tokens, K, "fp32", device="cuda:0")
+        _, ogt32, ogi32 = om32.step(image, tpd.float(), ipd.float(), label)
+    check_grads(prec, gt, ogt, ogt32, "text")
+    check_grads(prec, gi, ogi, ogi32, "image")
 
 
 def test_config2_full_size_properties():
@@ -178,7 +197,10 @@ def test_config2_full_size_properties():
           f"gt={rel_err(gt, ogt):.3e} gi={rel_err(gi, ogi):.3e}")
     assert abs(loss.item() - oloss.item()) <= 1e-3 * max(1.0, abs(oloss.item()))
     assert (logits - ologits).abs().max().item() <= 1e-3 * scale
-    assert rel_err(gt, ogt) <= GRAD_TOL["fp16"] and rel_err(gi, ogi) <= GRAD_TOL["fp16"]
+    om32 = OracleModel(convert_state_dict(sd, "fp32"), tokens, K, "fp32", device="cuda:0")
+    _, ogt32, ogi32 = om32.step(image, tpd.float(), ipd.float(), label)
+    check_grads("fp16", gt, ogt, ogt32, "text")
+    check_grads("fp16", gi, ogi, ogi32, "image")
     # permutation of the batch permutes the logits rows, bit-exactly
     perm = torch.randperm(B, generator=torch.Generator().manual_seed(0))
     logits_p = eval_logits(model, image[perm.cuda()])
@@ -199,5 +221,6 @@ def test_errors_are_loud():
         model(torch.zeros(1, 3, 32, 32, device="cuda:0"), torch.zeros(1, dtype=torch.int64, device="cuda:0"))
     with pytest.raises(IndexError):  # prompt + K does not fit in 77 tokens (trainers/rpo.py:177)
         long_tokens = tokens.clone()
+        long_tokens[0, 1:76] = 320  # push the EOT token (the argmax) to the last position
         long_tokens[0, 76] = 49407
         build_model("tiny", "fp16", 4, long_tokens)
