@@ -150,8 +150,10 @@ int rpo_ro_attention_fwd(const void *qkv_ctx, const void *q_prompt, void *out_ct
                          const int32_t *ctx_off, int32_t G, int32_t K, int32_t H, int32_t max_ctx, int32_t causal,
                          int32_t do_ctx, int32_t dtype, void *stream);
 /* gradient w.r.t. the prompt queries only (keys/values come from rows that carry no gradient):
- * dq_prompt [G*K, D] from d_out_prompt [G*K, D]. */
-int rpo_ro_attention_bwd(const void *qkv_ctx, const void *q_prompt, const void *d_out_prompt, void *dq_prompt,
+ * dq_prompt [G*K, D] from d_out_prompt [G*K, D]; out_prompt is the forward output of the same rows
+ * (used for the softmax-gradient row term sum_d dO*O). */
+int rpo_ro_attention_bwd(const void *qkv_ctx, const void *q_prompt, const void *out_prompt, const void *d_out_prompt,
+                         void *dq_prompt,
                          const int32_t *ctx_off, int32_t G, int32_t K, int32_t H, int32_t max_ctx, int32_t dtype,
                          void *stream);
 

@@ -74,7 +74,7 @@ def load():
     lib.rpo_layernorm_bwd.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, vp]
     lib.rpo_gemm_bias_act.argtypes = [vp, i64, vp, i64, vp, i64, i64, i32, i32, vp, i32, vp, vp, vp, i64, i32, i32, vp]
     lib.rpo_ro_attention_fwd.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
-    lib.rpo_ro_attention_bwd.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.rpo_ro_attention_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.rpo_logits_ce_fwd.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]
     lib.rpo_logits_ce_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp,
                                       i32, vp]

@@ -10,6 +10,8 @@
 // This file holds the exact-f32 SIMT kernels (one warp per query row, keys/values of one
 // (group, head) staged in shared memory).  They serve RPO_F32, where tensor cores (tf32) would
 // break the 1e-5 parity bar, and are the cross-check for the tensor-core path in attention_mma.cu.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace rpo {
@@ -217,8 +219,8 @@ int ro_attention_fwd_simt(const T *qkv_ctx, const T *q_prompt, T *out_ctx, T *ou
 }
 
 template <typename T>
-int ro_attention_bwd(const T *qkv_ctx, const T *q_prompt, const T *d_out, T *dq, const int *ctx_off, int G, int K,
-                     int H, int max_ctx, cudaStream_t st) {
+int ro_attention_bwd_simt(const T *qkv_ctx, const T *q_prompt, const T *d_out, T *dq, const int *ctx_off, int G, int K,
+                          int H, int max_ctx, cudaStream_t st) {
   RPO_REQUIRE(max_ctx >= 1 && max_ctx <= MAX_KT * 32, "at most 320 context rows per group");
   RPO_REQUIRE(G <= 65535, "grid limits");
   if (G == 0) return RPO_OK;
@@ -234,18 +236,47 @@ int ro_attention_bwd(const T *qkv_ctx, const T *q_prompt, const T *d_out, T *dq,
   return RPO_OK;
 }
 
+// tensor-core kernels (attention_mma.cu), 16-bit dtypes only
+template <typename T>
+int ro_attention_fwd_mma(const T *qkv_ctx, const T *q_prompt, T *out_ctx, T *out_prompt, const int *ctx_off, int G,
+                         int K, int H, int max_ctx, int causal, int do_ctx, cudaStream_t st);
+template <typename T>
+int ro_attention_bwd_mma(const T *qkv_ctx, const T *q_prompt, const T *o_prompt, const T *d_out, T *dq,
+                         const int *ctx_off, int G, int K, int H, int max_ctx, cudaStream_t st);
+
+// RPO_ATTN_SIMT=1 forces the exact-f32 SIMT kernels for every dtype (tests cross-check the two paths)
+static bool force_simt() {
+  const char *e = getenv("RPO_ATTN_SIMT");
+  return e && e[0] == '1';
+}
+
 template <typename T>
 int ro_attention_fwd(const T *qkv_ctx, const T *q_prompt, T *out_ctx, T *out_prompt, const int *ctx_off, int G, int K,
                      int H, int max_ctx, int causal, int do_ctx, cudaStream_t st) {
+  if constexpr (sizeof(T) == 2) {
+    if (max_ctx <= 288 && !force_simt())
+      return ro_attention_fwd_mma<T>(qkv_ctx, q_prompt, out_ctx, out_prompt, ctx_off, G, K, H, max_ctx, causal, do_ctx,
+                                     st);
+  }
   return ro_attention_fwd_simt<T>(qkv_ctx, q_prompt, out_ctx, out_prompt, ctx_off, G, K, H, max_ctx, causal, do_ctx,
                                   st);
+}
+
+template <typename T>
+int ro_attention_bwd(const T *qkv_ctx, const T *q_prompt, const T *o_prompt, const T *d_out, T *dq, const int *ctx_off,
+                     int G, int K, int H, int max_ctx, cudaStream_t st) {
+  if constexpr (sizeof(T) == 2) {
+    if (max_ctx <= 288 && !force_simt())
+      return ro_attention_bwd_mma<T>(qkv_ctx, q_prompt, o_prompt, d_out, dq, ctx_off, G, K, H, max_ctx, st);
+  }
+  return ro_attention_bwd_simt<T>(qkv_ctx, q_prompt, d_out, dq, ctx_off, G, K, H, max_ctx, st);
 }
 
 #define INSTANTIATE(T)                                                                                           \
   template int ro_attention_fwd<T>(const T *, const T *, T *, T *, const int *, int, int, int, int, int, int,    \
                                    cudaStream_t);                                                                \
-  template int ro_attention_bwd<T>(const T *, const T *, const T *, T *, const int *, int, int, int, int,        \
-                                   cudaStream_t);
+  template int ro_attention_bwd<T>(const T *, const T *, const T *, const T *, T *, const int *, int, int, int,  \
+                                   int, cudaStream_t);
 INSTANTIATE(float)
 INSTANTIATE(__half)
 INSTANTIATE(__nv_bfloat16)

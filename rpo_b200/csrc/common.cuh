@@ -182,8 +182,8 @@ template <typename T>
 int ro_attention_fwd(const T *qkv_ctx, const T *q_prompt, T *out_ctx, T *out_prompt, const int *ctx_off, int G, int K,
                      int H, int max_ctx, int causal, int do_ctx, cudaStream_t st);
 template <typename T>
-int ro_attention_bwd(const T *qkv_ctx, const T *q_prompt, const T *d_out, T *dq, const int *ctx_off, int G, int K,
-                     int H, int max_ctx, cudaStream_t st);
+int ro_attention_bwd(const T *qkv_ctx, const T *q_prompt, const T *o_prompt, const T *d_out, T *dq, const int *ctx_off,
+                     int G, int K, int H, int max_ctx, cudaStream_t st);
 
 template <typename T>
 int logits_ce_fwd(const T *img_feat, const T *text_feat, const float *logit_scale, const int64_t *label, int B, int C,

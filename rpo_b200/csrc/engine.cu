@@ -8,8 +8,9 @@
 // range, the prompt-only passes (text tower per step, the whole backward) are a pointer offset, and
 // the read-only mask (trainers/rpo.py:140-159) is never materialised: it is the split itself.
 //
-// Per block l the handle keeps x_in[l] (block input), qkv[l] (context q|k|v), qp[l] (prompt q),
-// x_mid[l] (after the attention residual) and fcpre[l] (MLP pre-activation of the prompt rows);
+// Per block l the handle keeps x_in[l] (block input), qkv[l] (context q|k|v), qp[l] (prompt q), o[l]
+// (attention output), x_mid[l] (after the attention residual) and fcpre[l] (MLP pre-activation of the
+// prompt rows);
 // that is everything the prompt-row backward needs, so nothing is recomputed.
 #include <vector>
 
@@ -99,7 +100,7 @@ static int tower_forward(RpoHandle *hd, Tower &tw, bool do_ctx, bool do_prompt, 
   for (int l = 0; l < tw.layers; ++l) {
     const RpoBlockWeights &bw = tw.blocks[l];
     T *x_in = at<T>(tw.x_in, l * xs), *x_out = at<T>(tw.x_in, (l + 1) * xs), *x_mid = at<T>(tw.x_mid, l * xs);
-    T *h = (T *)tw.h, *o = (T *)tw.o, *fc = (T *)tw.fc;
+    T *h = (T *)tw.h, *o = at<T>(tw.o, l * xs), *fc = (T *)tw.fc;
     T *qkv = at<T>(tw.qkv, (long long)l * tw.Mc_max * 3 * D);
     T *qp = at<T>(tw.qp, (long long)l * tw.Mp_max * D);
     T *fcpre = at<T>(tw.fcpre, (long long)l * tw.Mp_max * 4 * D);
@@ -168,7 +169,8 @@ static int tower_backward(RpoHandle *hd, Tower &tw, cudaStream_t st) {
     RPO_TRY(layernorm_bwd<T>(dh, x_mid, bw.ln2_w, dx, dx_mid, Mp, D, st));
     // attention: d attn-out = dx_mid . Wo ; dq ; d ln1-out = dq . Wq
     RPO_TRY(gemm_dispatch<T>(backend, dx_mid, D, (const T *)tw.out_wT[l], D, dao, D, Mp, D, D, ep, st));
-    RPO_TRY(ro_attention_bwd<T>(qkv, qp, dao, dq, tw.ctx_off, tw.G, tw.K, tw.H, tw.max_ctx, st));
+    RPO_TRY(ro_attention_bwd<T>(qkv, qp, at<T>(tw.o, l * xs) + Mc * D, dao, dq, tw.ctx_off, tw.G, tw.K, tw.H,
+                                tw.max_ctx, st));
     RPO_TRY(gemm_dispatch<T>(backend, dq, D, (const T *)tw.q_wT[l], D, dh, D, Mp, D, D, ep, st));
     RPO_TRY(layernorm_bwd<T>(dh, x_in, bw.ln1_w, dx_mid, dx, Mp, D, st));
   }
@@ -330,7 +332,7 @@ static int alloc_tower(RpoHandle *hd, Tower &tw, bool with_ctx_transients) {
   TAKE(x_mid, e * tw.layers * Mt * D);
   TAKE(fcpre, e * tw.layers * Mp * 4 * D);
   TAKE(h, e * Mt * D);
-  TAKE(o, e * Mt * D);
+  TAKE(o, e * tw.layers * Mt * D);
   TAKE(fc, e * Mt * 4 * D);
   TAKE(dx, e * Mp * D);
   TAKE(dx_mid, e * Mp * D);
@@ -346,7 +348,8 @@ static size_t tower_bytes(const Tower &tw, size_t e) {
   const long long D = tw.D, Mt = tw.Mtot_max, Mp = tw.Mp_max, Mc = tw.Mc_max;
   size_t b = sizeof(int) * (tw.Gmax + 1);
   b += e * ((size_t)(tw.layers + 1) * Mt * D + (size_t)tw.layers * Mc * 3 * D + (size_t)tw.layers * Mp * D +
-            (size_t)tw.layers * Mt * D + (size_t)tw.layers * Mp * 4 * D + 2 * (size_t)Mt * D + (size_t)Mt * 4 * D +
+            (size_t)tw.layers * Mt * D + (size_t)tw.layers * Mp * 4 * D + (size_t)(tw.layers + 1) * Mt * D +
+            (size_t)Mt * 4 * D +
             5 * (size_t)Mp * D + (size_t)Mp * 4 * D);
   return b + 16 * 256;
 }
@@ -658,12 +661,13 @@ int rpo_ro_attention_fwd(const void *qkv_ctx, const void *q_prompt, void *out_ct
                                        G, K, H, max_ctx, causal, do_ctx, (cudaStream_t)stream)));
 }
 
-int rpo_ro_attention_bwd(const void *qkv_ctx, const void *q_prompt, const void *d_out_prompt, void *dq_prompt,
-                         const int32_t *ctx_off, int32_t G, int32_t K, int32_t H, int32_t max_ctx, int32_t dtype,
-                         void *stream) {
-  RPO_REQUIRE(qkv_ctx && q_prompt && d_out_prompt && dq_prompt && ctx_off, "null argument");
-  DISPATCH(dtype, (ro_attention_bwd<T>((const T *)qkv_ctx, (const T *)q_prompt, (const T *)d_out_prompt,
-                                       (T *)dq_prompt, ctx_off, G, K, H, max_ctx, (cudaStream_t)stream)));
+int rpo_ro_attention_bwd(const void *qkv_ctx, const void *q_prompt, const void *out_prompt, const void *d_out_prompt,
+                         void *dq_prompt, const int32_t *ctx_off, int32_t G, int32_t K, int32_t H, int32_t max_ctx,
+                         int32_t dtype, void *stream) {
+  RPO_REQUIRE(qkv_ctx && q_prompt && out_prompt && d_out_prompt && dq_prompt && ctx_off, "null argument");
+  DISPATCH(dtype, (ro_attention_bwd<T>((const T *)qkv_ctx, (const T *)q_prompt, (const T *)out_prompt,
+                                       (const T *)d_out_prompt, (T *)dq_prompt, ctx_off, G, K, H, max_ctx,
+                                       (cudaStream_t)stream)));
 }
 
 int rpo_logits_ce_fwd(const void *img_feat, const void *text_feat, const float *logit_scale, const int64_t *label,

@@ -231,7 +231,7 @@ def test_ro_attention_fwd_bwd(prec, case):
     # backward: dq of the prompt queries vs autograd through the fp32 reference
     d_out = randn(G * K, D, dtype=dt, seed=42)
     dq = torch.zeros_like(qp)
-    _lib.check(lib.rpo_ro_attention_bwd(qkv.data_ptr(), qp.data_ptr(), d_out.data_ptr(), dq.data_ptr(),
+    _lib.check(lib.rpo_ro_attention_bwd(qkv.data_ptr(), qp.data_ptr(), out_p.data_ptr(), d_out.data_ptr(), dq.data_ptr(),
                                         off_d.data_ptr(), G, K, H, max(lens), code, st()))
     qpr = qp.cpu().float().requires_grad_(True)
     _, rp2 = ref_attention(qkv.cpu(), qpr, off, K, H, causal, True)
