@@ -322,6 +322,10 @@ __global__ void __launch_bounds__(THREADS)
 #pragma unroll
     for (int kd = 0; kd < 4; ++kd) ldsm_x4(dOs + swz(row, kd * 2 + (m >> 1)), df[kd][0], df[kd][1], df[kd][2], df[kd][3]);
   }
+  // dS is handed to the tensor core in the 16-bit dtype; for fp16 it is pre-scaled by 2^8 (exact) so
+  // that products of small probabilities and small gradients stay out of the subnormal range
+  constexpr float kDs = Num<T>::dtype == RPO_F16 ? 32.0f : 0.125f;
+  constexpr float kUn = Num<T>::dtype == RPO_F16 ? 1.0f / 256.0f : 1.0f;
   float gq[8][4];
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) gq[nt][0] = gq[nt][1] = gq[nt][2] = gq[nt][3] = 0.f;
@@ -338,12 +342,12 @@ __global__ void __launch_bounds__(THREADS)
         mma16816<T>(dp1, df[kd], b2, b3);
       }
       uint32_t a[4];
-      a[0] = pack2<T>(acc[2 * kk][0] * (dp0[0] - delta_a) * 0.125f, acc[2 * kk][1] * (dp0[1] - delta_a) * 0.125f);
-      a[1] = pack2<T>(acc[2 * kk][2] * (dp0[2] - delta_b) * 0.125f, acc[2 * kk][3] * (dp0[3] - delta_b) * 0.125f);
-      a[2] = pack2<T>(acc[2 * kk + 1][0] * (dp1[0] - delta_a) * 0.125f,
-                      acc[2 * kk + 1][1] * (dp1[1] - delta_a) * 0.125f);
-      a[3] = pack2<T>(acc[2 * kk + 1][2] * (dp1[2] - delta_b) * 0.125f,
-                      acc[2 * kk + 1][3] * (dp1[3] - delta_b) * 0.125f);
+      a[0] = pack2<T>(acc[2 * kk][0] * (dp0[0] - delta_a) * kDs, acc[2 * kk][1] * (dp0[1] - delta_a) * kDs);
+      a[1] = pack2<T>(acc[2 * kk][2] * (dp0[2] - delta_b) * kDs, acc[2 * kk][3] * (dp0[3] - delta_b) * kDs);
+      a[2] = pack2<T>(acc[2 * kk + 1][0] * (dp1[0] - delta_a) * kDs,
+                      acc[2 * kk + 1][1] * (dp1[1] - delta_a) * kDs);
+      a[3] = pack2<T>(acc[2 * kk + 1][2] * (dp1[2] - delta_b) * kDs,
+                      acc[2 * kk + 1][3] * (dp1[3] - delta_b) * kDs);
       const int keyk = kk * 16 + (m & 1) * 8 + (lane & 7);
 #pragma unroll
       for (int dp = 0; dp < 4; ++dp) {
@@ -353,6 +357,13 @@ __global__ void __launch_bounds__(THREADS)
         mma16816<T>(gq[dp * 2 + 1], a, b2, b3);
       }
     }
+  }
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    gq[nt][0] *= kUn;
+    gq[nt][1] *= kUn;
+    gq[nt][2] *= kUn;
+    gq[nt][3] *= kUn;
   }
   __syncwarp();
   store_tile<T>(Qs, Qs_gen, r_base, gq, lane, [&](int r) -> T * {

@@ -193,7 +193,7 @@ template <typename T>
 int logits_ce_bwd(const float *dlogits, const T *img_feat, const T *text_feat, const T *img_n, const T *img_s,
                   const T *text_n, const float *img_rnorm, const float *text_rnorm, const float *logit_scale, int B,
                   int C, int K, int E, T *dl_t, T *d_img_s, T *d_text_n, T *d_img_feat, T *d_text_feat,
-                  cudaStream_t st);
+                  float grad_scale, cudaStream_t st);
 
 // embedding / glue kernels (elementwise.cu)
 template <typename T>
@@ -207,7 +207,7 @@ int text_gather_ctx(const T *text_x, const int *ctx_off, const int *row_cls, con
 template <typename T>
 int broadcast_rows(const T *src, T *dst, int G, int K, int D, cudaStream_t st);
 template <typename T>
-int reduce_groups_f32(const T *src, float *dst, int G, int K, int D, cudaStream_t st);
+int reduce_groups_f32(const T *src, float *dst, int G, int K, int D, float scale, cudaStream_t st);
 template <typename T>
 int lnpre_prompt_bwd(const float *dsum, const T *img_prompt, const float *w, float *grad, int K, int D,
                      cudaStream_t st);

@@ -279,22 +279,22 @@ int broadcast_rows(const T *src, T *dst, int G, int K, int D, cudaStream_t st) {
 // grid.y splits the groups; partial sums are combined with atomics into a zeroed dst.
 template <typename T>
 __global__ void reduce_groups_kernel(const T *__restrict__ src, float *__restrict__ dst, int G, int K, int D,
-                                     int g_per_block) {
+                                     int g_per_block, float scale) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= K * D) return;
   int g0 = blockIdx.y * g_per_block;
   int g1 = min(G, g0 + g_per_block);
   float acc = 0.f;
   for (int g = g0; g < g1; ++g) acc += tof<T>(src[(size_t)g * K * D + idx]);
-  atomicAdd(dst + idx, acc);
+  atomicAdd(dst + idx, acc * scale);
 }
 template <typename T>
-int reduce_groups_f32(const T *src, float *dst, int G, int K, int D, cudaStream_t st) {
+int reduce_groups_f32(const T *src, float *dst, int G, int K, int D, float scale, cudaStream_t st) {
   RPO_CHECK_CUDA(cudaMemsetAsync(dst, 0, sizeof(float) * K * D, st));
   if (G == 0) return RPO_OK;
   int g_per_block = 16;
   dim3 grid((K * D + 255) / 256, (G + g_per_block - 1) / g_per_block);
-  reduce_groups_kernel<T><<<grid, 256, 0, st>>>(src, dst, G, K, D, g_per_block);
+  reduce_groups_kernel<T><<<grid, 256, 0, st>>>(src, dst, G, K, D, g_per_block, scale);
   RPO_LAUNCH_CHECK();
   return RPO_OK;
 }
@@ -400,7 +400,7 @@ int sgd_step(T *p, const float *g, float *buf, long long n, const float *lr, flo
   template int text_gather_ctx<T>(const T *, const int *, const int *, const int *, T *, long long, int, int,       \
                                   cudaStream_t);                                                                    \
   template int broadcast_rows<T>(const T *, T *, int, int, int, cudaStream_t);                                      \
-  template int reduce_groups_f32<T>(const T *, float *, int, int, int, cudaStream_t);                               \
+  template int reduce_groups_f32<T>(const T *, float *, int, int, int, float, cudaStream_t);                            \
   template int lnpre_prompt_bwd<T>(const float *, const T *, const float *, float *, int, int, cudaStream_t);       \
   template int transpose_2d<T>(const T *, T *, int, int, cudaStream_t);                                             \
   template int sgd_step<T>(T *, const float *, float *, long long, const float *, float, float, float, const int *, \

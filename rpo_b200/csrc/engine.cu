@@ -231,10 +231,13 @@ static int backward_impl(RpoHandle *hd, float *grad_flat, cudaStream_t st) {
   const int K = c.K, C = c.n_cls, E = c.embed_dim, Dv = c.v_width, Dt = c.t_width, B = hd->B;
   const int backend = c.gemm_backend;
   g_launch_count = 0;
+  // fp16 gradients of this path sit around 1e-5 .. 1e-3, i.e. in the subnormal range of the format: the
+  // backward runs on gradients scaled by 2^12 (exact) and the f32 reduction at the end divides it out
+  const float gs = (c.dtype == RPO_F16) ? 4096.0f : 1.0f;
   RPO_TRY(logits_ce_bwd<T>(hd->dlogits, (const T *)hd->img_feat, (const T *)hd->text_feat, (const T *)hd->img_n,
                            (const T *)hd->img_s, (const T *)hd->text_n, hd->img_norm, hd->text_norm, hd->w.logit_scale,
                            B, C, K, E, (T *)hd->dl_t, (T *)hd->d_img_s, (T *)hd->d_text_n, (T *)hd->d_img_feat,
-                           (T *)hd->d_text_feat, st));
+                           (T *)hd->d_text_feat, gs, st));
   Epilogue<T> ep{};
   // vision head: d ln_post-out = d img_feat . proj^T  (B operand = proj [Dv,E] itself, K-major in E)
   const long long Mp_v = (long long)B * K, Mp_t = (long long)C * K;
@@ -244,7 +247,7 @@ static int backward_impl(RpoHandle *hd, float *grad_flat, cudaStream_t st) {
   RPO_TRY(layernorm_bwd<T>((const T *)v.dh, xv_out, hd->w.ln_post_w, nullptr, (T *)v.dx, Mp_v, Dv, st));
   RPO_TRY(tower_backward<T>(hd, v, st));
   // d img_prompt: sum over images, then through ln_pre (trainers/rpo.py:204-206)
-  RPO_TRY(reduce_groups_f32<T>((const T *)v.dx, hd->dsum_v, B, K, Dv, st));
+  RPO_TRY(reduce_groups_f32<T>((const T *)v.dx, hd->dsum_v, B, K, Dv, 1.0f / gs, st));
   RPO_TRY(lnpre_prompt_bwd<T>(hd->dsum_v, (const T *)hd->img_prompt, hd->w.ln_pre_w, grad_flat + (size_t)K * Dt, K, Dv,
                               st));
   // text head
@@ -254,7 +257,7 @@ static int backward_impl(RpoHandle *hd, float *grad_flat, cudaStream_t st) {
   RPO_TRY(layernorm_bwd<T>((const T *)t.dh, xt_out, hd->w.ln_final_w, nullptr, (T *)t.dx, Mp_t, Dt, st));
   RPO_TRY(tower_backward<T>(hd, t, st));
   // d text_prompt: the prompt is shared by all classes (trainers/rpo.py:176-177)
-  RPO_TRY(reduce_groups_f32<T>((const T *)t.dx, grad_flat, C, K, Dt, st));
+  RPO_TRY(reduce_groups_f32<T>((const T *)t.dx, grad_flat, C, K, Dt, 1.0f / gs, st));
   hd->launches_bwd = g_launch_count;
   return RPO_OK;
 }
@@ -691,7 +694,7 @@ int rpo_logits_ce_bwd(const float *dlogits, const void *img_feat, const void *te
               "null argument");
   DISPATCH(dtype, (logits_ce_bwd<T>(dlogits, (const T *)img_feat, (const T *)text_feat, (const T *)img_n,
                                     (const T *)img_s, (const T *)text_n, img_rnorm, text_rnorm, logit_scale, B, C, K,
-                                    E, (T *)dl_t, (T *)d_img_s, (T *)d_text_n, (T *)d_img_feat, (T *)d_text_feat,
+                                    E, (T *)dl_t, (T *)d_img_s, (T *)d_text_n, (T *)d_img_feat, (T *)d_text_feat, 1.0f,
                                     (cudaStream_t)stream)));
 }
 

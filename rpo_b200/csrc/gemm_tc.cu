@@ -2,16 +2,21 @@
 // projections and their input-gradient counterparts):
 //     C[M,N] = epilogue( A[M,Kd] . B[N,Kd]^T )        A, B K-major (row-major, K contiguous)
 //
-// Blackwell-native structure (one 128 x BN output tile per CTA, 2 CTAs resident per SM so one
-// CTA's epilogue overlaps the other's main loop):
-//   warp 0      : TMA producer  -- cp.async.bulk.tensor 2D tiles (128B swizzle) into a 3-4 stage
-//                 shared-memory ring, completion on mbarriers (expect_tx)
-//   warp 1      : MMA issuer    -- one elected thread issues tcgen05.mma.cta_group::1.kind::f16
-//                 (M=128, N=BN, K=16) with the f32 accumulator in TMEM; tcgen05.commit releases
-//                 ring slots and finally signals the epilogue
-//   warps 2..5  : epilogue      -- tcgen05.ld (32 lanes x 32 columns per warp), fused bias /
-//                 QuickGELU / gelu-grad / residual, 16-byte stores
-// M tails are handled by TMA out-of-bounds zero fill on load and row predicates on store.
+// Persistent, warp-specialised Blackwell kernel: one CTA per SM loops over 128 x BN output tiles.
+//   warp 0      : TMA producer  -- cp.async.bulk.tensor 2D tiles (128B swizzle) into a STAGES-deep
+//                 shared-memory ring, completion on mbarriers (expect_tx); runs ahead across tiles
+//   warp 1      : MMA issuer    -- one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN,
+//                 K=16) into one of TWO TMEM accumulators; tcgen05.commit frees ring slots and
+//                 signals "accumulator full"
+//   warps 2..9  : epilogue      -- 8 warps (two per TMEM lane quarter, each owning half of the
+//                 columns) drain accumulator t%2 with tcgen05.ld while the MMA warp already fills
+//                 the other one: bias add in f32, ONE rounding to the dtype (the nn.Linear output
+//                 tensor), QuickGELU in packed 16-bit arithmetic (HMUL2 / tanh.approx.x2 / HFMA2,
+//                 4 instructions per 2 elements -- with K = 768 the epilogue would otherwise cost as
+//                 many issue slots as the main loop), stage the tile in swizzled shared memory,
+//                 then write it out with fully coalesced 16-byte stores, adding the residual rows
+//                 (also read coalesced) on the way.
+// M tails: TMA zero-fills out-of-bounds rows on load, stores are row-predicated.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -23,17 +28,22 @@ namespace tc {
 static constexpr int BM = 128;
 static constexpr int BK = 64;  // 64 x 2 B = 128 B = one swizzle row
 static constexpr int UMMA_K = 16;
-static constexpr int THREADS = 192;
+static constexpr int EPI_WARPS = 8;
+static constexpr int THREADS = 64 + EPI_WARPS * 32;  // producer warp + MMA warp + epilogue warps
 
 template <int BN>
 struct Cfg {
-  static constexpr int STAGES = (BN >= 128) ? 3 : 4;
+  static constexpr int STAGES = BN >= 128 ? 5 : (BN == 64 ? 6 : 8);
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int CSTAGE_BYTES = BM * BN * 2;  // output tile staging (16-bit)
+  static constexpr int BIAS_BYTES = BN * 4;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + CSTAGE_BYTES + BIAS_BYTES + BAR_BYTES + 1024;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulators
+  static_assert(STAGE_BYTES % 1024 == 0, "stages must stay 1024-byte aligned");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -43,6 +53,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -105,6 +118,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
 
 // K-major operand tile in shared memory, 128-byte swizzle, rows of 128 B, 8-row groups 1024 B apart
 // (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
@@ -125,28 +139,72 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt16, int M, int N) {
          ((uint32_t)(M >> 4) << 24);
 }
 
+// ---- packed 16-bit epilogue arithmetic --------------------------------------------------------
+template <typename T>
+struct Pk;
+template <>
+struct Pk<__half> {
+  using T2 = __half2;
+  static __device__ __forceinline__ T2 from_floats(float a, float b) { return __floats2half2_rn(a, b); }
+  static __device__ __forceinline__ T2 splat(float v) { return __float2half2_rn(v); }
+  static __device__ __forceinline__ T2 tanh2(T2 x) {
+    uint32_t r, xi = *reinterpret_cast<uint32_t *>(&x);
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(r) : "r"(xi));
+    return *reinterpret_cast<T2 *>(&r);
+  }
+};
+template <>
+struct Pk<__nv_bfloat16> {
+  using T2 = __nv_bfloat162;
+  static __device__ __forceinline__ T2 from_floats(float a, float b) { return __floats2bfloat162_rn(a, b); }
+  static __device__ __forceinline__ T2 splat(float v) { return __float2bfloat162_rn(v); }
+  static __device__ __forceinline__ T2 tanh2(T2 x) {
+    uint32_t r, xi = *reinterpret_cast<uint32_t *>(&x);
+    asm("tanh.approx.bf16x2 %0, %1;" : "=r"(r) : "r"(xi));
+    return *reinterpret_cast<T2 *>(&r);
+  }
+};
+// QuickGELU x * sigmoid(1.702 x) on two packed values: sigmoid(t) = 0.5 * tanh(t/2) + 0.5
+template <typename T>
+__device__ __forceinline__ typename Pk<T>::T2 quickgelu2(typename Pk<T>::T2 x) {
+  using P = Pk<T>;
+  typename P::T2 th = P::tanh2(__hmul2(x, P::splat(0.851f)));
+  typename P::T2 s = __hfma2(th, P::splat(0.5f), P::splat(0.5f));
+  return __hmul2(x, s);
+}
+
+// byte offset of 16-byte chunk c of row r in the swizzled [BM][BN] 16-bit staging tile
+template <int BN>
+__device__ __forceinline__ uint32_t cst_off(int r, int c) {
+  constexpr int CH = BN / 8;  // chunks per row
+  return (uint32_t)(r * (BN * 2) + ((c ^ (r & (CH - 1) & 7)) << 4));
+}
+
 template <typename T, int BN>
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(THREADS, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                   T *__restrict__ C, long long ldc, long long M, int N, int Kd, Epilogue<T> ep) {
+                   T *__restrict__ C, long long ldc, long long M, int N, int Kd, Epilogue<T> ep, int num_n_tiles,
+                   int num_tiles) {
   using C_ = Cfg<BN>;
+  using T2 = typename Pk<T>::T2;
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles need 1024-byte alignment
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C_::STAGES * C_::STAGE_BYTES);
-  // bars[0..S) full, bars[S..2S) empty, bars[2S] accumulator-ready; then the TMEM base address slot
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * C_::STAGES + 1);
+  uint8_t *cstage = smem + C_::STAGES * C_::STAGE_BYTES;
+  float *bias_s = reinterpret_cast<float *>(cstage + C_::CSTAGE_BYTES);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(cstage + C_::CSTAGE_BYTES + C_::BIAS_BYTES);
+  // bars: [0,S) full, [S,2S) empty, [2S,2S+2) accumulator full, [2S+2,2S+4) accumulator empty
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * C_::STAGES + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const long long m0 = (long long)blockIdx.y * BM;
-  const int n0 = blockIdx.x * BN;
   const int num_kb = Kd / BK;
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C_::STAGES + s); };
-  const uint32_t accum_bar = bar_base + 8u * (2 * C_::STAGES);
+  auto acc_full = [&](int a) { return bar_base + 8u * (2 * C_::STAGES + a); };
+  auto acc_empty = [&](int a) { return bar_base + 8u * (2 * C_::STAGES + 2 + a); };
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
@@ -155,7 +213,10 @@ __global__ void __launch_bounds__(THREADS, 2)
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(acc_full(a), 1);
+      mbar_init(acc_empty(a), EPI_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -166,71 +227,123 @@ __global__ void __launch_bounds__(THREADS, 2)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
+    // ===== TMA producer =====
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        int s = kb % C_::STAGES;
-        uint32_t ph = (kb / C_::STAGES) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1);  // fresh barrier: parity-1 wait passes immediately
-        mbar_arrive_expect_tx(full_bar(s), C_::STAGE_BYTES);
-        uint32_t a_dst = smem_base + s * C_::STAGE_BYTES;
-        tma_load_2d(a_dst, &map_a, full_bar(s), kb * BK, (int)m0);
-        tma_load_2d(a_dst + C_::A_BYTES, &map_b, full_bar(s), kb * BK, n0);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / num_n_tiles) * BM, n0 = (tile % num_n_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % C_::STAGES;
+          const uint32_t ph = (it / C_::STAGES) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);  // fresh barrier: parity-1 wait passes immediately
+          mbar_arrive_expect_tx(full_bar(s), C_::STAGE_BYTES);
+          const uint32_t a_dst = smem_base + s * C_::STAGE_BYTES;
+          tma_load_2d(a_dst, &map_a, full_bar(s), kb * BK, m0);
+          tma_load_2d(a_dst + C_::A_BYTES, &map_b, full_bar(s), kb * BK, n0);
+        }
       }
     }
   } else if (warp == 1) {
+    // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(Num<T>::dtype == RPO_BF16 ? 1 : 0, BM, BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        int s = kb % C_::STAGES;
-        uint32_t ph = (kb / C_::STAGES) & 1;
-        mbar_wait(full_bar(s), ph);
+      uint32_t it = 0, t = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+        const int a = t & 1;
+        mbar_wait(acc_empty(a), ((t >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
-        uint32_t a_addr = smem_base + s * C_::STAGE_BYTES;
-        uint64_t adesc = make_smem_desc(a_addr);
-        uint64_t bdesc = make_smem_desc(a_addr + C_::A_BYTES);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(a * BN);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % C_::STAGES;
+          const uint32_t ph = (it / C_::STAGES) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + s * C_::STAGE_BYTES;
+          const uint64_t adesc = make_smem_desc(a_addr);
+          const uint64_t bdesc = make_smem_desc(a_addr + C_::A_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // advance 16 elements = 32 bytes along K inside the swizzle row: +2 in 16-byte units
-          umma_f16(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 elements = 32 bytes along K inside the swizzle row: +2 in 16-byte units
+            umma_f16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(empty_bar(s));  // frees the ring slot once these MMAs have read it
         }
-        umma_commit(empty_bar(s));  // frees the ring slot once these MMAs have read it
+        umma_commit(acc_full(a));  // accumulator complete
       }
-      umma_commit(accum_bar);  // accumulator complete
     }
   } else {
-    // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+    // ===== epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
     const int q = warp & 3;
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-    const long long m = m0 + q * 32 + lane;
-    const bool row_ok = m < M;
-    constexpr int VEC = 8;  // 16-bit elements per 16-byte vector
+    const int half_id = (warp - 2) >> 2;       // which half of the tile's columns
+    const int etid = threadIdx.x - 64;         // 0..255
+    constexpr int HALVES = BN >= 64 ? 2 : 1;   // BN = 32: one 32-column tcgen05.ld covers the tile
+    constexpr int COLS_PER_WARP = BN / HALVES;
+    constexpr int CH = BN / 8;                 // 16-byte chunks per staged row
+    constexpr int ROWS_PER_PASS = (EPI_WARPS * 32) / CH;
+    const int r_loc = q * 32 + lane;           // this thread's accumulator row inside the tile
+    uint32_t t = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      const int a = t & 1;
+      const long long m0 = (long long)(tile / num_n_tiles) * BM;
+      const int n0 = (tile % num_n_tiles) * BN;
+      if (etid < BN) bias_s[etid] = ep.bias ? tof<T>(ep.bias[n0 + etid]) : 0.f;
+      mbar_wait(acc_full(a), (t >> 1) & 1);
+      tc_fence_after();
+      epi_bar_sync();  // staging tile free (previous copy-out done) and bias visible
+      const long long m = m0 + r_loc;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t acc[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
-      if (row_ok) {
+      for (int cc = 0; cc < (half_id < HALVES ? COLS_PER_WARP : 0); cc += 32) {
+        const int c0 = half_id * COLS_PER_WARP + cc;
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c0), acc);
 #pragma unroll
-        for (int g = 0; g < 32 / VEC; ++g) {
-          const int n = n0 + c0 + g * VEC;
-          const long long off = m * ldc + n;
-          Vec16<T> res, aux, out, pre, bias;
-          if (ep.bias) bias = ld16(ep.bias + n);
-          if (ep.residual) res = ld16(ep.residual + off);
-          if (ep.gelu_grad_aux) aux = ld16(ep.gelu_grad_aux + off);
+        for (int g = 0; g < 4; ++g) {
+          const int cl = c0 + g * 8;  // tile-local column of this 16-byte group
+          __align__(16) T2 h[4];
 #pragma unroll
-          for (int e = 0; e < VEC; ++e) {
-            float v = __uint_as_float(acc[g * VEC + e]);
-            if (ep.bias) v += tof<T>(bias.v[e]);
-            v = rnd<T>(v);
-            pre.v[e] = fromf<T>(v);
-            if (ep.act == RPO_ACT_QUICKGELU) v = rnd<T>(quickgelu_rounded<T>(v));
-            if (ep.gelu_grad_aux) v = rnd<T>(v * quickgelu_grad(tof<T>(aux.v[e])));
-            if (ep.residual) v += tof<T>(res.v[e]);
-            out.v[e] = fromf<T>(v);
+          for (int e = 0; e < 4; ++e) {
+            const float2 b2 = *reinterpret_cast<const float2 *>(bias_s + cl + 2 * e);
+            h[e] = Pk<T>::from_floats(__uint_as_float(acc[g * 8 + 2 * e]) + b2.x,
+                                      __uint_as_float(acc[g * 8 + 2 * e + 1]) + b2.y);
           }
-          if (ep.aux_out && m >= ep.aux_row0) st16(ep.aux_out + (m - ep.aux_row0) * ldc + n, pre);
-          st16(C + off, out);
+          if (ep.aux_out && m >= ep.aux_row0 && m < M)
+            *reinterpret_cast<uint4 *>(ep.aux_out + (m - ep.aux_row0) * ldc + n0 + cl) = *reinterpret_cast<uint4 *>(h);
+          if (ep.act == RPO_ACT_QUICKGELU) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h[e] = quickgelu2<T>(h[e]);
+          }
+          if (ep.gelu_grad_aux && m < M) {  // backward only (small M): f32 math
+            Vec16<T> aux = ld16(ep.gelu_grad_aux + m * ldc + n0 + cl);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float2 v = make_float2(tof<T>(reinterpret_cast<T *>(&h[e])[0]), tof<T>(reinterpret_cast<T *>(&h[e])[1]));
+              h[e] = Pk<T>::from_floats(v.x * quickgelu_grad(tof<T>(aux.v[2 * e])),
+                                        v.y * quickgelu_grad(tof<T>(aux.v[2 * e + 1])));
+            }
+          }
+          *reinterpret_cast<uint4 *>(cstage + cst_off<BN>(r_loc, cl >> 3)) = *reinterpret_cast<uint4 *>(h);
+        }
+      }
+      // accumulator drained: hand it back to the MMA warp before the copy-out
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(a));
+      epi_bar_sync();  // whole tile staged
+      // coalesced copy-out (+ residual): 16 bytes per thread, ROWS_PER_PASS full rows per pass
+#pragma unroll 1
+      for (int r0 = 0; r0 < BM; r0 += ROWS_PER_PASS) {
+        const int r = r0 + etid / CH, c = etid % CH;
+        const long long mm = m0 + r;
+        if (mm < M) {
+          uint4 v = *reinterpret_cast<const uint4 *>(cstage + cst_off<BN>(r, c));
+          const long long off = mm * ldc + n0 + c * 8;
+          if (ep.residual) {
+            uint4 rv = *reinterpret_cast<const uint4 *>(ep.residual + off);
+            T2 *pv = reinterpret_cast<T2 *>(&v), *pr = reinterpret_cast<T2 *>(&rv);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pv[e] = __hadd2(pv[e], pr[e]);
+          }
+          *reinterpret_cast<uint4 *>(C + off) = v;
         }
       }
     }
@@ -260,6 +373,16 @@ static EncodeTiledFn get_encode_fn() {
       fn = reinterpret_cast<EncodeTiledFn>(p);
   }
   return fn;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
 }
 
 // 2D row-major [rows, cols] 16-bit tensor with row stride ld (elements); box = [box_rows, 64 cols]
@@ -297,8 +420,11 @@ static int launch(const T *A, long long lda, const T *B, long long ldb, T *C, lo
   CUtensorMap map_a, map_b;
   RPO_TRY(make_map(&map_a, Num<T>::dtype, A, M, Kd, lda, BM));
   RPO_TRY(make_map(&map_b, Num<T>::dtype, B, N, Kd, ldb, BN));
-  dim3 grid(N / BN, (unsigned)((M + BM - 1) / BM));
-  gemm_tc_kernel<T, BN><<<grid, THREADS, C_::SMEM_BYTES, st>>>(map_a, map_b, C, ldc, M, N, Kd, ep);
+  const int num_n_tiles = N / BN;
+  const long long num_tiles = ((M + BM - 1) / BM) * num_n_tiles;
+  const int grid = (int)(num_tiles < sm_count() ? num_tiles : sm_count());
+  gemm_tc_kernel<T, BN><<<grid, THREADS, C_::SMEM_BYTES, st>>>(map_a, map_b, C, ldc, M, N, Kd, ep, num_n_tiles,
+                                                               (int)num_tiles);
   RPO_LAUNCH_CHECK();
   return RPO_OK;
 }
@@ -312,7 +438,7 @@ bool gemm_tcgen05_supported(int dtype, long long lda, long long ldb, long long l
   if (Kd % tc::BK != 0 || N % 32 != 0) return false;
   if (lda % 8 != 0 || ldb % 8 != 0 || ldc % 8 != 0) return false;
   if (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) return false;
-  if ((M + tc::BM - 1) / tc::BM > 65535) return false;
+  if (((M + tc::BM - 1) / tc::BM) * (long long)(N / 32) > 0x7fffffffLL) return false;
   return true;
 }
 
@@ -324,13 +450,12 @@ int gemm_tcgen05(const T *A, long long lda, const T *B, long long ldb, T *C, lon
     return RPO_ERR_INVALID;
   } else {
     RPO_REQUIRE(gemm_tcgen05_supported(Num<T>::dtype, lda, ldb, ldc, M, N, Kd, A, B, C), "tcgen05 GEMM shape");
-    if (ep.bias) RPO_REQUIRE(((uintptr_t)ep.bias & 15) == 0, "bias must be 16-byte aligned");
     if (ep.residual) RPO_REQUIRE(((uintptr_t)ep.residual & 15) == 0, "residual must be 16-byte aligned");
     if (ep.gelu_grad_aux) RPO_REQUIRE(((uintptr_t)ep.gelu_grad_aux & 15) == 0, "aux must be 16-byte aligned");
     if (ep.aux_out) RPO_REQUIRE(((uintptr_t)ep.aux_out & 15) == 0, "aux_out must be 16-byte aligned");
-    // tile width: the widest BN that still yields at least ~one wave of CTAs on 148 SMs
-    long long mt = (M + tc::BM - 1) / tc::BM;
-    const int target = 148;
+    // tile width: the widest BN that still gives every SM a tile
+    const long long mt = (M + tc::BM - 1) / tc::BM;
+    const int target = tc::sm_count();
     if (N % 128 == 0 && mt * (N / 128) >= target) return tc::launch<T, 128>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);
     if (N % 64 == 0 && mt * (N / 64) >= target) return tc::launch<T, 64>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);
     return tc::launch<T, 32>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);

@@ -160,12 +160,12 @@ template <typename T>
 int logits_ce_bwd(const float *dlogits, const T *img_feat, const T *text_feat, const T *img_n, const T *img_s,
                   const T *text_n, const float *img_norm, const float *text_norm, const float *logit_scale, int B,
                   int C, int K, int E, T *dl_t, T *d_img_s, T *d_text_n, T *d_img_feat, T *d_text_feat,
-                  cudaStream_t st) {
+                  float grad_scale, cudaStream_t st) {
   (void)img_feat;
   (void)text_feat;
   long long n = (long long)B * C;
   // `logits /= K` then the dtype cast of the gradient flowing into each per-pair GEMM output
-  scale_cast_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dlogits, dl_t, n, 1.0f / (float)K);
+  scale_cast_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dlogits, dl_t, n, grad_scale / (float)K);
   RPO_LAUNCH_CHECK();
   Epilogue<T> ep{};
   // d img_s[b,k,:] = sum_c dl[b,c] text_n[c,k,:]
@@ -189,7 +189,7 @@ int logits_ce_bwd(const float *dlogits, const T *img_feat, const T *text_feat, c
                                 T *, float *, float *, T *, float *, float *, float *, cudaStream_t);               \
   template int logits_ce_bwd<T>(const float *, const T *, const T *, const T *, const T *, const T *,               \
                                 const float *, const float *, const float *, int, int, int, int, T *, T *, T *,     \
-                                T *, T *, cudaStream_t);
+                                T *, T *, float, cudaStream_t);
 INSTANTIATE(float)
 INSTANTIATE(__half)
 INSTANTIATE(__nv_bfloat16)
