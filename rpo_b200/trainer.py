@@ -1,0 +1,154 @@
+"""Host-side mirror of the reference's Dassl trainer plugin (trainers/rpo.py:24-39, 235-357): the class
+`RPO` with `check_cfg`, `build_model`, `forward_backward`, `parse_batch_train` and `load_model`,
+registered into Dassl's TRAINER_REGISTRY under the same name, so the reference's `train.py`
+(`import trainers.rpo` at train.py:31, `build_trainer(cfg)` at :163) runs unchanged once
+`trainers/rpo.py` re-exports this module (see INTEGRATION.md and integration/rpo.py).
+
+Only the model behind `self.model` changes: `rpo_b200.model.CustomCLIP` (sm_100a kernels through
+the C ABI) instead of the PyTorch-op implementation.  The trainer itself stays host glue, as in the
+reference: Dassl builds the optimizer and scheduler over `prompt_learner`, `loss.backward()` reaches
+the two prompt Parameters through `rpo_b200.model._RpoLoss`, `optim.step()` is torch's.
+
+Deliberate differences from trainers/rpo.py (none changes a result):
+  * `nn.DataParallel` (:282-285) is not used.  It cannot train RPO (per-replica scalar losses are
+    gathered into a vector and `backward()` has no `.mean()`).  Multi-GPU is one
+    process per GPU: if `torch.distributed` is initialised the prompt gradients are averaged with
+    one all-reduce of a flat f32 buffer before `optim.step()`.
+  * `torch.autograd.set_detect_anomaly(True)` (:288) is not switched on (a debugging aid that halves
+    throughput); set RPO_B200_DETECT_ANOMALY=1 to get it back.
+  * PREC="amp": the reference keeps fp32 weights and autocasts the matmuls; here the fp32 engine runs
+    (at least as precise as autocast) and the GradScaler is kept so the control flow is identical.
+
+Dassl is imported lazily: without it (this repository's test environment) the class is still
+importable over `object` so that its methods can be exercised with a stand-in base.
+"""
+import os
+import os.path as osp
+
+import torch
+
+from .model import CustomCLIP, PromptLearner  # noqa: F401  (re-exported: the reference module defines both)
+
+try:  # pragma: no cover - Dassl is not installed in the build container
+    from dassl.engine import TRAINER_REGISTRY, TrainerX
+    from dassl.optim import build_lr_scheduler, build_optimizer
+    from dassl.utils import load_checkpoint, load_pretrained_weights
+    HAVE_DASSL = True
+except Exception:  # ImportError or a broken partial install
+    TRAINER_REGISTRY = None
+    TrainerX = object
+    build_lr_scheduler = build_optimizer = load_checkpoint = load_pretrained_weights = None
+    HAVE_DASSL = False
+
+
+def load_clip_to_cpu(cfg):
+    """trainers/rpo.py:24-39 -- needs the host checkout's `clip` package (download + build_model are
+    init-time host code and stay the reference's)."""
+    from clip import clip
+    backbone_name = cfg.MODEL.BACKBONE.NAME
+    model_path = clip._download(clip._MODELS[backbone_name])
+    try:
+        jit = torch.jit.load(model_path, map_location="cpu").eval()
+        state_dict = jit.state_dict()
+    except RuntimeError:
+        state_dict = torch.load(model_path, map_location="cpu")
+    return clip.build_model(state_dict)
+
+
+def allreduce_mean_(params, group=None):
+    """Averages the gradients of `params` over the process group with ONE all-reduce of a flat f32
+    buffer.  No-op when torch.distributed is not initialised or world size is 1.
+    Returns the world size used."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1
+    world = dist.get_world_size(group)
+    if world == 1:
+        return 1
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return world
+    flat = torch.cat([g.detach().reshape(-1).float() for g in grads])
+    dist.all_reduce(flat, group=group)
+    flat.div_(world)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g).to(g.dtype))
+        off += n
+    return world
+
+
+class RPO(TrainerX):
+    def check_cfg(self, cfg):
+        assert cfg.TRAINER.RPO.PREC in ["fp16", "fp32", "amp"]  # trainers/rpo.py:238
+
+    def build_model(self):
+        cfg = self.cfg
+        classnames = self.dm.dataset.classnames
+        print(f"Loading CLIP (backbone: {cfg.MODEL.BACKBONE.NAME})")
+        clip_model = load_clip_to_cpu(cfg)
+        if cfg.TRAINER.RPO.PREC in ("fp32", "amp"):
+            clip_model.float()  # CLIP's default precision is fp16 (trainers/rpo.py:247-249)
+        print("Building custom CLIP (rpo_b200: sm_100a kernels)")
+        self.model = CustomCLIP(cfg, classnames, cfg.DATASET.PROMPT, clip_model)
+        for name, param in self.model.named_parameters():  # :258-260
+            if "prompt_learner" not in name:
+                param.requires_grad_(False)
+        enabled = {n for n, p in self.model.named_parameters() if p.requires_grad}
+        print(f"Parameters to be updated: {enabled}")
+        if cfg.MODEL.INIT_WEIGHTS:
+            load_pretrained_weights(self.model.prompt_learner, cfg.MODEL.INIT_WEIGHTS)
+        self.model.to(self.device)
+        # only the prompt learner goes to the optimizer (:274-276)
+        self.optim = build_optimizer(self.model.prompt_learner, cfg.OPTIM)
+        self.sched = build_lr_scheduler(self.optim, cfg.OPTIM)
+        self.register_model("prompt_learner", self.model.prompt_learner, self.optim, self.sched)
+        self.scaler = torch.amp.GradScaler("cuda") if cfg.TRAINER.RPO.PREC == "amp" else None
+        if os.environ.get("RPO_B200_DETECT_ANOMALY") == "1":
+            torch.autograd.set_detect_anomaly(True)
+
+    def forward_backward(self, batch):
+        image, label = self.parse_batch_train(batch)
+        model, optim, scaler = self.model, self.optim, self.scaler
+        loss = model(image, label)
+        optim.zero_grad()
+        if scaler is not None:
+            scaler.scale(loss).backward()
+            allreduce_mean_(list(model.prompt_learner.parameters()))
+            scaler.step(optim)
+            scaler.update()
+        else:
+            loss.backward()
+            allreduce_mean_(list(model.prompt_learner.parameters()))
+            optim.step()
+        loss_summary = {"loss": loss.item()}
+        if (self.batch_idx + 1) == self.num_batches:
+            self.update_lr()
+        return loss_summary
+
+    def parse_batch_train(self, batch):
+        return batch["img"].to(self.device), batch["label"].to(self.device)
+
+    def load_model(self, directory, epoch=None):
+        if not directory:
+            print("Note that load_model() is skipped as no pretrained model is given")
+            return
+        names = self.get_model_names()
+        model_file = "model-best.pth.tar" if epoch is None else "model.pth.tar-" + str(epoch)
+        loader = load_checkpoint or (lambda p: torch.load(p, map_location="cpu"))
+        for name in names:
+            model_path = osp.join(directory, name, model_file)
+            if not osp.exists(model_path):
+                raise FileNotFoundError('Model not found at "{}"'.format(model_path))
+            checkpoint = loader(model_path)
+            state_dict = checkpoint["state_dict"]
+            epoch = checkpoint["epoch"]
+            for legacy in ("token_prefix", "token_suffix"):  # CoOp leftovers (:348-352)
+                state_dict.pop(legacy, None)
+            print('Loading weights to {} from "{}" (epoch = {})'.format(name, model_path, epoch))
+            self._models[name].load_state_dict(state_dict, strict=False)
+
+
+if HAVE_DASSL:  # pragma: no cover
+    RPO = TRAINER_REGISTRY.register()(RPO)

@@ -31,9 +31,12 @@ GRAD_TOL = {"fp32": 3e-5, "fp16": 6e-2, "bf16": 2.5e-1}
 
 def check_grads(prec, ours, ref_same_prec, ref_fp32, what):
     direct = rel_err(ours, ref_same_prec)
-    assert direct <= GRAD_TOL[prec], f"{what}: {direct:.3e} vs the {prec} reference"
+    floor = rel_err(ref_same_prec, ref_fp32) if prec != "fp32" else 0.0
+    # the direct distance to the 16-bit reference cannot be asked to be smaller than that reference's
+    # own distance from the fp32 one (at batch 32 its fp16 backward is 7e-2 off)
+    assert direct <= max(GRAD_TOL[prec], 1.25 * floor + 2e-3), f"{what}: {direct:.3e} vs the {prec} reference " \
+                                                              f"(whose own distance from fp32 is {floor:.3e})"
     if prec != "fp32":
-        floor = rel_err(ref_same_prec, ref_fp32)
         mine = rel_err(ours, ref_fp32)
         assert mine <= 2.0 * floor + 2e-3, f"{what}: {mine:.3e} from the fp32 reference; the reference's own " \
                                            f"{prec} run is {floor:.3e} away"
