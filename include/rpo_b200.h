@@ -183,6 +183,14 @@ int64_t rpo_debug_fetch(RpoHandle *h, int32_t which, int32_t layer, void *dst, i
 /* number of kernel launches issued by the last rpo_forward + rpo_backward pair */
 int64_t rpo_launch_count(const RpoHandle *h);
 
+/* Launch profiler (diagnostics; not for use inside CUDA-graph capture).  Between rpo_profile_begin and
+ * rpo_profile_end every kernel this library launches from the calling thread is followed by a CUDA
+ * event on its stream.  rpo_profile_end synchronises, writes one line per launch into buf --
+ * "<source file:line>\t<microseconds since the previous launch finished>\t<tag: GEMM shape etc.>" --
+ * and returns the number of launches (-1 on error). */
+int rpo_profile_begin(void *stream);
+int64_t rpo_profile_end(char *buf, int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,7 +19,7 @@ SYMBOLS = [
     "rpo_last_error", "rpo_version", "rpo_create", "rpo_destroy", "rpo_device_bytes", "rpo_bind_weights",
     "rpo_set_classes", "rpo_forward", "rpo_backward", "rpo_sgd_step", "rpo_layernorm_fwd", "rpo_layernorm_bwd",
     "rpo_gemm_bias_act", "rpo_ro_attention_fwd", "rpo_ro_attention_bwd", "rpo_logits_ce_fwd", "rpo_logits_ce_bwd",
-    "rpo_debug_fetch", "rpo_launch_count",
+    "rpo_debug_fetch", "rpo_launch_count", "rpo_profile_begin", "rpo_profile_end",
 ]
 
 
@@ -82,6 +82,9 @@ def load():
     lib.rpo_debug_fetch.restype = i64
     lib.rpo_launch_count.argtypes = [vp]
     lib.rpo_launch_count.restype = i64
+    lib.rpo_profile_begin.argtypes = [vp]
+    lib.rpo_profile_end.argtypes = [C.c_char_p, i64]
+    lib.rpo_profile_end.restype = i64
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("rpo_version",):

@@ -383,6 +383,7 @@ static int launch_fwd(const T *qkv_ctx, const T *q_prompt, T *out_ctx, T *out_pr
   }
   const int n_q = (do_ctx ? max_ctx : 0) + K;
   dim3 grid((n_q + QT - 1) / QT, H, G);
+  prof_tag("attn_fwd G=%d H=%d K=%d max_ctx=%d do_ctx=%d", G, H, K, max_ctx, do_ctx);
   ro_attn_fwd_mma<T, NT><<<grid, THREADS, smem, st>>>(qkv_ctx, q_prompt, out_ctx, out_prompt, ctx_off, K, H, causal,
                                                       do_ctx);
   RPO_LAUNCH_CHECK();
@@ -400,6 +401,7 @@ static int launch_bwd(const T *qkv_ctx, const T *q_prompt, const T *o_prompt, co
     configured = smem;
   }
   dim3 grid(H, G, (K + QT - 1) / QT);
+  prof_tag("attn_bwd G=%d H=%d K=%d max_ctx=%d", G, H, K, max_ctx);
   ro_attn_bwd_mma<T, NT><<<grid, THREADS, smem, st>>>(qkv_ctx, q_prompt, o_prompt, d_out, dq, ctx_off, K, H);
   RPO_LAUNCH_CHECK();
   return RPO_OK;

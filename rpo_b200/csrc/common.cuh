@@ -41,11 +41,18 @@ extern thread_local int64_t g_launch_count;
     if (_s != RPO_OK) return _s;   \
   } while (0)
 
-// every kernel launch goes through this so that launches are counted and checked
-#define RPO_LAUNCH_CHECK()                    \
-  do {                                        \
-    rpo::g_launch_count++;                    \
-    RPO_CHECK_CUDA(cudaPeekAtLastError());    \
+// every kernel launch goes through this so that launches are counted and checked; `st` (the stream
+// of the launch) must be in scope.  With the launch profiler armed (rpo_profile_begin) a CUDA event
+// is recorded after the launch so that rpo_profile_end can report per-launch device times measured
+// at the clocks of a real, back-to-back step (ncu's serialised launches run at idle clocks).
+void prof_mark(const char *file, int line, cudaStream_t st);
+void prof_tag(const char *fmt, ...);
+extern thread_local bool g_prof_on;
+#define RPO_LAUNCH_CHECK()                                      \
+  do {                                                          \
+    rpo::g_launch_count++;                                      \
+    RPO_CHECK_CUDA(cudaPeekAtLastError());                      \
+    if (rpo::g_prof_on) rpo::prof_mark(__FILE__, __LINE__, st); \
   } while (0)
 
 inline size_t dtype_size(int dtype) { return dtype == RPO_F32 ? 4 : 2; }

@@ -27,6 +27,19 @@ __device__ __forceinline__ void load_row(const T *row, int nv, int lane, float (
   }
 }
 
+// N consecutive f32 parameters (LayerNorm affine) with 16-byte loads; p is 16-byte aligned
+template <int N>
+__device__ __forceinline__ void load_f32(const float *__restrict__ p, float (&out)[N]) {
+#pragma unroll
+  for (int i = 0; i < N / 4; ++i) {
+    float4 v = __ldg(reinterpret_cast<const float4 *>(p) + i);
+    out[4 * i] = v.x;
+    out[4 * i + 1] = v.y;
+    out[4 * i + 2] = v.z;
+    out[4 * i + 3] = v.w;
+  }
+}
+
 template <typename T, int MAXV>
 __device__ __forceinline__ void row_stats(const float (&vals)[MAXV * Vec16<T>::N], int nv, int lane, int D,
                                           float &mean, float &rstd) {
@@ -69,11 +82,11 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const T *__restri
     int vi = lane + 32 * i;
     if (vi < nv) {
       Vec16<T> o;
+      float wv[VEC], bv[VEC];
+      load_f32<VEC>(w + vi * VEC, wv);
+      load_f32<VEC>(b + vi * VEC, bv);
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) {
-        int c = vi * VEC + e;
-        o.v[e] = fromf<T>((vals[i * VEC + e] - mean) * rstd * __ldg(w + c) + __ldg(b + c));
-      }
+      for (int e = 0; e < VEC; ++e) o.v[e] = fromf<T>((vals[i * VEC + e] - mean) * rstd * wv[e] + bv[e]);
       st16(y + row * D + (size_t)vi * VEC, o);
     }
   }
@@ -100,10 +113,11 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const T *__restri
   for (int i = 0; i < MAXV; ++i) {
     int vi = lane + 32 * i;
     if (vi < nv) {
+      float wv[VEC];
+      load_f32<VEC>(w + vi * VEC, wv);
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
-        int c = vi * VEC + e;
-        float g = gv[i * VEC + e] * __ldg(w + c);
+        float g = gv[i * VEC + e] * wv[e];
         float xh = (xv[i * VEC + e] - mean) * rstd;
         gv[i * VEC + e] = g;
         xv[i * VEC + e] = xh;
@@ -136,8 +150,10 @@ static bool ln_shape_ok(int D, size_t esz) { return D > 0 && D <= 1024 && (D * e
 template <typename T>
 int layernorm_fwd(const T *x, const float *w, const float *b, T *y, long long rows, int D, cudaStream_t st) {
   RPO_REQUIRE(ln_shape_ok(D, sizeof(T)), "LayerNorm width must be <= 1024 and a multiple of 16 bytes");
+  RPO_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)w | (uintptr_t)b) & 15) == 0, "LayerNorm buffers must be 16-byte aligned");
   if (rows <= 0) return RPO_OK;
   unsigned grid = (unsigned)((rows + LN_WARPS - 1) / LN_WARPS);
+  prof_tag("ln_fwd rows=%lld D=%d", rows, D);
   ln_fwd_kernel<T><<<grid, LN_WARPS * 32, 0, st>>>(x, w, b, y, rows, D);
   RPO_LAUNCH_CHECK();
   return RPO_OK;
@@ -146,8 +162,10 @@ template <typename T>
 int layernorm_bwd(const T *dy, const T *x, const float *w, const T *dres, T *dx, long long rows, int D,
                   cudaStream_t st) {
   RPO_REQUIRE(ln_shape_ok(D, sizeof(T)), "LayerNorm width must be <= 1024 and a multiple of 16 bytes");
+  RPO_REQUIRE((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)dres | (uintptr_t)w) & 15) == 0, "LayerNorm buffers must be 16-byte aligned");
   if (rows <= 0) return RPO_OK;
   unsigned grid = (unsigned)((rows + LN_WARPS - 1) / LN_WARPS);
+  prof_tag("ln_bwd rows=%lld D=%d", rows, D);
   ln_bwd_kernel<T><<<grid, LN_WARPS * 32, 0, st>>>(dy, x, w, dres, dx, rows, D);
   RPO_LAUNCH_CHECK();
   return RPO_OK;

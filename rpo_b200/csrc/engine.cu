@@ -12,6 +12,10 @@
 // (attention output), x_mid[l] (after the attention residual) and fcpre[l] (MLP pre-activation of the
 // prompt rows);
 // that is everything the prompt-row backward needs, so nothing is recomputed.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include <vector>
 
 #include "common.cuh"
@@ -21,6 +25,35 @@ namespace rpo {
 thread_local std::string g_last_error;
 thread_local int64_t g_launch_count = 0;
 void set_error(const std::string &msg) { g_last_error = msg; }
+
+// ---- launch profiler (see RPO_LAUNCH_CHECK) -------------------------------------------------------
+thread_local bool g_prof_on = false;
+struct ProfEntry {
+  std::string where, tag;
+  cudaEvent_t ev;
+};
+static thread_local std::vector<ProfEntry> g_prof;
+static thread_local std::string g_prof_tag;
+static thread_local cudaEvent_t g_prof_start = nullptr;
+void prof_tag(const char *fmt, ...) {
+  if (!g_prof_on) return;
+  char buf[160];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_prof_tag = buf;
+}
+void prof_mark(const char *file, int line, cudaStream_t st) {
+  ProfEntry e;
+  const char *base = strrchr(file, '/');
+  e.where = std::string(base ? base + 1 : file) + ":" + std::to_string(line);
+  e.tag = g_prof_tag;
+  g_prof_tag.clear();
+  if (cudaEventCreate(&e.ev) != cudaSuccess) return;
+  cudaEventRecord(e.ev, st);
+  g_prof.push_back(e);
+}
 
 struct Arena {
   char *base = nullptr;
@@ -79,6 +112,11 @@ struct RpoHandle {
   int *row_cls = nullptr, *row_pos = nullptr;
   const void *img_prompt = nullptr;  // from the last forward (needed by the ln_pre backward)
   int64_t launches_fwd = 0, launches_bwd = 0;
+  // The text tower (C*K prompt rows: many short, latency-bound kernels) runs on a side stream next to
+  // the vision tower, fork/joined with events so that the pair stays capturable into one CUDA graph.
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool overlap = true;
 };
 
 namespace rpo {
@@ -189,6 +227,25 @@ static int forward_impl(RpoHandle *hd, const void *image, int image_dtype, int B
   v.G = B;
   v.Mc = (long long)B * S;
   const long long Mp_v = (long long)B * K;
+  // ---- text tower, prompt rows only (context K/V cached by rpo_set_classes) (:173-191) ----
+  cudaStream_t st_main = st;
+  const long long Mp_t = (long long)C * K;
+  {
+    cudaStream_t st = st_main;  // launch sites below refer to `st`
+    if (hd->overlap) {
+      RPO_CHECK_CUDA(cudaEventRecord(hd->ev_fork, st_main));
+      RPO_CHECK_CUDA(cudaStreamWaitEvent(hd->side, hd->ev_fork, 0));
+      st = hd->side;
+    }
+    RPO_TRY(broadcast_rows<T>((const T *)text_prompt, (T *)t.x_in + t.Mc * Dt, C, K, Dt, st));
+    RPO_TRY(tower_forward<T>(hd, t, false, true, st));
+    T *xt_out = at<T>(t.x_in, (long long)t.layers * t.Mtot_max * Dt) + t.Mc * Dt;
+    RPO_TRY(layernorm_fwd<T>(xt_out, hd->w.ln_final_w, hd->w.ln_final_b, (T *)hd->hp_t, Mp_t, Dt, st));
+    Epilogue<T> ep{};
+    RPO_TRY(gemm_dispatch<T>(backend, (const T *)hd->hp_t, Dt, (const T *)hd->t_projT, Dt, (T *)hd->text_feat, E, Mp_t,
+                             E, Dt, ep, st));
+    if (hd->overlap) RPO_CHECK_CUDA(cudaEventRecord(hd->ev_join, hd->side));
+  }
   RPO_TRY(im2col_patches<T>(image, image_dtype, (T *)hd->patches, B, c.v_res, c.v_patch, hd->pk_pad, st));
   Epilogue<T> ep{};
   const int pk = hd->pk_pad;
@@ -204,14 +261,7 @@ static int forward_impl(RpoHandle *hd, const void *image, int image_dtype, int B
   RPO_TRY(layernorm_fwd<T>(xv_out, hd->w.ln_post_w, hd->w.ln_post_b, (T *)hd->hp_v, Mp_v, Dv, st));
   RPO_TRY(gemm_dispatch<T>(backend, (const T *)hd->hp_v, Dv, (const T *)hd->v_projT, Dv, (T *)hd->img_feat, E, Mp_v, E,
                            Dv, ep, st));
-  // ---- text tower, prompt rows only (context K/V cached by rpo_set_classes) (:173-191) ----
-  const long long Mp_t = (long long)C * K;
-  RPO_TRY(broadcast_rows<T>((const T *)text_prompt, (T *)t.x_in + t.Mc * Dt, C, K, Dt, st));
-  RPO_TRY(tower_forward<T>(hd, t, false, true, st));
-  T *xt_out = at<T>(t.x_in, (long long)t.layers * t.Mtot_max * Dt) + t.Mc * Dt;
-  RPO_TRY(layernorm_fwd<T>(xt_out, hd->w.ln_final_w, hd->w.ln_final_b, (T *)hd->hp_t, Mp_t, Dt, st));
-  RPO_TRY(gemm_dispatch<T>(backend, (const T *)hd->hp_t, Dt, (const T *)hd->t_projT, Dt, (T *)hd->text_feat, E, Mp_t,
-                           E, Dt, ep, st));
+  if (hd->overlap) RPO_CHECK_CUDA(cudaStreamWaitEvent(st_main, hd->ev_join, 0));
   // ---- logits + CE (:215-230) ----
   float *lg = logits ? logits : hd->logits_f;
   RPO_TRY(logits_ce_fwd<T>((const T *)hd->img_feat, (const T *)hd->text_feat, hd->w.logit_scale, label, B, C, K, E,
@@ -239,8 +289,26 @@ static int backward_impl(RpoHandle *hd, float *grad_flat, cudaStream_t st) {
                            B, C, K, E, (T *)hd->dl_t, (T *)hd->d_img_s, (T *)hd->d_text_n, (T *)hd->d_img_feat,
                            (T *)hd->d_text_feat, gs, st));
   Epilogue<T> ep{};
-  // vision head: d ln_post-out = d img_feat . proj^T  (B operand = proj [Dv,E] itself, K-major in E)
   const long long Mp_v = (long long)B * K, Mp_t = (long long)C * K;
+  {
+    // text head + text tower backward, on the side stream next to the vision backward
+    cudaStream_t st_main = st;
+    cudaStream_t st = st_main;
+    if (hd->overlap) {
+      RPO_CHECK_CUDA(cudaEventRecord(hd->ev_fork, st_main));
+      RPO_CHECK_CUDA(cudaStreamWaitEvent(hd->side, hd->ev_fork, 0));
+      st = hd->side;
+    }
+    RPO_TRY(gemm_dispatch<T>(backend, (const T *)hd->d_text_feat, E, (const T *)hd->w.t_proj, E, (T *)t.dh, Dt, Mp_t,
+                             Dt, E, ep, st));
+    T *xt_out = at<T>(t.x_in, (long long)t.layers * t.Mtot_max * Dt) + t.Mc * Dt;
+    RPO_TRY(layernorm_bwd<T>((const T *)t.dh, xt_out, hd->w.ln_final_w, nullptr, (T *)t.dx, Mp_t, Dt, st));
+    RPO_TRY(tower_backward<T>(hd, t, st));
+    // d text_prompt: the prompt is shared by all classes (trainers/rpo.py:176-177)
+    RPO_TRY(reduce_groups_f32<T>((const T *)t.dx, grad_flat, C, K, Dt, 1.0f / gs, st));
+    if (hd->overlap) RPO_CHECK_CUDA(cudaEventRecord(hd->ev_join, hd->side));
+  }
+  // vision head: d ln_post-out = d img_feat . proj^T  (B operand = proj [Dv,E] itself, K-major in E)
   RPO_TRY(gemm_dispatch<T>(backend, (const T *)hd->d_img_feat, E, (const T *)hd->w.v_proj, E, (T *)v.dh, Dv, Mp_v, Dv,
                            E, ep, st));
   T *xv_out = at<T>(v.x_in, (long long)v.layers * v.Mtot_max * Dv) + v.Mc * Dv;
@@ -250,14 +318,7 @@ static int backward_impl(RpoHandle *hd, float *grad_flat, cudaStream_t st) {
   RPO_TRY(reduce_groups_f32<T>((const T *)v.dx, hd->dsum_v, B, K, Dv, 1.0f / gs, st));
   RPO_TRY(lnpre_prompt_bwd<T>(hd->dsum_v, (const T *)hd->img_prompt, hd->w.ln_pre_w, grad_flat + (size_t)K * Dt, K, Dv,
                               st));
-  // text head
-  RPO_TRY(gemm_dispatch<T>(backend, (const T *)hd->d_text_feat, E, (const T *)hd->w.t_proj, E, (T *)t.dh, Dt, Mp_t, Dt,
-                           E, ep, st));
-  T *xt_out = at<T>(t.x_in, (long long)t.layers * t.Mtot_max * Dt) + t.Mc * Dt;
-  RPO_TRY(layernorm_bwd<T>((const T *)t.dh, xt_out, hd->w.ln_final_w, nullptr, (T *)t.dx, Mp_t, Dt, st));
-  RPO_TRY(tower_backward<T>(hd, t, st));
-  // d text_prompt: the prompt is shared by all classes (trainers/rpo.py:176-177)
-  RPO_TRY(reduce_groups_f32<T>((const T *)t.dx, grad_flat, C, K, Dt, 1.0f / gs, st));
+  if (hd->overlap) RPO_CHECK_CUDA(cudaStreamWaitEvent(st, hd->ev_join, 0));
   hd->launches_bwd = g_launch_count;
   return RPO_OK;
 }
@@ -469,12 +530,26 @@ int rpo_create(const RpoConfig *cfg, RpoHandle **out) {
     delete h;
     return RPO_ERR_CUDA;
   }
+  {
+    const char *e = getenv("RPO_SINGLE_STREAM");
+    h->overlap = !(e && e[0] == '1');
+  }
+  if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    set_error("could not create the side stream / events");
+    rpo_destroy(h);
+    return RPO_ERR_CUDA;
+  }
   *out = h;
   return RPO_OK;
 }
 
 void rpo_destroy(RpoHandle *h) {
   if (!h) return;
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->side) cudaStreamDestroy(h->side);
   for (void *p : h->owned) cudaFree(p);
   if (h->arena.base) cudaFree(h->arena.base);
   delete h;
@@ -573,6 +648,40 @@ int rpo_backward(RpoHandle *h, float *grad_flat, void *stream) {
 }
 
 int64_t rpo_launch_count(const RpoHandle *h) { return h ? h->launches_fwd + h->launches_bwd : 0; }
+
+int rpo_profile_begin(void *stream) {
+  for (ProfEntry &e : g_prof) cudaEventDestroy(e.ev);
+  g_prof.clear();
+  if (!g_prof_start) RPO_CHECK_CUDA(cudaEventCreate(&g_prof_start));
+  RPO_CHECK_CUDA(cudaEventRecord(g_prof_start, (cudaStream_t)stream));
+  g_prof_on = true;
+  return RPO_OK;
+}
+
+int64_t rpo_profile_end(char *buf, int64_t cap) {
+  g_prof_on = false;
+  if (g_prof.empty()) return 0;
+  if (cudaEventSynchronize(g_prof.back().ev) != cudaSuccess) return -1;
+  std::string out;
+  cudaEvent_t prev = g_prof_start;
+  for (ProfEntry &e : g_prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, prev, e.ev);
+    char line[320];
+    snprintf(line, sizeof(line), "%s\t%.3f\t%s\n", e.where.c_str(), ms * 1e3f, e.tag.c_str());
+    out += line;
+    prev = e.ev;
+  }
+  const int64_t n = (int64_t)g_prof.size();
+  for (ProfEntry &e : g_prof) cudaEventDestroy(e.ev);
+  g_prof.clear();
+  if (buf && cap > 0) {
+    size_t m = out.size() < (size_t)cap - 1 ? out.size() : (size_t)cap - 1;
+    memcpy(buf, out.data(), m);
+    buf[m] = 0;
+  }
+  return n;
+}
 
 int rpo_sgd_step(void *param, int32_t dtype, const float *grad, float *momentum_buf, int64_t n, const float *lr,
                  float momentum, float weight_decay, float grad_scale, const int32_t *first_step, void *stream) {

@@ -82,6 +82,8 @@ template <typename T>
 int gemm_dispatch(int backend, const T *A, long long lda, const T *B, long long ldb, T *C, long long ldc, long long M,
                   int N, int Kd, const Epilogue<T> &ep, cudaStream_t st) {
   if (M <= 0) return RPO_OK;
+  prof_tag("gemm M=%lld N=%d K=%d%s%s%s%s", M, N, Kd, ep.bias ? " +bias" : "", ep.act ? " +gelu" : "",
+           ep.residual ? " +res" : "", ep.gelu_grad_aux ? " *gelu'" : "");
   bool tc_ok = gemm_tcgen05_supported(Num<T>::dtype, lda, ldb, ldc, M, N, Kd, A, B, C);
   if (backend == RPO_GEMM_TCGEN05) {
     RPO_REQUIRE(tc_ok, "shape/dtype not supported by the tcgen05 GEMM");
