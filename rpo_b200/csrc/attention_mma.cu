@@ -13,6 +13,8 @@
 // The backward kernel produces dQ for the prompt queries only (nothing else on the path needs a
 // gradient): P is recomputed, delta = rowsum(dO * O) comes from the saved forward output, and
 // dS = P * (dP - delta) / 8 is formed 16 keys at a time so that only S stays resident in registers.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace rpo {
@@ -200,6 +202,8 @@ __global__ void __launch_bounds__(THREADS)
   extern __shared__ __align__(128) uint8_t sm[];
   const int g = blockIdx.z, h = blockIdx.y;
   const int D = H * HD;
+  pdl_wait();
+  pdl_trigger();
   const int row0 = ctx_off[g];
   const int n = ctx_off[g + 1] - row0;
   const int n_ctx_q = do_ctx ? n : 0;
@@ -274,6 +278,8 @@ __global__ void __launch_bounds__(THREADS)
   extern __shared__ __align__(128) uint8_t sm[];
   const int g = blockIdx.y, h = blockIdx.x;
   const int D = H * HD;
+  pdl_wait();
+  pdl_trigger();
   const int row0 = ctx_off[g];
   const int n = ctx_off[g + 1] - row0;
   const int n16 = (n + 15) & ~15;
@@ -371,6 +377,244 @@ __global__ void __launch_bounds__(THREADS)
   });
 }
 
+// ---- forward, streaming ("flash") form -----------------------------------------------------------
+// One CTA = one (group, head) and up to 128 query rows (blockDim.x/32 warps x 16 rows).  K and V of
+// the (group, head) are staged ONCE per CTA in 64-key chunks, one cp.async commit group per chunk, so
+// the tensor-core work on chunk c overlaps the loads of chunks c+1.. ; softmax is the online form
+// (running row max m and row sum l, accumulator rescaled by exp2((m_old - m_new)/8 log2e) per chunk),
+// which keeps the live score fragment at 64 keys = 32 registers and lets two CTAs (16 warps) share an
+// SM.  Probabilities are rounded to the 16-bit dtype where they feed the P.V tensor-core product (the
+// reference rounds the normalised probability tensor; here the division by l happens once at the
+// end in f32 -- same 2^-11 relative rounding, within the 1e-3 parity bar).
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_pending(int pending) {
+  switch (pending) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+  }
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+static constexpr int KC = 64;          // keys per chunk
+static constexpr int MAX_CHUNKS = 5;   // 288 context rows
+static constexpr int FL_MAX_WARPS = 8;
+
+// rows [r_lo, r_hi) of a head slice into swizzled smem rows (zero-filled at and beyond n)
+template <typename T>
+__device__ __forceinline__ void stage_row_range(uint32_t dst, const T *base, long long ld, int r_lo, int r_hi, int n) {
+  for (int idx = threadIdx.x + r_lo * 8; idx < r_hi * 8; idx += blockDim.x) {
+    int r = idx >> 3, c = idx & 7;
+    if (r < n)
+      cp_async16(dst + swz(r, c), base + (long long)r * ld + c * 8);
+    else
+      st_zero16(dst + swz(r, c));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(FL_MAX_WARPS * 32, 2)
+    ro_attn_fwd_flash(const T *__restrict__ qkv_ctx, const T *__restrict__ q_prompt, T *__restrict__ out_ctx,
+                      T *__restrict__ out_prompt, const int *__restrict__ ctx_off, int K, int H, int causal,
+                      int do_ctx) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  const int g = blockIdx.z, h = blockIdx.y;
+  const int D = H * HD;
+  pdl_wait();
+  pdl_trigger();
+  const int row0 = ctx_off[g];
+  const int n = ctx_off[g + 1] - row0;
+  const int n_ctx_q = do_ctx ? n : 0;
+  const int n_q = n_ctx_q + K;
+  const int rows_cta = (blockDim.x >> 5) * 16;
+  const int q_begin = blockIdx.x * rows_cta;
+  if (q_begin >= n_q) return;
+  const int n16 = (n + 15) & ~15;
+  const int nchunks = (n16 + KC - 1) / KC;
+  const uint32_t Ks = smem_u32(sm), Vs = Ks + n16 * ROW_BYTES, Qs = Vs + n16 * ROW_BYTES;
+  uint8_t *Qs_gen = sm + 2 * n16 * ROW_BYTES;
+  const T *kbase = qkv_ctx + (long long)row0 * 3 * D + D + h * HD;
+  // group 0: Q tile + first K/V chunk; group c: K/V chunk c
+  for (int idx = threadIdx.x; idx < rows_cta * 8; idx += blockDim.x) {
+    int r = idx >> 3, c = idx & 7;
+    int qi = q_begin + r;
+    if (qi < n_q) {
+      const T *src = qi < n_ctx_q ? qkv_ctx + (long long)(row0 + qi) * 3 * D + h * HD
+                                  : q_prompt + ((long long)g * K + (qi - n_ctx_q)) * D + h * HD;
+      cp_async16(Qs + swz(r, c), src + c * 8);
+    } else {
+      st_zero16(Qs + swz(r, c));
+    }
+  }
+  for (int c = 0; c < nchunks; ++c) {
+    const int lo = c * KC, hi = min(n16, lo + KC);
+    stage_row_range<T>(Ks, kbase, 3LL * D, lo, hi, n);
+    stage_row_range<T>(Vs, kbase + D, 3LL * D, lo, hi, n);
+    cp_async_commit();
+  }
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r_base = warp * 16;
+  const bool active = q_begin + r_base < n_q;  // warp-uniform
+  const int m = lane >> 3;
+  const int qa = q_begin + r_base + (lane >> 2), qb = qa + 8;
+  const int nvis_a = (causal && qa < n_ctx_q) ? min(n, qa + 1) : n;
+  const int nvis_b = (causal && qb < n_ctx_q) ? min(n, qb + 1) : n;
+  const float sl2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+  const int c0 = 2 * (lane & 3);
+
+  uint32_t qf[4][4];
+  float o[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+  float m_a = -INFINITY, m_b = -INFINITY, l_a = 0.f, l_b = 0.f;
+  // per-lane ldmatrix offsets.  Key rows advance in multiples of 8, so (row & 7) == (lane & 7) and the
+  // XOR swizzle term depends only on the lane and the (compile-time) 16-byte column index.
+  uint32_t xk[4], xv[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    xk[i] = (uint32_t)(((i * 2 + (m & 1)) ^ (lane & 7)) << 4);
+    xv[i] = (uint32_t)(((i * 2 + (m >> 1)) ^ (lane & 7)) << 4);
+  }
+  const uint32_t k_lane = Ks + (uint32_t)(((m >> 1) * 8 + (lane & 7)) * ROW_BYTES);
+  const uint32_t v_lane = Vs + (uint32_t)(((m & 1) * 8 + (lane & 7)) * ROW_BYTES);
+
+  for (int c = 0; c < nchunks; ++c) {
+    cp_async_wait_pending(nchunks - 1 - c);
+    __syncthreads();
+    if (!active) continue;
+    if (c == 0) {
+      const int row = r_base + (m & 1) * 8 + (lane & 7);
+#pragma unroll
+      for (int kd = 0; kd < 4; ++kd)
+        ldsm_x4(Qs + swz(row, kd * 2 + (m >> 1)), qf[kd][0], qf[kd][1], qf[kd][2], qf[kd][3]);
+    }
+    const int k0 = c * KC;
+    const int ng = (min(n16, k0 + KC) - k0) >> 4;  // 16-key groups in this chunk (1..4), CTA-uniform
+    const uint32_t kc = k_lane + (uint32_t)(k0 * ROW_BYTES), vc = v_lane + (uint32_t)(k0 * ROW_BYTES);
+    float s[8][4];
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      s[2 * np][0] = s[2 * np][1] = s[2 * np][2] = s[2 * np][3] = 0.f;
+      s[2 * np + 1][0] = s[2 * np + 1][1] = s[2 * np + 1][2] = s[2 * np + 1][3] = 0.f;
+      if (np < ng) {
+#pragma unroll
+        for (int kd = 0; kd < 4; ++kd) {
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4(kc + (uint32_t)(np * 16 * ROW_BYTES) + xk[kd], b0, b1, b2, b3);
+          mma16816<T>(s[2 * np], qf[kd], b0, b1);
+          mma16816<T>(s[2 * np + 1], qf[kd], b2, b3);
+        }
+      }
+    }
+    // mask (only where something is masked: causal rows, the ragged tail of the last chunk) + chunk max
+    float mxa = -INFINITY, mxb = -INFINITY;
+    if (causal || k0 + KC > n) {  // CTA-uniform
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int col = k0 + nt * 8 + c0;
+        if (col >= nvis_a) s[nt][0] = -INFINITY;
+        if (col + 1 >= nvis_a) s[nt][1] = -INFINITY;
+        if (col >= nvis_b) s[nt][2] = -INFINITY;
+        if (col + 1 >= nvis_b) s[nt][3] = -INFINITY;
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      mxa = fmaxf(mxa, fmaxf(s[nt][0], s[nt][1]));
+      mxb = fmaxf(mxb, fmaxf(s[nt][2], s[nt][3]));
+    }
+    // every row sees key 0, so after chunk 0 the running max is finite
+    const float mna = fmaxf(m_a, quad_max(mxa)), mnb = fmaxf(m_b, quad_max(mxb));
+    const float al_a = ex2_approx((m_a - mna) * sl2), al_b = ex2_approx((m_b - mnb) * sl2);
+    m_a = mna;
+    m_b = mnb;
+    const float oa = mna * sl2, ob = mnb * sl2;
+    float sa = 0.f, sb = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = ex2_approx(fmaf(s[nt][0], sl2, -oa));
+      s[nt][1] = ex2_approx(fmaf(s[nt][1], sl2, -oa));
+      s[nt][2] = ex2_approx(fmaf(s[nt][2], sl2, -ob));
+      s[nt][3] = ex2_approx(fmaf(s[nt][3], sl2, -ob));
+      sa += s[nt][0] + s[nt][1];
+      sb += s[nt][2] + s[nt][3];
+    }
+    l_a = l_a * al_a + sa;
+    l_b = l_b * al_b + sb;
+    if (__any_sync(0xffffffffu, al_a != 1.0f || al_b != 1.0f)) {  // running max moved for some row of the warp
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        o[nt][0] *= al_a;
+        o[nt][1] *= al_a;
+        o[nt][2] *= al_b;
+        o[nt][3] *= al_b;
+      }
+    }
+    // O += P V_chunk
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      if (kk < ng) {
+        uint32_t a[4];
+        a[0] = pack2<T>(s[2 * kk][0], s[2 * kk][1]);
+        a[1] = pack2<T>(s[2 * kk][2], s[2 * kk][3]);
+        a[2] = pack2<T>(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        a[3] = pack2<T>(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+        for (int dp = 0; dp < 4; ++dp) {
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4_trans(vc + (uint32_t)(kk * 16 * ROW_BYTES) + xv[dp], b0, b1, b2, b3);
+          mma16816<T>(o[dp * 2], a, b0, b1);
+          mma16816<T>(o[dp * 2 + 1], a, b2, b3);
+        }
+      }
+    }
+  }
+  if (!active) return;
+  const float ia = 1.0f / quad_sum(l_a), ib = 1.0f / quad_sum(l_b);
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    o[nt][0] *= ia;
+    o[nt][1] *= ia;
+    o[nt][2] *= ib;
+    o[nt][3] *= ib;
+  }
+  __syncwarp();  // the warp's Q rows were consumed into registers at chunk 0: reuse them as staging
+  store_tile<T>(Qs, Qs_gen, r_base, o, lane, [&](int r) -> T * {
+    int qi = q_begin + r;
+    if (qi >= n_q) return nullptr;
+    return qi < n_ctx_q ? out_ctx + (long long)(row0 + qi) * D + h * HD
+                        : out_prompt + ((long long)g * K + (qi - n_ctx_q)) * D + h * HD;
+  });
+}
+
+template <typename T>
+static int launch_fwd_flash(const T *qkv_ctx, const T *q_prompt, T *out_ctx, T *out_prompt, const int *ctx_off, int G,
+                            int K, int H, int max_ctx, int causal, int do_ctx, cudaStream_t st) {
+  const int n16 = (max_ctx + 15) & ~15;
+  const int n_q = (do_ctx ? max_ctx : 0) + K;
+  const int tiles = (n_q + 15) / 16;
+  const int ncta = (tiles + FL_MAX_WARPS - 1) / FL_MAX_WARPS;
+  const int warps = (tiles + ncta - 1) / ncta;  // L=221: 2 CTAs x 7 warps; L=281: 3 x 6
+  const int smem = (2 * n16 + warps * 16) * ROW_BYTES;
+  static int configured = 0;
+  if (smem > configured) {
+    RPO_CHECK_CUDA(cudaFuncSetAttribute(ro_attn_fwd_flash<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  dim3 grid(ncta, H, G);
+  prof_tag("attn_fwd G=%d H=%d K=%d max_ctx=%d do_ctx=%d", G, H, K, max_ctx, do_ctx);
+  RPO_CHECK_CUDA(launch_pdl(ro_attn_fwd_flash<T>, grid, dim3(warps * 32), smem, st, qkv_ctx, q_prompt, out_ctx, out_prompt,
+                            ctx_off, K, H, causal, do_ctx));
+  RPO_LAUNCH_CHECK();
+  return RPO_OK;
+}
+
 template <typename T, int NT>
 static int launch_fwd(const T *qkv_ctx, const T *q_prompt, T *out_ctx, T *out_prompt, const int *ctx_off, int G, int K,
                       int H, int max_ctx, int causal, int do_ctx, cudaStream_t st) {
@@ -384,8 +628,8 @@ static int launch_fwd(const T *qkv_ctx, const T *q_prompt, T *out_ctx, T *out_pr
   const int n_q = (do_ctx ? max_ctx : 0) + K;
   dim3 grid((n_q + QT - 1) / QT, H, G);
   prof_tag("attn_fwd G=%d H=%d K=%d max_ctx=%d do_ctx=%d", G, H, K, max_ctx, do_ctx);
-  ro_attn_fwd_mma<T, NT><<<grid, THREADS, smem, st>>>(qkv_ctx, q_prompt, out_ctx, out_prompt, ctx_off, K, H, causal,
-                                                      do_ctx);
+  RPO_CHECK_CUDA(launch_pdl(ro_attn_fwd_mma<T, NT>, grid, dim3(THREADS), smem, st, qkv_ctx, q_prompt, out_ctx, out_prompt,
+                            ctx_off, K, H, causal, do_ctx));
   RPO_LAUNCH_CHECK();
   return RPO_OK;
 }
@@ -402,7 +646,8 @@ static int launch_bwd(const T *qkv_ctx, const T *q_prompt, const T *o_prompt, co
   }
   dim3 grid(H, G, (K + QT - 1) / QT);
   prof_tag("attn_bwd G=%d H=%d K=%d max_ctx=%d", G, H, K, max_ctx);
-  ro_attn_bwd_mma<T, NT><<<grid, THREADS, smem, st>>>(qkv_ctx, q_prompt, o_prompt, d_out, dq, ctx_off, K, H);
+  RPO_CHECK_CUDA(launch_pdl(ro_attn_bwd_mma<T, NT>, grid, dim3(THREADS), smem, st, qkv_ctx, q_prompt, o_prompt, d_out, dq,
+                            ctx_off, K, H));
   RPO_LAUNCH_CHECK();
   return RPO_OK;
 }
@@ -423,6 +668,9 @@ int ro_attention_fwd_mma(const T *qkv_ctx, const T *q_prompt, T *out_ctx, T *out
   RPO_REQUIRE(max_ctx >= 1 && max_ctx <= 288, "at most 288 context rows per group on the tensor-core path");
   RPO_REQUIRE(G <= 65535 && H <= 65535, "grid limits");
   if (G == 0 || (!do_ctx && K == 0)) return RPO_OK;
+  static const bool single_pass = [] { const char *e = getenv("RPO_ATTN_SINGLEPASS"); return e && e[0] == '1'; }();
+  if (!single_pass)
+    return amma::launch_fwd_flash<T>(qkv_ctx, q_prompt, out_ctx, out_prompt, ctx_off, G, K, H, max_ctx, causal, do_ctx, st);
   AMMA_PICK(launch_fwd, qkv_ctx, q_prompt, out_ctx, out_prompt, ctx_off, G, K, H, max_ctx, causal, do_ctx, st);
 }
 

@@ -57,6 +57,34 @@ extern thread_local bool g_prof_on;
 
 inline size_t dtype_size(int dtype) { return dtype == RPO_F32 ? 4 : 2; }
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------
+// The towers are chains of ~170 short dependent kernels per step.  Kernels launched through
+// launch_pdl() carry cudaLaunchAttributeProgrammaticStreamSerialization: their CTAs may be scheduled
+// while the previous kernel on the stream is still draining, run their prologue (barrier init, TMEM
+// allocation, tensor-map and weight-tile prefetch), and block in pdl_wait() -- griddepcontrol.wait
+// returns only when the upstream grid has COMPLETED and its writes are visible -- before touching
+// anything an upstream kernel produces or still reads.  Every kernel launched this way must call
+// pdl_wait() in each thread that reads or writes activations.  RPO_NO_PDL=1 turns the attribute off.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- dtype traits -------------------------------------------------------------------------------
 template <typename T>
 struct Num;
@@ -148,6 +176,9 @@ struct Epilogue {
   T *aux_out;              // [M - aux_row0, ldc] or null: pre-activation copy for rows >= aux_row0
   long long aux_row0;
   int act;
+  // operand B is a frozen weight (never written on the step's streams): its first tiles may be
+  // fetched before the upstream kernel has finished (programmatic dependent launch)
+  int b_frozen;
 
   // v: f32 accumulator for element (m, n); returns the value to store (already rounded through T
   // at the points where the reference materialises a dtype tensor).

@@ -71,6 +71,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const T *__restri
   constexpr int MAXV = 32 / VEC;
   long long row = (long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
+  pdl_wait();
+  pdl_trigger();
   if (row >= rows) return;
   int nv = D / VEC;
   float vals[MAXV * VEC];
@@ -101,6 +103,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const T *__restri
   constexpr int MAXV = 32 / VEC;
   long long row = (long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
+  pdl_wait();
+  pdl_trigger();
   if (row >= rows) return;
   int nv = D / VEC;
   float xv[MAXV * VEC], gv[MAXV * VEC];
@@ -154,7 +158,7 @@ int layernorm_fwd(const T *x, const float *w, const float *b, T *y, long long ro
   if (rows <= 0) return RPO_OK;
   unsigned grid = (unsigned)((rows + LN_WARPS - 1) / LN_WARPS);
   prof_tag("ln_fwd rows=%lld D=%d", rows, D);
-  ln_fwd_kernel<T><<<grid, LN_WARPS * 32, 0, st>>>(x, w, b, y, rows, D);
+  RPO_CHECK_CUDA(launch_pdl(ln_fwd_kernel<T>, dim3(grid), dim3(LN_WARPS * 32), 0, st, x, w, b, y, rows, D));
   RPO_LAUNCH_CHECK();
   return RPO_OK;
 }
@@ -166,7 +170,7 @@ int layernorm_bwd(const T *dy, const T *x, const float *w, const T *dres, T *dx,
   if (rows <= 0) return RPO_OK;
   unsigned grid = (unsigned)((rows + LN_WARPS - 1) / LN_WARPS);
   prof_tag("ln_bwd rows=%lld D=%d", rows, D);
-  ln_bwd_kernel<T><<<grid, LN_WARPS * 32, 0, st>>>(dy, x, w, dres, dx, rows, D);
+  RPO_CHECK_CUDA(launch_pdl(ln_bwd_kernel<T>, dim3(grid), dim3(LN_WARPS * 32), 0, st, dy, x, w, dres, dx, rows, D));
   RPO_LAUNCH_CHECK();
   return RPO_OK;
 }

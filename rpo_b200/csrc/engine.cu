@@ -25,6 +25,13 @@ namespace rpo {
 thread_local std::string g_last_error;
 thread_local int64_t g_launch_count = 0;
 void set_error(const std::string &msg) { g_last_error = msg; }
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char *e = getenv("RPO_NO_PDL");
+    return !(e && e[0] == '1');
+  }();
+  return on;
+}
 
 // ---- launch profiler (see RPO_LAUNCH_CHECK) -------------------------------------------------------
 thread_local bool g_prof_on = false;
@@ -121,6 +128,14 @@ struct RpoHandle {
 
 namespace rpo {
 
+// every GEMM of the towers multiplies by a frozen CLIP weight (trainers/rpo.py:258-260)
+template <typename T>
+static Epilogue<T> frozen_ep() {
+  Epilogue<T> e{};
+  e.b_frozen = 1;
+  return e;
+}
+
 template <typename T>
 static T *at(char *base, long long elem_off) {
   return reinterpret_cast<T *>(base) + elem_off;
@@ -144,27 +159,27 @@ static int tower_forward(RpoHandle *hd, Tower &tw, bool do_ctx, bool do_prompt, 
     T *fcpre = at<T>(tw.fcpre, (long long)l * tw.Mp_max * 4 * D);
     // x = x + attn(ln_1(x))                                             clip/model.py:189
     RPO_TRY(layernorm_fwd<T>(x_in + r0 * D, bw.ln1_w, bw.ln1_b, h + r0 * D, rows, D, st));
-    Epilogue<T> ep{};
+    Epilogue<T> ep = frozen_ep<T>();
     if (do_ctx) {
-      ep = Epilogue<T>{};
+      ep = frozen_ep<T>();
       ep.bias = (const T *)bw.in_b;
       RPO_TRY(gemm_dispatch<T>(backend, h, D, (const T *)bw.in_w, D, qkv, 3 * D, Mc, 3 * D, D, ep, st));
     }
     if (do_prompt) {
       // prompts are queries only: project with the q third of in_proj (rows 0..D-1)
-      ep = Epilogue<T>{};
+      ep = frozen_ep<T>();
       ep.bias = (const T *)bw.in_b;
       RPO_TRY(gemm_dispatch<T>(backend, h + Mc * D, D, (const T *)bw.in_w, D, qp, D, Mp, D, D, ep, st));
     }
     RPO_TRY(ro_attention_fwd<T>(qkv, qp, o, o + Mc * D, tw.ctx_off, tw.G, do_prompt ? tw.K : 0, tw.H, tw.max_ctx,
                                 tw.causal, do_ctx ? 1 : 0, st));
-    ep = Epilogue<T>{};
+    ep = frozen_ep<T>();
     ep.bias = (const T *)bw.out_b;
     ep.residual = x_in + r0 * D;
     RPO_TRY(gemm_dispatch<T>(backend, o + r0 * D, D, (const T *)bw.out_w, D, x_mid + r0 * D, D, rows, D, D, ep, st));
     // x = x + mlp(ln_2(x))                                              clip/model.py:190
     RPO_TRY(layernorm_fwd<T>(x_mid + r0 * D, bw.ln2_w, bw.ln2_b, h + r0 * D, rows, D, st));
-    ep = Epilogue<T>{};
+    ep = frozen_ep<T>();
     ep.bias = (const T *)bw.fc_b;
     ep.act = RPO_ACT_QUICKGELU;
     if (do_prompt) {
@@ -173,7 +188,7 @@ static int tower_forward(RpoHandle *hd, Tower &tw, bool do_ctx, bool do_prompt, 
     }
     RPO_TRY(gemm_dispatch<T>(backend, h + r0 * D, D, (const T *)bw.fc_w, D, fc + r0 * 4 * D, 4 * D, rows, 4 * D, D, ep,
                              st));
-    ep = Epilogue<T>{};
+    ep = frozen_ep<T>();
     ep.bias = (const T *)bw.proj_b;
     ep.residual = x_mid + r0 * D;
     RPO_TRY(gemm_dispatch<T>(backend, fc + r0 * 4 * D, 4 * D, (const T *)bw.proj_w, 4 * D, x_out + r0 * D, D, rows, D,
@@ -198,11 +213,11 @@ static int tower_backward(RpoHandle *hd, Tower &tw, cudaStream_t st) {
     T *qkv = at<T>(tw.qkv, (long long)l * tw.Mc_max * 3 * D);
     T *qp = at<T>(tw.qp, (long long)l * tw.Mp_max * D);
     T *fcpre = at<T>(tw.fcpre, (long long)l * tw.Mp_max * 4 * D);
-    Epilogue<T> ep{};
+    Epilogue<T> ep = frozen_ep<T>();
     // MLP: d gelu-input = (dx . W2) * quickgelu'(pre);  d ln2-out = that . W1
     ep.gelu_grad_aux = fcpre;
     RPO_TRY(gemm_dispatch<T>(backend, dx, D, (const T *)tw.proj_wT[l], D, dpre, 4 * D, Mp, 4 * D, D, ep, st));
-    ep = Epilogue<T>{};
+    ep = frozen_ep<T>();
     RPO_TRY(gemm_dispatch<T>(backend, dpre, 4 * D, (const T *)tw.fc_wT[l], 4 * D, dh, D, Mp, D, 4 * D, ep, st));
     RPO_TRY(layernorm_bwd<T>(dh, x_mid, bw.ln2_w, dx, dx_mid, Mp, D, st));
     // attention: d attn-out = dx_mid . Wo ; dq ; d ln1-out = dq . Wq
@@ -241,13 +256,13 @@ static int forward_impl(RpoHandle *hd, const void *image, int image_dtype, int B
     RPO_TRY(tower_forward<T>(hd, t, false, true, st));
     T *xt_out = at<T>(t.x_in, (long long)t.layers * t.Mtot_max * Dt) + t.Mc * Dt;
     RPO_TRY(layernorm_fwd<T>(xt_out, hd->w.ln_final_w, hd->w.ln_final_b, (T *)hd->hp_t, Mp_t, Dt, st));
-    Epilogue<T> ep{};
+    Epilogue<T> ep = frozen_ep<T>();
     RPO_TRY(gemm_dispatch<T>(backend, (const T *)hd->hp_t, Dt, (const T *)hd->t_projT, Dt, (T *)hd->text_feat, E, Mp_t,
                              E, Dt, ep, st));
     if (hd->overlap) RPO_CHECK_CUDA(cudaEventRecord(hd->ev_join, hd->side));
   }
   RPO_TRY(im2col_patches<T>(image, image_dtype, (T *)hd->patches, B, c.v_res, c.v_patch, hd->pk_pad, st));
-  Epilogue<T> ep{};
+  Epilogue<T> ep = frozen_ep<T>();
   const int pk = hd->pk_pad;
   RPO_TRY(gemm_dispatch<T>(backend, (const T *)hd->patches, pk, (const T *)hd->conv_w_eff, pk, (T *)hd->patch_emb, Dv,
                            (long long)B * hd->NP, Dv, pk, ep, st));
@@ -288,7 +303,7 @@ static int backward_impl(RpoHandle *hd, float *grad_flat, cudaStream_t st) {
                            (const T *)hd->img_s, (const T *)hd->text_n, hd->img_norm, hd->text_norm, hd->w.logit_scale,
                            B, C, K, E, (T *)hd->dl_t, (T *)hd->d_img_s, (T *)hd->d_text_n, (T *)hd->d_img_feat,
                            (T *)hd->d_text_feat, gs, st));
-  Epilogue<T> ep{};
+  Epilogue<T> ep = frozen_ep<T>();
   const long long Mp_v = (long long)B * K, Mp_t = (long long)C * K;
   {
     // text head + text tower backward, on the side stream next to the vision backward

@@ -18,6 +18,8 @@
 //                 (also read coalesced) on the way.
 // M tails: TMA zero-fills out-of-bounds rows on load, stores are row-predicated.
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -31,9 +33,13 @@ static constexpr int UMMA_K = 16;
 static constexpr int EPI_WARPS = 8;
 static constexpr int THREADS = 64 + EPI_WARPS * 32;  // producer warp + MMA warp + epilogue warps
 
-template <int BN>
+// LIGHT configurations keep shared memory under half an SM (and TMEM at <= 128 columns) so that two
+// CTAs -- of the same launch or of kernels running on the other stream -- share an SM: the small-M
+// GEMM chains (text tower, backward) are latency-bound, and a second resident CTA hides it.
+template <int BN, bool LIGHT>
 struct Cfg {
-  static constexpr int STAGES = BN >= 128 ? 5 : (BN == 64 ? 6 : 8);
+  static constexpr int STAGES = LIGHT ? (BN == 64 ? 3 : 4) : (BN >= 128 ? 5 : (BN == 64 ? 6 : 8));
+  static constexpr int MIN_CTAS = LIGHT ? 2 : 1;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -44,6 +50,7 @@ struct Cfg {
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulators
   static_assert(STAGE_BYTES % 1024 == 0, "stages must stay 1024-byte aligned");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+  static_assert(!LIGHT || (BN <= 64 && SMEM_BYTES <= 113 * 1024), "light configurations must fit twice per SM");
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -180,12 +187,117 @@ __device__ __forceinline__ uint32_t cst_off(int r, int c) {
   return (uint32_t)(r * (BN * 2) + ((c ^ (r & (CH - 1) & 7)) << 4));
 }
 
+// ---- epilogue of one 128 x BN accumulator tile (shared by the single-CTA and the CTA-pair kernel) ------
+// Phase 0 (before the accumulator is ready, i.e. hidden behind the main loop): prefetch this tile's
+//          residual rows -- or the gelu' auxiliary rows -- in the COALESCED copy-out layout
+//          (16 bytes per thread, BN/16 rows per thread).  Loading them inside the copy-out loop
+//          serialises one L2/HBM round trip per pass; loading them per accumulator row in the
+//          drain loop is uncoalesced (lane = row).
+// Phase 1: drain TMEM (tcgen05.ld 32 columns at a time), bias in f32, ONE rounding to the dtype,
+//          QuickGELU in packed 16-bit math, stage into swizzled shared memory.
+// Phase 2: hand the accumulator back to the MMA warp, then copy out with 16-byte coalesced stores,
+//          applying gelu'(aux) (f32 math) / adding the residual from the prefetched registers.
 template <typename T, int BN>
-__global__ void __launch_bounds__(THREADS, 1)
+struct Epi {
+  using T2 = typename Pk<T>::T2;
+  static constexpr int CH = BN / 8;                          // 16-byte chunks per staged row
+  static constexpr int ROWS_PER_PASS = (EPI_WARPS * 32) / CH;
+  static constexpr int PASSES = BM / ROWS_PER_PASS;          // BN / 16
+  static constexpr int HALVES = BN >= 64 ? 2 : 1;            // BN = 32: one 32-column tcgen05.ld covers the tile
+  static constexpr int COLS_PER_WARP = BN / HALVES;
+
+  uint4 pre[PASSES];
+
+  __device__ __forceinline__ void prefetch(const Epilogue<T> &ep, long long m0, int n0, long long M, long long ldc,
+                                           int etid) {
+    const T *src = ep.residual ? ep.residual : ep.gelu_grad_aux;
+    if (!src) return;
+#pragma unroll
+    for (int i = 0; i < PASSES; ++i) {
+      const int r = i * ROWS_PER_PASS + etid / CH, c = etid % CH;
+      const long long mm = m0 + r;
+      pre[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (mm < M) pre[i] = __ldg(reinterpret_cast<const uint4 *>(src + mm * ldc + n0 + c * 8));
+    }
+  }
+
+  // TMEM accumulator `tmem_acc` (lane/column base of this tile's accumulator) -> staged tile
+  __device__ __forceinline__ void drain(const Epilogue<T> &ep, uint32_t tmem_acc, uint8_t *cstage, const float *bias_s,
+                                        long long m0, int n0, long long M, long long ldc, int warp, int lane) {
+    const int q = warp & 3;
+    const int half_id = (warp - 2) >> 2;
+    const int r_loc = q * 32 + lane;
+    const long long m = m0 + r_loc;
+    const bool aux_inline = ep.gelu_grad_aux && ep.residual;  // both: registers hold the residual
+#pragma unroll 1
+    for (int cc = 0; cc < (half_id < HALVES ? COLS_PER_WARP : 0); cc += 32) {
+      const int c0 = half_id * COLS_PER_WARP + cc;
+      uint32_t acc[32];
+      tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int cl = c0 + g * 8;  // tile-local column of this 16-byte group
+        __align__(16) T2 h[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 b2 = *reinterpret_cast<const float2 *>(bias_s + cl + 2 * e);
+          h[e] = Pk<T>::from_floats(__uint_as_float(acc[g * 8 + 2 * e]) + b2.x,
+                                    __uint_as_float(acc[g * 8 + 2 * e + 1]) + b2.y);
+        }
+        if (ep.aux_out && m >= ep.aux_row0 && m < M)
+          *reinterpret_cast<uint4 *>(ep.aux_out + (m - ep.aux_row0) * ldc + n0 + cl) = *reinterpret_cast<uint4 *>(h);
+        if (ep.act == RPO_ACT_QUICKGELU) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) h[e] = quickgelu2<T>(h[e]);
+        }
+        if (aux_inline && m < M) {
+          Vec16<T> aux = ld16(ep.gelu_grad_aux + m * ldc + n0 + cl);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float2 v = make_float2(tof<T>(reinterpret_cast<T *>(&h[e])[0]), tof<T>(reinterpret_cast<T *>(&h[e])[1]));
+            h[e] = Pk<T>::from_floats(v.x * quickgelu_grad(tof<T>(aux.v[2 * e])),
+                                      v.y * quickgelu_grad(tof<T>(aux.v[2 * e + 1])));
+          }
+        }
+        *reinterpret_cast<uint4 *>(cstage + cst_off<BN>(r_loc, cl >> 3)) = *reinterpret_cast<uint4 *>(h);
+      }
+    }
+  }
+
+  __device__ __forceinline__ void copy_out(const Epilogue<T> &ep, const uint8_t *cstage, T *__restrict__ C,
+                                           long long m0, int n0, long long M, long long ldc, int etid) {
+    const bool aux_pre = ep.gelu_grad_aux && !ep.residual;
+#pragma unroll
+    for (int i = 0; i < PASSES; ++i) {
+      const int r = i * ROWS_PER_PASS + etid / CH, c = etid % CH;
+      const long long mm = m0 + r;
+      if (mm < M) {
+        uint4 v = *reinterpret_cast<const uint4 *>(cstage + cst_off<BN>(r, c));
+        T2 *pv = reinterpret_cast<T2 *>(&v), *pp = reinterpret_cast<T2 *>(&pre[i]);
+        if (aux_pre) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const T *hv = reinterpret_cast<const T *>(&pv[e]), *av = reinterpret_cast<const T *>(&pp[e]);
+            pv[e] = Pk<T>::from_floats(tof<T>(hv[0]) * quickgelu_grad(tof<T>(av[0])),
+                                       tof<T>(hv[1]) * quickgelu_grad(tof<T>(av[1])));
+          }
+        }
+        if (ep.residual) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) pv[e] = __hadd2(pv[e], pp[e]);
+        }
+        *reinterpret_cast<uint4 *>(C + mm * ldc + n0 + c * 8) = v;
+      }
+    }
+  }
+};
+
+template <typename T, int BN, bool LIGHT>
+__global__ void __launch_bounds__(THREADS, (Cfg<BN, LIGHT>::MIN_CTAS))
     gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    T *__restrict__ C, long long ldc, long long M, int N, int Kd, Epilogue<T> ep, int num_n_tiles,
                    int num_tiles) {
-  using C_ = Cfg<BN>;
+  using C_ = Cfg<BN, LIGHT>;
   using T2 = typename Pk<T>::T2;
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles need 1024-byte alignment
@@ -225,21 +337,36 @@ __global__ void __launch_bounds__(THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();  // the next kernel on the stream may start its own prologue
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
+      // weight tiles of the first ring fill do not depend on the upstream kernel: fetch them before
+      // the dependency wait, so their HBM latency overlaps the previous kernel's tail
+      uint32_t pre = 0;
+      if (ep.b_frozen && (int)blockIdx.x < num_tiles) {
+        const int n0 = ((int)blockIdx.x % num_n_tiles) * BN;
+        const int npre = num_kb < C_::STAGES ? num_kb : C_::STAGES;
+        for (; (int)pre < npre; ++pre) {
+          mbar_arrive_expect_tx(full_bar(pre), C_::STAGE_BYTES);
+          tma_load_2d(smem_base + pre * C_::STAGE_BYTES + C_::A_BYTES, &map_b, full_bar(pre), pre * BK, n0);
+        }
+      }
+      pdl_wait();
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / num_n_tiles) * BM, n0 = (tile % num_n_tiles) * BN;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % C_::STAGES;
           const uint32_t ph = (it / C_::STAGES) & 1;
-          mbar_wait(empty_bar(s), ph ^ 1);  // fresh barrier: parity-1 wait passes immediately
-          mbar_arrive_expect_tx(full_bar(s), C_::STAGE_BYTES);
           const uint32_t a_dst = smem_base + s * C_::STAGE_BYTES;
+          if (it >= pre) {
+            mbar_wait(empty_bar(s), ph ^ 1);  // fresh barrier: parity-1 wait passes immediately
+            mbar_arrive_expect_tx(full_bar(s), C_::STAGE_BYTES);
+            tma_load_2d(a_dst + C_::A_BYTES, &map_b, full_bar(s), kb * BK, n0);
+          }
           tma_load_2d(a_dst, &map_a, full_bar(s), kb * BK, m0);
-          tma_load_2d(a_dst + C_::A_BYTES, &map_b, full_bar(s), kb * BK, n0);
         }
       }
     }
@@ -273,79 +400,26 @@ __global__ void __launch_bounds__(THREADS, 1)
     }
   } else {
     // ===== epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
-    const int q = warp & 3;
-    const int half_id = (warp - 2) >> 2;       // which half of the tile's columns
-    const int etid = threadIdx.x - 64;         // 0..255
-    constexpr int HALVES = BN >= 64 ? 2 : 1;   // BN = 32: one 32-column tcgen05.ld covers the tile
-    constexpr int COLS_PER_WARP = BN / HALVES;
-    constexpr int CH = BN / 8;                 // 16-byte chunks per staged row
-    constexpr int ROWS_PER_PASS = (EPI_WARPS * 32) / CH;
-    const int r_loc = q * 32 + lane;           // this thread's accumulator row inside the tile
+    const int etid = threadIdx.x - 64;  // 0..255
+    Epi<T, BN> epi;
     uint32_t t = 0;
+    pdl_wait();  // residual / aux rows come from upstream kernels; C may still be read by them
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
       const int a = t & 1;
       const long long m0 = (long long)(tile / num_n_tiles) * BM;
       const int n0 = (tile % num_n_tiles) * BN;
+      epi.prefetch(ep, m0, n0, M, ldc, etid);
       if (etid < BN) bias_s[etid] = ep.bias ? tof<T>(ep.bias[n0 + etid]) : 0.f;
       mbar_wait(acc_full(a), (t >> 1) & 1);
       tc_fence_after();
       epi_bar_sync();  // staging tile free (previous copy-out done) and bias visible
-      const long long m = m0 + r_loc;
-#pragma unroll 1
-      for (int cc = 0; cc < (half_id < HALVES ? COLS_PER_WARP : 0); cc += 32) {
-        const int c0 = half_id * COLS_PER_WARP + cc;
-        uint32_t acc[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c0), acc);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int cl = c0 + g * 8;  // tile-local column of this 16-byte group
-          __align__(16) T2 h[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 b2 = *reinterpret_cast<const float2 *>(bias_s + cl + 2 * e);
-            h[e] = Pk<T>::from_floats(__uint_as_float(acc[g * 8 + 2 * e]) + b2.x,
-                                      __uint_as_float(acc[g * 8 + 2 * e + 1]) + b2.y);
-          }
-          if (ep.aux_out && m >= ep.aux_row0 && m < M)
-            *reinterpret_cast<uint4 *>(ep.aux_out + (m - ep.aux_row0) * ldc + n0 + cl) = *reinterpret_cast<uint4 *>(h);
-          if (ep.act == RPO_ACT_QUICKGELU) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) h[e] = quickgelu2<T>(h[e]);
-          }
-          if (ep.gelu_grad_aux && m < M) {  // backward only (small M): f32 math
-            Vec16<T> aux = ld16(ep.gelu_grad_aux + m * ldc + n0 + cl);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float2 v = make_float2(tof<T>(reinterpret_cast<T *>(&h[e])[0]), tof<T>(reinterpret_cast<T *>(&h[e])[1]));
-              h[e] = Pk<T>::from_floats(v.x * quickgelu_grad(tof<T>(aux.v[2 * e])),
-                                        v.y * quickgelu_grad(tof<T>(aux.v[2 * e + 1])));
-            }
-          }
-          *reinterpret_cast<uint4 *>(cstage + cst_off<BN>(r_loc, cl >> 3)) = *reinterpret_cast<uint4 *>(h);
-        }
-      }
+      epi.drain(ep, tmem_base + (uint32_t)(a * BN), cstage, bias_s, m0, n0, M, ldc, warp, lane);
       // accumulator drained: hand it back to the MMA warp before the copy-out
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(a));
       epi_bar_sync();  // whole tile staged
-      // coalesced copy-out (+ residual): 16 bytes per thread, ROWS_PER_PASS full rows per pass
-#pragma unroll 1
-      for (int r0 = 0; r0 < BM; r0 += ROWS_PER_PASS) {
-        const int r = r0 + etid / CH, c = etid % CH;
-        const long long mm = m0 + r;
-        if (mm < M) {
-          uint4 v = *reinterpret_cast<const uint4 *>(cstage + cst_off<BN>(r, c));
-          const long long off = mm * ldc + n0 + c * 8;
-          if (ep.residual) {
-            uint4 rv = *reinterpret_cast<const uint4 *>(ep.residual + off);
-            T2 *pv = reinterpret_cast<T2 *>(&v), *pr = reinterpret_cast<T2 *>(&rv);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) pv[e] = __hadd2(pv[e], pr[e]);
-          }
-          *reinterpret_cast<uint4 *>(C + off) = v;
-        }
-      }
+      epi.copy_out(ep, cstage, C, m0, n0, M, ldc, etid);
     }
   }
   tc_fence_before();
@@ -353,6 +427,215 @@ __global__ void __launch_bounds__(THREADS, 1)
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C_::TMEM_COLS);
+  }
+}
+
+// =================================================================================================
+// CTA-pair variant (cta_group::2): two CTAs of a cluster, on the two SMs of a TPC, compute one
+// 256 x BN tile.  CTA r loads rows [m0 + 128 r, +128) of A and rows [n0 + BN/2 r, +BN/2) of B -- half
+// of the B tile each -- and ONE thread of the leader CTA issues tcgen05.mma.cta_group::2 (M = 256),
+// which reads both CTAs' shared memory and accumulates 128 x BN into each CTA's own TMEM.  Operand
+// bytes fetched per FLOP drop from 1/64 (128 x 128 tiles) to 1/128 B (256 x 256): the big vision
+// GEMMs are limited by L2->SM operand traffic (~9.8 TB/s measured), not by the tensor pipe.
+//   full[s]      (leader's copy) : TMA bytes of BOTH CTAs land here (.cta_group::2 loads signal the
+//                                  leader's barrier); the leader arms it with 2 x the per-CTA bytes
+//   empty[s]     (each CTA)      : tcgen05.commit multicast {0,1} frees the slot in both CTAs
+//   acc_full[a]  (each CTA)      : multicast commit after the last k-block of a tile
+//   acc_empty[a] (leader's copy) : 2 x 8 epilogue warps (local + remote arrives) hand TMEM back
+// =================================================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t leader_bar, int c0,
+                                                 int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int BN>
+struct Cfg2 {
+  static constexpr int STAGES = BN >= 256 ? 4 : 6;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;  // this CTA's half of the B tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int CSTAGE_BYTES = BM * BN * 2;
+  static constexpr int BIAS_BYTES = BN * 4;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + CSTAGE_BYTES + BIAS_BYTES + BAR_BYTES + 1024;
+  static constexpr int TMEM_COLS = 2 * BN <= 256 ? 256 : 512;
+  static_assert(STAGE_BYTES % 1024 == 0 && A_BYTES % 1024 == 0, "operand tiles must stay 1024-byte aligned");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+template <typename T, int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+    gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    T *__restrict__ C, long long ldc, long long M, int N, int Kd, Epilogue<T> ep, int num_n_tiles,
+                    int num_tiles) {
+  using C_ = Cfg2<BN>;
+  using T2 = typename Pk<T>::T2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *cstage = smem + C_::STAGES * C_::STAGE_BYTES;
+  float *bias_s = reinterpret_cast<float *>(cstage + C_::CSTAGE_BYTES);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(cstage + C_::CSTAGE_BYTES + C_::BIAS_BYTES);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * C_::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int num_kb = Kd / BK;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C_::STAGES + s); };
+  auto acc_full = [&](int a) { return bar_base + 8u * (2 * C_::STAGES + a); };
+  auto acc_empty = [&](int a) { return bar_base + 8u * (2 * C_::STAGES + 2 + a); };
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+    for (int s = 0; s < C_::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(acc_full(a), 1);
+      mbar_init(acc_empty(a), 2 * EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)C_::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();  // both CTAs' barriers are initialised before any remote signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs; transaction bytes of both land on the leader's barrier) =====
+    if (lane == 0) {
+      uint32_t pre = 0;
+      if (ep.b_frozen && cluster_id < num_tiles) {  // weight tiles ahead of the dependency wait (see gemm_tc_kernel)
+        const int n0 = (cluster_id % num_n_tiles) * BN + (int)rank * (BN / 2);
+        const int npre = num_kb < C_::STAGES ? num_kb : C_::STAGES;
+        for (; (int)pre < npre; ++pre) {
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(pre), 2 * C_::STAGE_BYTES);
+          tma_load_2d_pair(smem_base + pre * C_::STAGE_BYTES + C_::A_BYTES, &map_b, mapa_shared(full_bar(pre), 0),
+                           pre * BK, n0);
+        }
+      }
+      pdl_wait();
+      uint32_t it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m0 = (tile / num_n_tiles) * (2 * BM) + (int)rank * BM;
+        const int n0 = (tile % num_n_tiles) * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % C_::STAGES;
+          const uint32_t ph = (it / C_::STAGES) & 1;
+          const uint32_t lead_full = mapa_shared(full_bar(s), 0);
+          const uint32_t a_dst = smem_base + s * C_::STAGE_BYTES;
+          if (it >= pre) {
+            mbar_wait(empty_bar(s), ph ^ 1);
+            if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * C_::STAGE_BYTES);
+            tma_load_2d_pair(a_dst + C_::A_BYTES, &map_b, lead_full, kb * BK, n0);
+          }
+          tma_load_2d_pair(a_dst, &map_a, lead_full, kb * BK, m0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread of the leader CTA drives both SMs' tensor cores =====
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc(Num<T>::dtype == RPO_BF16 ? 1 : 0, 2 * BM, BN);
+      uint32_t it = 0, t = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++t) {
+        const int a = t & 1;
+        mbar_wait(acc_empty(a), ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(a * BN);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % C_::STAGES;
+          const uint32_t ph = (it / C_::STAGES) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + s * C_::STAGE_BYTES;
+          const uint64_t adesc = make_smem_desc(a_addr);
+          const uint64_t bdesc = make_smem_desc(a_addr + C_::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_f16_pair(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0);
+          umma_commit_pair(empty_bar(s));
+        }
+        umma_commit_pair(acc_full(a));
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs, 128 rows x BN columns each) =====
+    const int etid = threadIdx.x - 64;
+    Epi<T, BN> epi;
+    uint32_t t = 0;
+    pdl_wait();
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++t) {
+      const int a = t & 1;
+      const long long m0 = (long long)(tile / num_n_tiles) * (2 * BM) + (long long)rank * BM;
+      const int n0 = (tile % num_n_tiles) * BN;
+      epi.prefetch(ep, m0, n0, M, ldc, etid);
+      for (int i = etid; i < BN; i += EPI_WARPS * 32) bias_s[i] = ep.bias ? tof<T>(ep.bias[n0 + i]) : 0.f;
+      mbar_wait(acc_full(a), (t >> 1) & 1);
+      tc_fence_after();
+      epi_bar_sync();
+      epi.drain(ep, tmem_base + (uint32_t)(a * BN), cstage, bias_s, m0, n0, M, ldc, warp, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(acc_empty(a), 0));
+      epi_bar_sync();
+      epi.copy_out(ep, cstage, C, m0, n0, M, ldc, etid);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();  // no CTA may free TMEM or exit while its pair still reads its shared memory / signals it
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C_::TMEM_COLS)
+                 : "memory");
   }
 }
 
@@ -407,13 +690,13 @@ static int make_map(CUtensorMap *map, int dtype, const void *ptr, long long rows
   return RPO_OK;
 }
 
-template <typename T, int BN>
+template <typename T, int BN, bool LIGHT>
 static int launch(const T *A, long long lda, const T *B, long long ldb, T *C, long long ldc, long long M, int N,
                   int Kd, const Epilogue<T> &ep, cudaStream_t st) {
-  using C_ = Cfg<BN>;
+  using C_ = Cfg<BN, LIGHT>;
   static bool attr_set = false;
   if (!attr_set) {
-    RPO_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<T, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RPO_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<T, BN, LIGHT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         C_::SMEM_BYTES));
     attr_set = true;
   }
@@ -422,11 +705,79 @@ static int launch(const T *A, long long lda, const T *B, long long ldb, T *C, lo
   RPO_TRY(make_map(&map_b, Num<T>::dtype, B, N, Kd, ldb, BN));
   const int num_n_tiles = N / BN;
   const long long num_tiles = ((M + BM - 1) / BM) * num_n_tiles;
-  const int grid = (int)(num_tiles < sm_count() ? num_tiles : sm_count());
-  gemm_tc_kernel<T, BN><<<grid, THREADS, C_::SMEM_BYTES, st>>>(map_a, map_b, C, ldc, M, N, Kd, ep, num_n_tiles,
-                                                               (int)num_tiles);
+  const long long slots = (long long)sm_count() * C_::MIN_CTAS;
+  const int grid = (int)(num_tiles < slots ? num_tiles : slots);
+  RPO_CHECK_CUDA(launch_pdl(gemm_tc_kernel<T, BN, LIGHT>, dim3(grid), dim3(THREADS), C_::SMEM_BYTES, st, map_a, map_b, C, ldc, M, N,
+                            Kd, ep, num_n_tiles, (int)num_tiles));
   RPO_LAUNCH_CHECK();
   return RPO_OK;
+}
+
+template <typename T, int BN>
+static int launch_pair(const T *A, long long lda, const T *B, long long ldb, T *C, long long ldc, long long M, int N,
+                       int Kd, const Epilogue<T> &ep, cudaStream_t st) {
+  using C_ = Cfg2<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RPO_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<T, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        C_::SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap map_a, map_b;
+  RPO_TRY(make_map(&map_a, Num<T>::dtype, A, M, Kd, lda, BM));
+  RPO_TRY(make_map(&map_b, Num<T>::dtype, B, N, Kd, ldb, BN / 2));
+  const int num_n_tiles = N / BN;
+  const long long num_tiles = ((M + 2 * BM - 1) / (2 * BM)) * num_n_tiles;
+  const int pairs = sm_count() / 2;
+  const int grid = 2 * (int)(num_tiles < pairs ? num_tiles : pairs);
+  prof_tag("gemm2 M=%lld N=%d K=%d BN=%d%s%s%s", M, N, Kd, BN, ep.bias ? " +bias" : "",
+           ep.act == RPO_ACT_QUICKGELU ? " +gelu" : (ep.gelu_grad_aux ? " *gelu'" : ""), ep.residual ? " +res" : "");
+  RPO_CHECK_CUDA(launch_pdl(gemm_tc2_kernel<T, BN>, dim3(grid), dim3(THREADS), C_::SMEM_BYTES, st, map_a, map_b, C, ldc, M, N, Kd,
+                            ep, num_n_tiles, (int)num_tiles));
+  RPO_LAUNCH_CHECK();
+  return RPO_OK;
+}
+
+// ---- tile configuration --------------------------------------------------------------------------
+// P256/P128: CTA pairs, 256 x BN tiles.  S128/S64/S32: one CTA per SM, 128 x BN tiles, deep ring.
+// L64/L32: light 128 x BN tiles, two CTAs per SM.  RPO_GEMM_FORCE=<name> pins one (tuning sweeps).
+enum { CFG_P256 = 0, CFG_P128, CFG_S128, CFG_S64, CFG_S32, CFG_L64, CFG_L32, CFG_COUNT };
+static const char *const kCfgNames[CFG_COUNT] = {"p256", "p128", "s128", "s64", "s32", "l64", "l32"};
+
+static bool cfg_valid(int cfg, int N) {
+  switch (cfg) {
+    case CFG_P256: return N % 256 == 0;
+    case CFG_P128: case CFG_S128: return N % 128 == 0;
+    case CFG_S64: case CFG_L64: return N % 64 == 0;
+    default: return N % 32 == 0;
+  }
+}
+
+static int pick_config(long long M, int N, int Kd) {
+  static const int forced = [] {
+    const char *e = getenv("RPO_GEMM_FORCE");
+    if (e)
+      for (int i = 0; i < CFG_COUNT; ++i)
+        if (strcmp(e, kCfgNames[i]) == 0) return i;
+    return -1;
+  }();
+  if (forced >= 0 && cfg_valid(forced, N)) return forced;
+  // Measured on B200 over the step's shapes (tools/kernel_bench.py with RPO_GEMM_FORCE, profiles/r01_gemm_config_sweep.txt):
+  //  * M >= 5120 (the vision tower's all-row GEMMs): operand traffic from L2 is the limiter, so CTA pairs
+  //    (256 x 256, half the bytes per FLOP) win whenever N or K is long enough to amortise their 2-round tail;
+  //    short N = K = 768 problems are better balanced by 128 x 128 tiles (336 tiles on 148 SMs).
+  //  * smaller M (text tower C*K rows, the prompt-row backward): latency-bound chains -- the light
+  //    128 x 64 configuration (two CTAs per SM) is best or within 5% of best on every such shape; long-K,
+  //    few-tile problems get 128 x 32 tiles to put more SMs on the serial K loop.
+  const long long mt = (M + BM - 1) / BM;
+  if (mt >= 40) {
+    if (N % 256 == 0 && (N >= 2048 || Kd >= 2048)) return CFG_P256;
+    if (N % 128 == 0) return CFG_S128;
+    if (N % 64 == 0) return CFG_S64;
+    return CFG_S32;
+  }
+  if (N % 64 == 0 && !(Kd >= 2048 && mt * (N / 64) < 100)) return CFG_L64;
+  return CFG_L32;
 }
 
 }  // namespace tc
@@ -453,12 +804,16 @@ int gemm_tcgen05(const T *A, long long lda, const T *B, long long ldb, T *C, lon
     if (ep.residual) RPO_REQUIRE(((uintptr_t)ep.residual & 15) == 0, "residual must be 16-byte aligned");
     if (ep.gelu_grad_aux) RPO_REQUIRE(((uintptr_t)ep.gelu_grad_aux & 15) == 0, "aux must be 16-byte aligned");
     if (ep.aux_out) RPO_REQUIRE(((uintptr_t)ep.aux_out & 15) == 0, "aux_out must be 16-byte aligned");
-    // tile width: the widest BN that still gives every SM a tile
-    const long long mt = (M + tc::BM - 1) / tc::BM;
-    const int target = tc::sm_count();
-    if (N % 128 == 0 && mt * (N / 128) >= target) return tc::launch<T, 128>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);
-    if (N % 64 == 0 && mt * (N / 64) >= target) return tc::launch<T, 64>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);
-    return tc::launch<T, 32>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);
+    const int cfg = tc::pick_config(M, N, Kd);
+    switch (cfg) {
+      case tc::CFG_P256: return tc::launch_pair<T, 256>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);
+      case tc::CFG_P128: return tc::launch_pair<T, 128>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);
+      case tc::CFG_S128: return tc::launch<T, 128, false>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);
+      case tc::CFG_S64: return tc::launch<T, 64, false>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);
+      case tc::CFG_S32: return tc::launch<T, 32, false>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);
+      case tc::CFG_L64: return tc::launch<T, 64, true>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);
+      default: return tc::launch<T, 32, true>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);
+    }
   }
 }
 

@@ -99,7 +99,9 @@ def ref_gemm(A, B, bias=None, act=0, residual=None, gelu_aux=None):
 
 
 GEMM_SHAPES = [(7072, 768, 768), (300, 2304, 768), (768, 3072, 768), (768, 768, 3072), (1, 512, 512),
-               (129, 1536, 512), (2400, 128, 2048), (6272, 768, 768), (100, 96, 64)]
+               (129, 1536, 512), (2400, 128, 2048), (6272, 768, 768), (100, 96, 64),
+               # CTA-pair (cta_group::2) tiles: 256 x 256 and 256 x 128, ragged M tails in the second CTA
+               (6304, 2304, 768), (10000, 384, 256), (9999, 128, 64), (2400, 2048, 512)]
 
 
 @pytest.mark.parametrize("prec", ["fp16", "bf16"])
@@ -138,6 +140,37 @@ def test_gemm_epilogues(prec, backend):
     assert relmax(out, ref) <= tol
     # gelu-gradient epilogue of the backward
     out, _ = run_gemm(A, B, prec, backend, gelu_aux=auxg)
+    ref, _ = ref_gemm(A, B, gelu_aux=auxg)
+    assert relmax(out, ref) <= tol
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_gemm_pair_epilogues(prec):
+    """The CTA-pair kernel at the vision tower's real shapes, every fused epilogue."""
+    dt = DT[prec]
+    tol = TOL[prec] * 3
+    M = 7072
+    # c_fc: bias + QuickGELU, pre-activation of the prompt rows (>= 6304) captured
+    A = randn(M, 768, dtype=dt, seed=50)
+    B = randn(3072, 768, dtype=dt, seed=51, scale=768 ** -0.5)
+    bias = randn(3072, dtype=dt, seed=52, scale=0.3)
+    out, aux = run_gemm(A, B, prec, _lib.GEMM_TCGEN05, bias=bias, act=1, aux_row0=6304)
+    ref, pre = ref_gemm(A, B, bias=bias, act=1)
+    assert relmax(out, ref) <= tol
+    assert relmax(aux, pre[6304:]) <= tol
+    # c_proj: bias + residual, long K
+    A = randn(M, 3072, dtype=dt, seed=53)
+    B = randn(768, 3072, dtype=dt, seed=54, scale=3072 ** -0.5)
+    bias = randn(768, dtype=dt, seed=55, scale=0.3)
+    res = randn(M, 768, dtype=dt, seed=56)
+    out, _ = run_gemm(A, B, prec, _lib.GEMM_TCGEN05, bias=bias, residual=res)
+    ref, _ = ref_gemm(A, B, bias=bias, residual=res)
+    assert relmax(out, ref) <= tol
+    # 256 x 128 pair tiles with the gelu-gradient epilogue
+    A = randn(10000, 256, dtype=dt, seed=57)
+    B = randn(384, 256, dtype=dt, seed=58, scale=256 ** -0.5)
+    auxg = randn(10000, 384, dtype=dt, seed=59)
+    out, _ = run_gemm(A, B, prec, _lib.GEMM_TCGEN05, gelu_aux=auxg)
     ref, _ = ref_gemm(A, B, gelu_aux=auxg)
     assert relmax(out, ref) <= tol
 
