@@ -216,16 +216,15 @@ def kernel_rooflines(model, peaks):
 
     def attn(i):
         j = i % nbuf
-        _lib.check(lib.rpo_ro_attention_fwd(qkv[j].data_ptr(), qp[j].data_ptr(), out[j].data_ptr(),
-                                            out[j].data_ptr() + B * S * D * 2, off.data_ptr(), B, K, H, S, 0, 1, code,
-                                            st))
+        _lib.check(lib.rpo_ro_attention_fwd_dense(qkv[j].data_ptr(), qp[j].data_ptr(), out[j].data_ptr(),
+                                                  out[j].data_ptr() + B * S * D * 2, B, S, K, H, code, st))
 
     t_attn = time_kernel(attn, 48)
     L = S + K
     attn_bytes = 2 * (2 * L + 2 * S) * 64 * H * B  # read Q[L], K[S], V[S]; write O[L]; 2 B/elem
     attn_flops = 4 * L * S * 64 * H * B
     roof_attn = {
-        "kernel": "ro_attention_fwd (vision, per layer: 32 images x 12 heads, L=221 queries, S=197 keys)",
+        "kernel": "ro_attn_fwd_tc = rpo_ro_attention_fwd_dense (tcgen05; vision, per layer: 32 images x 12 heads, L=221 queries, S=197 keys)",
         "bound": "hbm", "achieved": attn_bytes / t_attn / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
         "frac": attn_bytes / t_attn / 1e9 / peaks["hbm"], "traffic": None,
         "peak_source": f"{peaks['source']} copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",

@@ -149,6 +149,13 @@ int rpo_gemm_bias_act(const void *A, int64_t lda, const void *B, int64_t ldb, vo
 int rpo_ro_attention_fwd(const void *qkv_ctx, const void *q_prompt, void *out_ctx, void *out_prompt,
                          const int32_t *ctx_off, int32_t G, int32_t K, int32_t H, int32_t max_ctx, int32_t causal,
                          int32_t do_ctx, int32_t dtype, void *stream);
+/* Same contract for the vision tower's shape -- every group has exactly n_ctx context rows, no causal
+ * mask (visual_mask, trainers/rpo.py:153-159), context and prompt rows all queries -- on the tcgen05
+ * path: TMA-staged Q/K/V, S = QK^T and O = PV as tcgen05.mma with TMEM accumulators, one softmax
+ * thread per query row.  16-bit dtypes; n_ctx <= 256 and (n_ctx % 128) + K <= 128 (returns
+ * RPO_ERR_INVALID otherwise: use rpo_ro_attention_fwd).  qkv_ctx [G*n_ctx, 3D], q_prompt [G*K, D]. */
+int rpo_ro_attention_fwd_dense(const void *qkv_ctx, const void *q_prompt, void *out_ctx, void *out_prompt, int32_t G,
+                               int32_t n_ctx, int32_t K, int32_t H, int32_t dtype, void *stream);
 /* gradient w.r.t. the prompt queries only (keys/values come from rows that carry no gradient):
  * dq_prompt [G*K, D] from d_out_prompt [G*K, D]; out_prompt is the forward output of the same rows
  * (used for the softmax-gradient row term sum_d dO*O). */

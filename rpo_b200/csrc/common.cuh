@@ -219,6 +219,11 @@ int layernorm_bwd(const T *dy, const T *x, const float *w, const T *dres, T *dx,
 template <typename T>
 int ro_attention_fwd(const T *qkv_ctx, const T *q_prompt, T *out_ctx, T *out_prompt, const int *ctx_off, int G, int K,
                      int H, int max_ctx, int causal, int do_ctx, cudaStream_t st);
+// tcgen05 forward for uniform groups without causal mask (the vision tower): attention_tc.cu
+bool ro_attention_fwd_dense_supported(int dtype, int n, int K, int H);
+template <typename T>
+int ro_attention_fwd_dense(const T *qkv_ctx, const T *q_prompt, T *out_ctx, T *out_prompt, int G, int n, int K, int H,
+                           cudaStream_t st);
 template <typename T>
 int ro_attention_bwd(const T *qkv_ctx, const T *q_prompt, const T *o_prompt, const T *d_out, T *dq, const int *ctx_off,
                      int G, int K, int H, int max_ctx, cudaStream_t st);

@@ -76,6 +76,7 @@ struct Arena {
 struct Tower {
   int D = 0, H = 0, layers = 0, K = 0, causal = 0;
   int G = 0, Gmax = 0, max_ctx = 0;
+  int uniform_n = 0;  // > 0: every group has exactly this many context rows (vision tower)
   long long Mc = 0, Mc_max = 0, Mp_max = 0, Mtot_max = 0;
   int *ctx_off = nullptr;  // device [Gmax+1]
   // per-layer saved activations
@@ -171,8 +172,12 @@ static int tower_forward(RpoHandle *hd, Tower &tw, bool do_ctx, bool do_prompt, 
       ep.bias = (const T *)bw.in_b;
       RPO_TRY(gemm_dispatch<T>(backend, h + Mc * D, D, (const T *)bw.in_w, D, qp, D, Mp, D, D, ep, st));
     }
-    RPO_TRY(ro_attention_fwd<T>(qkv, qp, o, o + Mc * D, tw.ctx_off, tw.G, do_prompt ? tw.K : 0, tw.H, tw.max_ctx,
-                                tw.causal, do_ctx ? 1 : 0, st));
+    if (do_ctx && do_prompt && tw.uniform_n > 0 && !tw.causal &&
+        ro_attention_fwd_dense_supported(Num<T>::dtype, tw.uniform_n, tw.K, tw.H))
+      RPO_TRY(ro_attention_fwd_dense<T>(qkv, qp, o, o + Mc * D, tw.G, tw.uniform_n, tw.K, tw.H, st));
+    else
+      RPO_TRY(ro_attention_fwd<T>(qkv, qp, o, o + Mc * D, tw.ctx_off, tw.G, do_prompt ? tw.K : 0, tw.H, tw.max_ctx,
+                                  tw.causal, do_ctx ? 1 : 0, st));
     ep = frozen_ep<T>();
     ep.bias = (const T *)bw.out_b;
     ep.residual = x_in + r0 * D;
@@ -467,7 +472,7 @@ int rpo_create(const RpoConfig *cfg, RpoHandle **out) {
   h->pk_pad = (c.dtype == RPO_F32) ? h->pk : (h->pk + 63) / 64 * 64;
   Tower &v = h->vis, &t = h->txt;
   v.D = c.v_width; v.H = c.v_heads; v.layers = c.v_layers; v.K = c.K; v.causal = 0;
-  v.Gmax = c.max_batch; v.max_ctx = h->S;
+  v.Gmax = c.max_batch; v.max_ctx = h->S; v.uniform_n = h->S;
   v.Mc_max = (long long)c.max_batch * h->S; v.Mp_max = (long long)c.max_batch * c.K; v.Mtot_max = v.Mc_max + v.Mp_max;
   t.D = c.t_width; t.H = c.t_heads; t.layers = c.t_layers; t.K = c.K; t.causal = 1;
   t.Gmax = c.n_cls; t.G = c.n_cls; t.max_ctx = c.ctx_len;
@@ -786,6 +791,20 @@ int rpo_ro_attention_fwd(const void *qkv_ctx, const void *q_prompt, void *out_ct
   RPO_REQUIRE(!do_ctx || out_ctx, "context output buffer");
   DISPATCH(dtype, (ro_attention_fwd<T>((const T *)qkv_ctx, (const T *)q_prompt, (T *)out_ctx, (T *)out_prompt, ctx_off,
                                        G, K, H, max_ctx, causal, do_ctx, (cudaStream_t)stream)));
+}
+
+int rpo_ro_attention_fwd_dense(const void *qkv_ctx, const void *q_prompt, void *out_ctx, void *out_prompt, int32_t G,
+                               int32_t n_ctx, int32_t K, int32_t H, int32_t dtype, void *stream) {
+  RPO_REQUIRE(qkv_ctx && out_ctx, "null argument");
+  RPO_REQUIRE(K == 0 || (q_prompt && out_prompt), "prompt buffers");
+  RPO_REQUIRE(dtype == RPO_F16 || dtype == RPO_BF16, "the tcgen05 attention needs a 16-bit dtype");
+  RPO_REQUIRE(ro_attention_fwd_dense_supported(dtype, n_ctx, K, H), "shape not supported by the tcgen05 attention");
+  if (dtype == RPO_F16)
+    return ro_attention_fwd_dense<__half>((const __half *)qkv_ctx, (const __half *)q_prompt, (__half *)out_ctx,
+                                          (__half *)out_prompt, G, n_ctx, K, H, (cudaStream_t)stream);
+  return ro_attention_fwd_dense<__nv_bfloat16>((const __nv_bfloat16 *)qkv_ctx, (const __nv_bfloat16 *)q_prompt,
+                                               (__nv_bfloat16 *)out_ctx, (__nv_bfloat16 *)out_prompt, G, n_ctx, K, H,
+                                               (cudaStream_t)stream);
 }
 
 int rpo_ro_attention_bwd(const void *qkv_ctx, const void *q_prompt, const void *out_prompt, const void *d_out_prompt,

@@ -272,6 +272,59 @@ def test_ro_attention_fwd_bwd(prec, case):
     assert relmax(dq.cpu(), qpr.grad) <= tol
 
 
+DENSE_CASES = [
+    # (name, G, n_ctx, K, H): the vision tower's shapes and the edges of what the tcgen05 kernel accepts
+    ("vitb16_k24", 3, 197, 24, 12), ("vitb16_k4", 2, 197, 4, 12), ("vitb16_k48", 2, 197, 48, 12),
+    ("one_tile", 2, 50, 24, 2), ("exact_128", 2, 128, 16, 2), ("n256", 2, 256, 100, 1), ("tiny", 1, 17, 5, 2),
+    ("no_prompts", 2, 197, 0, 2),
+]
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("case", DENSE_CASES, ids=[c[0] for c in DENSE_CASES])
+def test_ro_attention_fwd_dense_tcgen05(prec, case):
+    """The tcgen05 attention (vision form) against the fp32 reference and against the mma.sync kernel."""
+    lib = _lib.load()
+    _, G, n, K, H = case
+    dt = DT[prec]
+    D = H * 64
+    off = [g * n for g in range(G + 1)]
+    qkv = randn(G * n, 3 * D, dtype=dt, seed=60)
+    qp = randn(max(1, G * K), D, dtype=dt, seed=61)
+    out_ctx = torch.zeros(G * n, D, dtype=dt, device=dev())
+    out_p = torch.full((max(1, G * K), D), 7.0, dtype=dt, device=dev())
+    code = _lib.dtype_code(dt)
+    _lib.check(lib.rpo_ro_attention_fwd_dense(qkv.data_ptr(), qp.data_ptr(), out_ctx.data_ptr(), out_p.data_ptr(), G, n,
+                                              K, H, code, st()))
+    torch.cuda.synchronize()
+    rc, rp = ref_attention(qkv.cpu(), qp.cpu()[:G * K], off, K, H, 0, True)
+    tol = TOL[prec] * 2
+    assert relmax(out_ctx.cpu(), rc) <= tol
+    if K:
+        assert relmax(out_p.cpu()[:G * K], rp) <= tol
+    # cross-check with the mma.sync path on identical inputs
+    off_d = torch.tensor(off, dtype=torch.int32, device=dev())
+    oc2 = torch.zeros_like(out_ctx)
+    op2 = torch.zeros_like(out_p)
+    _lib.check(lib.rpo_ro_attention_fwd(qkv.data_ptr(), qp.data_ptr(), oc2.data_ptr(), op2.data_ptr(), off_d.data_ptr(),
+                                        G, K, H, n, 0, 1, code, st()))
+    assert relmax(out_ctx, oc2) <= tol
+
+
+def test_ro_attention_fwd_dense_rejects_unsupported():
+    lib = _lib.load()
+    x = torch.zeros(8, dtype=torch.float16, device=dev())
+    # 257 context rows (ViT-L/14) need two UMMA N blocks: not on this path
+    assert lib.rpo_ro_attention_fwd_dense(x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), 1, 257, 24, 16,
+                                          _lib.RPO_F16, st()) == -1
+    # prompts that would straddle two query tiles
+    assert lib.rpo_ro_attention_fwd_dense(x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), 1, 197, 64, 12,
+                                          _lib.RPO_F16, st()) == -1
+    # fp32 goes through the exact SIMT kernels
+    assert lib.rpo_ro_attention_fwd_dense(x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), 1, 197, 24, 12,
+                                          _lib.RPO_F32, st()) == -1
+
+
 # ---------------------------------------------------------------------------------------------------
 def ref_logits(img_feat, text_feat, logit_scale, K):
     i = img_feat.float()

@@ -24,15 +24,31 @@ def peaks():
     return 6650.0, 1590.0
 
 
+USE_GRAPH = True
+
+
 def timeit(fn, iters=40, warm=5):
+    """Seconds per launch.  The `iters` launches are captured into ONE CUDA graph (as the training step is), so
+    host-side costs -- ctypes, tensor-map encoding, launch -- are outside the measurement."""
     for i in range(warm):
         fn(i)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(iters):
-        fn(i)
-    e1.record()
+    if USE_GRAPH:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for i in range(iters):
+                fn(i)
+        g.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        g.replay()
+        e1.record()
+    else:
+        e0.record()
+        for i in range(iters):
+            fn(i)
+        e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters * 1e-3
 
@@ -43,11 +59,15 @@ def main():
     ap.add_argument("--tag", default="")
     ap.add_argument("--cublas", action="store_true", help="also time torch.matmul (cuBLAS) on each GEMM shape")
     ap.add_argument("--only", default="", help="comma list: gemm,attn,ln")
+    ap.add_argument("--no-dense", action="store_true", help="vision attention through the mma.sync kernel")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches (host-bound for short kernels)")
+    ap.add_argument("--nbuf", type=int, default=0, help="override the number of rotated buffers (1 = warm L2)")
     a = ap.parse_args()
+    global USE_GRAPH
+    USE_GRAPH = not a.no_graph
     dt = {"fp16": torch.float16, "bf16": torch.bfloat16}[a.prec]
     lib = _lib.load()
     dev = torch.device("cuda:0")
-    st = _lib.stream_ptr(dev)
     code = _lib.dtype_code(dt)
     hbm, tf = peaks()
     g = torch.Generator(device="cpu").manual_seed(0)
@@ -70,7 +90,7 @@ def main():
         shapes = []
     for label, M, N, Kd, has_bias, act, has_res, has_aux in shapes:
         per = (M * Kd + N * Kd + M * N * (1 + has_res + has_aux)) * 2
-        nbuf = max(2, min(12, int(300e6 // per) + 1))
+        nbuf = a.nbuf or max(2, min(12, int(300e6 // per) + 1))
         A = [torch.randn(M, Kd, generator=g).to(dt).to(dev) for _ in range(nbuf)]
         W = [(torch.randn(N, Kd, generator=g) * Kd ** -0.5).to(dt).to(dev) for _ in range(nbuf)]
         Cm = [torch.empty(M, N, dtype=dt, device=dev) for _ in range(nbuf)]
@@ -82,7 +102,7 @@ def main():
             j = i % nbuf
             _lib.check(lib.rpo_gemm_bias_act(A[j].data_ptr(), Kd, W[j].data_ptr(), Kd, Cm[j].data_ptr(), N, M, N, Kd,
                                              _lib.ptr(bias), act, _lib.ptr(res[j]) if res else None,
-                                             _lib.ptr(aux[j]) if aux else None, None, 0, code, _lib.GEMM_AUTO, st))
+                                             _lib.ptr(aux[j]) if aux else None, None, 0, code, _lib.GEMM_AUTO, _lib.stream_ptr(dev)))
 
         t = timeit(fn)
         fl = 2.0 * M * N * Kd
@@ -97,7 +117,7 @@ def main():
                                       if "attn" in only else []):
         D = H * 64
         L = (n if do_ctx else 0) + K
-        nbuf = 10
+        nbuf = a.nbuf or 10
         qkv = [torch.randn(G * n, 3 * D, generator=g).to(dt).to(dev) for _ in range(nbuf)]
         qp = [torch.randn(G * K, D, generator=g).to(dt).to(dev) for _ in range(nbuf)]
         oc = [torch.empty(G * n, D, dtype=dt, device=dev) for _ in range(nbuf)]
@@ -105,16 +125,23 @@ def main():
         dq = [torch.empty(G * K, D, dtype=dt, device=dev) for _ in range(nbuf)]
         off = torch.arange(0, (G + 1) * n, n, dtype=torch.int32, device=dev)
 
+        dense = do_ctx and not a.no_dense
+
         def fwd(i):
             j = i % nbuf
-            _lib.check(lib.rpo_ro_attention_fwd(qkv[j].data_ptr(), qp[j].data_ptr(), oc[j].data_ptr(), op[j].data_ptr(),
-                                                off.data_ptr(), G, K, H, n, 0, do_ctx, code, st))
+            if dense:
+                _lib.check(lib.rpo_ro_attention_fwd_dense(qkv[j].data_ptr(), qp[j].data_ptr(), oc[j].data_ptr(),
+                                                          op[j].data_ptr(), G, n, K, H, code, _lib.stream_ptr(dev)))
+            else:
+                _lib.check(lib.rpo_ro_attention_fwd(qkv[j].data_ptr(), qp[j].data_ptr(), oc[j].data_ptr(),
+                                                    op[j].data_ptr(), off.data_ptr(), G, K, H, n, 0, do_ctx, code,
+                                                    _lib.stream_ptr(dev)))
 
         def bwd(i):
             j = i % nbuf
             _lib.check(lib.rpo_ro_attention_bwd(qkv[j].data_ptr(), qp[j].data_ptr(), op[j].data_ptr(),
                                                 qp[(j + 1) % nbuf].data_ptr(), dq[j].data_ptr(), off.data_ptr(), G, K, H,
-                                                n, code, st))
+                                                n, code, _lib.stream_ptr(dev)))
 
         t = timeit(fwd)
         by = 2 * (2 * L + 2 * n) * 64 * H * G
@@ -129,7 +156,7 @@ def main():
 
     # LayerNorm forward
     for rows, D in ([(7072, 768), (2400, 512), (768, 768)] if "ln" in only else []):
-        nbuf = 12
+        nbuf = a.nbuf or 12
         x = [torch.randn(rows, D, generator=g).to(dt).to(dev) for _ in range(nbuf)]
         y = [torch.empty(rows, D, dtype=dt, device=dev) for _ in range(nbuf)]
         w = torch.ones(D, dtype=torch.float32, device=dev)
@@ -138,7 +165,7 @@ def main():
         def ln(i):
             j = i % nbuf
             _lib.check(lib.rpo_layernorm_fwd(x[j].data_ptr(), w.data_ptr(), b.data_ptr(), y[j].data_ptr(), rows, D,
-                                             code, st))
+                                             code, _lib.stream_ptr(dev)))
 
         t = timeit(ln)
         by = 2 * rows * D * 2
