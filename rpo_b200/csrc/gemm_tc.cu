@@ -35,17 +35,27 @@ static constexpr int EPI_WARPS = 8;
 static constexpr int THREADS = 64 + EPI_WARPS * 32;  // producer warp + MMA warp + epilogue warps
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
 
+// output staging geometry of the epilogue (see Epi below)
+template <int BN>
+struct EpiGeo {
+  static constexpr int SLAB = BN >= 64 ? 64 : 32;
+  static constexpr int NSLAB = BN / SLAB;
+  static constexpr int NBUF = NSLAB > 1 ? 2 : 1;
+  static constexpr int SLAB_BYTES = BM * SLAB * 2;
+  static constexpr int CSTAGE_BYTES = NBUF * SLAB_BYTES;
+};
+
 // LIGHT configurations keep shared memory under half an SM (and TMEM at <= 128 columns) so that two
 // CTAs -- of the same launch or of kernels running on the other stream -- share an SM: the small-M
 // GEMM chains (text tower, backward) are latency-bound, and a second resident CTA hides it.
 template <int BN, bool LIGHT>
 struct Cfg {
-  static constexpr int STAGES = LIGHT ? (BN == 64 ? 3 : 4) : (BN >= 128 ? 5 : (BN == 64 ? 6 : 8));
+  static constexpr int STAGES = LIGHT ? (BN == 64 ? 3 : 5) : (BN >= 128 ? 6 : 8);
   static constexpr int MIN_CTAS = LIGHT ? 2 : 1;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int CSTAGE_BYTES = BM * BN * 2;  // output tile staging (16-bit)
+  static constexpr int CSTAGE_BYTES = EpiGeo<BN>::CSTAGE_BYTES;  // output slab staging (16-bit)
   static constexpr int BIAS_BYTES = BN * 4;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + CSTAGE_BYTES + BIAS_BYTES + BAR_BYTES + 1024;
@@ -89,99 +99,118 @@ __device__ __forceinline__ typename Pk<T>::T2 quickgelu2(typename Pk<T>::T2 x) {
   return __hmul2(x, s);
 }
 
-// byte offset of 16-byte chunk c of row r in the swizzled [BM][BN] 16-bit staging tile
-template <int BN>
-__device__ __forceinline__ uint32_t cst_off(int r, int c) {
-  constexpr int CH = BN / 8;  // chunks per row
-  return (uint32_t)(r * (BN * 2) + ((c ^ (r & (CH - 1) & 7)) << 4));
+// ---- epilogue of one 128 x BN accumulator tile (shared by the single-CTA and the CTA-pair kernel) ------
+// The tile leaves in SLABS of 64 columns through a double-buffered 16 KB staging area, so that shared
+// memory goes to the operand ring (the main loop is bound by TMA latency x bytes in flight: 6 stages of
+// 32 KB instead of 4 is ~1.4x on the big GEMMs).  Per slab:
+//   prefetch : residual rows -- or gelu' auxiliary rows -- of the NEXT slab in the coalesced copy-out
+//              layout (16 bytes per thread and pass), so their L2/HBM round trip hides behind the drain
+//   drain    : tcgen05.ld 32 accumulator columns per warp (8 warps = 4 TMEM lane quarters x 2 column
+//              halves), bias in f32, ONE rounding to the dtype (the nn.Linear output tensor), QuickGELU in
+//              packed 16-bit math, 16-byte stores into the XOR-swizzled staging slab
+//   copy-out : 16-byte coalesced global stores (full 128-byte row segments), applying gelu'(aux) in f32 /
+//              adding the residual from the prefetched registers.
+// One named barrier per slab: slab s+2 reuses the buffer of slab s, and every thread has left copy-out(s)
+// before it arrives at the barrier after drain(s+1).
+
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4 &v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
 }
 
-// ---- epilogue of one 128 x BN accumulator tile (shared by the single-CTA and the CTA-pair kernel) ------
-// Phase 0 (before the accumulator is ready, i.e. hidden behind the main loop): prefetch this tile's
-//          residual rows -- or the gelu' auxiliary rows -- in the COALESCED copy-out layout
-//          (16 bytes per thread, BN/16 rows per thread).  Loading them inside the copy-out loop
-//          serialises one L2/HBM round trip per pass; loading them per accumulator row in the
-//          drain loop is uncoalesced (lane = row).
-// Phase 1: drain TMEM (tcgen05.ld 32 columns at a time), bias in f32, ONE rounding to the dtype,
-//          QuickGELU in packed 16-bit math, stage into swizzled shared memory.
-// Phase 2: hand the accumulator back to the MMA warp, then copy out with 16-byte coalesced stores,
-//          applying gelu'(aux) (f32 math) / adding the residual from the prefetched registers.
 template <typename T, int BN>
 struct Epi {
   using T2 = typename Pk<T>::T2;
-  static constexpr int CH = BN / 8;                          // 16-byte chunks per staged row
+  using G = EpiGeo<BN>;
+  static constexpr int SLAB = G::SLAB;
+  static constexpr int CH = SLAB / 8;                        // 16-byte chunks per staged row
   static constexpr int ROWS_PER_PASS = (EPI_WARPS * 32) / CH;
-  static constexpr int PASSES = BM / ROWS_PER_PASS;          // BN / 16
-  static constexpr int HALVES = BN >= 64 ? 2 : 1;            // BN = 32: one 32-column tcgen05.ld covers the tile
-  static constexpr int COLS_PER_WARP = BN / HALVES;
+  static constexpr int PASSES = BM / ROWS_PER_PASS;
+  static constexpr int DRAIN_HALVES = SLAB / 32;             // warps with half_id >= this idle in the drain
 
-  uint4 pre[PASSES];
+  static __device__ __forceinline__ uint32_t st_off(int r, int c) {
+    return (uint32_t)(r * (SLAB * 2) + ((c ^ (r & (CH - 1))) << 4));
+  }
 
-  __device__ __forceinline__ void prefetch(const Epilogue<T> &ep, long long m0, int n0, long long M, long long ldc,
-                                           int etid) {
-    const T *src = ep.residual ? ep.residual : ep.gelu_grad_aux;
-    if (!src) return;
+  // per-tile, per-thread constants (everything below is 32-bit arithmetic on them)
+  int rows_valid;   // rows of this tile inside M (1..128)
+  int aux_r0;       // first tile-local row whose pre-activation goes to aux_out (>= 128: none)
+  long long pass_stride;  // elements between the rows of consecutive copy-out passes
+  const T *src_row;  // residual / gelu' aux: row (etid / CH) of the tile, column chunk (etid % CH)
+  T *dst_row;        // C: same position
+
+  __device__ __forceinline__ void prefetch(int sc, int r0, uint4 (&pre)[PASSES]) {
+    if (!src_row) return;
+    const T *p = src_row + sc;
 #pragma unroll
     for (int i = 0; i < PASSES; ++i) {
-      const int r = i * ROWS_PER_PASS + etid / CH, c = etid % CH;
-      const long long mm = m0 + r;
       pre[i] = make_uint4(0u, 0u, 0u, 0u);
-      if (mm < M) pre[i] = __ldg(reinterpret_cast<const uint4 *>(src + mm * ldc + n0 + c * 8));
+      if (r0 + i * ROWS_PER_PASS < rows_valid) pre[i] = __ldg(reinterpret_cast<const uint4 *>(p));
+      p += pass_stride;
     }
   }
 
-  // TMEM accumulator `tmem_acc` (lane/column base of this tile's accumulator) -> staged tile
-  __device__ __forceinline__ void drain(const Epilogue<T> &ep, uint32_t tmem_acc, uint8_t *cstage, const float *bias_s,
-                                        long long m0, int n0, long long M, long long ldc, int warp, int lane) {
+  // 32 accumulator columns of this warp's 32 rows -> staging slab.  sc0: first column of the slab inside the tile
+  __device__ __forceinline__ void drain(const Epilogue<T> &ep, uint32_t tmem_acc, uint32_t slab, uint32_t bias_s,
+                                        long long m0, int n0, int sc0, long long ldc, int warp, int lane) {
     const int q = warp & 3;
     const int half_id = (warp - 2) >> 2;
+    if (half_id >= DRAIN_HALVES) return;
     const int r_loc = q * 32 + lane;
-    const long long m = m0 + r_loc;
-    const bool aux_inline = ep.gelu_grad_aux && ep.residual;  // both: registers hold the residual
-#pragma unroll 1
-    for (int cc = 0; cc < (half_id < HALVES ? COLS_PER_WARP : 0); cc += 32) {
-      const int c0 = half_id * COLS_PER_WARP + cc;
-      uint32_t acc[32];
-      tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
+    const int c0 = sc0 + half_id * 32;  // tile-local first column of this warp's 32
+    uint32_t acc[32];
+    tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
+    __align__(16) T2 h[16];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float4 b4 = lds_f32x4(bias_s + (uint32_t)((c0 + g * 4) * 4));
+      h[2 * g] = Pk<T>::from_floats(__uint_as_float(acc[g * 4]) + b4.x, __uint_as_float(acc[g * 4 + 1]) + b4.y);
+      h[2 * g + 1] = Pk<T>::from_floats(__uint_as_float(acc[g * 4 + 2]) + b4.z, __uint_as_float(acc[g * 4 + 3]) + b4.w);
+    }
+    if (r_loc >= aux_r0 && r_loc < rows_valid) {  // pre-activation of the prompt rows (forward c_fc only)
+      T *ao = ep.aux_out + (m0 + r_loc - ep.aux_row0) * ldc + n0 + c0;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4 *>(ao + g * 8) = *reinterpret_cast<uint4 *>(&h[4 * g]);
+    }
+    if (ep.act == RPO_ACT_QUICKGELU) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) h[e] = quickgelu2<T>(h[e]);
+    }
+    if (ep.gelu_grad_aux && ep.residual && r_loc < rows_valid) {  // both: the prefetch registers hold the residual
+      const T *ax = ep.gelu_grad_aux + (m0 + r_loc) * ldc + n0 + c0;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        const int cl = c0 + g * 8;  // tile-local column of this 16-byte group
-        __align__(16) T2 h[4];
+        Vec16<T> aux = ld16(ax + g * 8);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float2 b2 = *reinterpret_cast<const float2 *>(bias_s + cl + 2 * e);
-          h[e] = Pk<T>::from_floats(__uint_as_float(acc[g * 8 + 2 * e]) + b2.x,
-                                    __uint_as_float(acc[g * 8 + 2 * e + 1]) + b2.y);
+          const T *hv = reinterpret_cast<const T *>(&h[4 * g + e]);
+          h[4 * g + e] = Pk<T>::from_floats(tof<T>(hv[0]) * quickgelu_grad(tof<T>(aux.v[2 * e])),
+                                            tof<T>(hv[1]) * quickgelu_grad(tof<T>(aux.v[2 * e + 1])));
         }
-        if (ep.aux_out && m >= ep.aux_row0 && m < M)
-          *reinterpret_cast<uint4 *>(ep.aux_out + (m - ep.aux_row0) * ldc + n0 + cl) = *reinterpret_cast<uint4 *>(h);
-        if (ep.act == RPO_ACT_QUICKGELU) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) h[e] = quickgelu2<T>(h[e]);
-        }
-        if (aux_inline && m < M) {
-          Vec16<T> aux = ld16(ep.gelu_grad_aux + m * ldc + n0 + cl);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float2 v = make_float2(tof<T>(reinterpret_cast<T *>(&h[e])[0]), tof<T>(reinterpret_cast<T *>(&h[e])[1]));
-            h[e] = Pk<T>::from_floats(v.x * quickgelu_grad(tof<T>(aux.v[2 * e])),
-                                      v.y * quickgelu_grad(tof<T>(aux.v[2 * e + 1])));
-          }
-        }
-        *reinterpret_cast<uint4 *>(cstage + cst_off<BN>(r_loc, cl >> 3)) = *reinterpret_cast<uint4 *>(h);
       }
     }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) sts128(slab + st_off(r_loc, half_id * 4 + g), *reinterpret_cast<uint4 *>(&h[4 * g]));
   }
 
-  __device__ __forceinline__ void copy_out(const Epilogue<T> &ep, const uint8_t *cstage, T *__restrict__ C,
-                                           long long m0, int n0, long long M, long long ldc, int etid) {
+  __device__ __forceinline__ void copy_out(const Epilogue<T> &ep, uint32_t slab, int sc, int r0, int c, uint4 (&pre)[PASSES]) {
     const bool aux_pre = ep.gelu_grad_aux && !ep.residual;
+    const bool res = ep.residual != nullptr;
+    T *p = dst_row + sc;
 #pragma unroll
     for (int i = 0; i < PASSES; ++i) {
-      const int r = i * ROWS_PER_PASS + etid / CH, c = etid % CH;
-      const long long mm = m0 + r;
-      if (mm < M) {
-        uint4 v = *reinterpret_cast<const uint4 *>(cstage + cst_off<BN>(r, c));
+      const int r = r0 + i * ROWS_PER_PASS;
+      if (r < rows_valid) {
+        uint4 v = lds128(slab + st_off(r, c));
         T2 *pv = reinterpret_cast<T2 *>(&v), *pp = reinterpret_cast<T2 *>(&pre[i]);
         if (aux_pre) {
 #pragma unroll
@@ -191,12 +220,56 @@ struct Epi {
                                        tof<T>(hv[1]) * quickgelu_grad(tof<T>(av[1])));
           }
         }
-        if (ep.residual) {
+        if (res) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) pv[e] = __hadd2(pv[e], pp[e]);
         }
-        *reinterpret_cast<uint4 *>(C + mm * ldc + n0 + c * 8) = v;
+        *reinterpret_cast<uint4 *>(p) = v;
       }
+      p += pass_stride;
+    }
+  }
+
+  // Whole tile.  `arrive_acc_empty` hands the accumulator back to the MMA warp (called by one lane per warp).
+  template <typename Arrive>
+  __device__ __forceinline__ void run_tile(const Epilogue<T> &ep, uint32_t tmem_acc, uint32_t cstage, uint32_t bias_s,
+                                           T *__restrict__ C, long long m0, int n0, long long M, long long ldc,
+                                           uint32_t acc_full_bar, uint32_t acc_full_parity, Arrive arrive_acc_empty) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int etid = threadIdx.x - 64;
+    const int r0 = etid / CH, c = etid % CH;
+    rows_valid = (int)(M - m0 < BM ? M - m0 : BM);
+    aux_r0 = BM;
+    if (ep.aux_out) aux_r0 = ep.aux_row0 > m0 ? (ep.aux_row0 - m0 < BM ? (int)(ep.aux_row0 - m0) : BM) : 0;
+    pass_stride = (long long)ROWS_PER_PASS * ldc;
+    const long long pos = (m0 + r0) * ldc + n0 + c * 8;
+    const T *src = ep.residual ? ep.residual : ep.gelu_grad_aux;
+    src_row = src ? src + pos : nullptr;
+    dst_row = C + pos;
+    uint4 pre[PASSES], nxt[PASSES];
+    prefetch(0, r0, pre);
+    for (int i = etid; i < BN; i += EPI_WARPS * 32) {
+      const float bv = ep.bias ? tof<T>(ep.bias[n0 + i]) : 0.f;
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + (uint32_t)(i * 4)), "f"(bv) : "memory");
+    }
+    mbar_wait(acc_full_bar, acc_full_parity);
+    tc_fence_after();
+    epi_bar_sync();  // bias visible; the last copy-out of the previous tile is finished
+#pragma unroll 1
+    for (int sl = 0; sl < G::NSLAB; ++sl) {
+      const uint32_t slab = cstage + (uint32_t)((sl % G::NBUF) * G::SLAB_BYTES);
+      drain(ep, tmem_acc, slab, bias_s, m0, n0, sl * SLAB, ldc, warp, lane);
+      if (sl == G::NSLAB - 1) {  // accumulator drained: hand it back before the last copy-out
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive_acc_empty();
+      } else {
+        prefetch((sl + 1) * SLAB, r0, nxt);
+      }
+      epi_bar_sync();  // slab staged
+      copy_out(ep, slab, sl * SLAB, r0, c, pre);
+#pragma unroll
+      for (int i = 0; i < PASSES; ++i) pre[i] = nxt[i];
     }
   }
 };
@@ -309,7 +382,6 @@ __global__ void __launch_bounds__(THREADS, (Cfg<BN, LIGHT>::MIN_CTAS))
     }
   } else {
     // ===== epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
-    const int etid = threadIdx.x - 64;  // 0..255
     Epi<T, BN> epi;
     uint32_t t = 0;
     pdl_wait();  // residual / aux rows come from upstream kernels; C may still be read by them
@@ -317,18 +389,9 @@ __global__ void __launch_bounds__(THREADS, (Cfg<BN, LIGHT>::MIN_CTAS))
       const int a = t & 1;
       const long long m0 = (long long)(tile / num_n_tiles) * BM;
       const int n0 = (tile % num_n_tiles) * BN;
-      epi.prefetch(ep, m0, n0, M, ldc, etid);
-      if (etid < BN) bias_s[etid] = ep.bias ? tof<T>(ep.bias[n0 + etid]) : 0.f;
-      mbar_wait(acc_full(a), (t >> 1) & 1);
-      tc_fence_after();
-      epi_bar_sync();  // staging tile free (previous copy-out done) and bias visible
-      epi.drain(ep, tmem_base + (uint32_t)(a * BN), cstage, bias_s, m0, n0, M, ldc, warp, lane);
-      // accumulator drained: hand it back to the MMA warp before the copy-out
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty(a));
-      epi_bar_sync();  // whole tile staged
-      epi.copy_out(ep, cstage, C, m0, n0, M, ldc, etid);
+      const uint32_t empty_a = acc_empty(a);
+      epi.run_tile(ep, tmem_base + (uint32_t)(a * BN), smem_u32(cstage), smem_u32(bias_s), C, m0, n0, M, ldc, acc_full(a), (t >> 1) & 1,
+                   [&]() { mbar_arrive(empty_a); });
     }
   }
   tc_fence_before();
@@ -393,11 +456,11 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, u
 
 template <int BN>
 struct Cfg2 {
-  static constexpr int STAGES = BN >= 256 ? 4 : 6;
+  static constexpr int STAGES = BN >= 256 ? 6 : 8;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / 2) * BK * 2;  // this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int CSTAGE_BYTES = BM * BN * 2;
+  static constexpr int CSTAGE_BYTES = EpiGeo<BN>::CSTAGE_BYTES;
   static constexpr int BIAS_BYTES = BN * 4;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + CSTAGE_BYTES + BIAS_BYTES + BAR_BYTES + 1024;
@@ -518,7 +581,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
     }
   } else {
     // ===== epilogue (both CTAs, 128 rows x BN columns each) =====
-    const int etid = threadIdx.x - 64;
     Epi<T, BN> epi;
     uint32_t t = 0;
     pdl_wait();
@@ -526,17 +588,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
       const int a = t & 1;
       const long long m0 = (long long)(tile / num_n_tiles) * (2 * BM) + (long long)rank * BM;
       const int n0 = (tile % num_n_tiles) * BN;
-      epi.prefetch(ep, m0, n0, M, ldc, etid);
-      for (int i = etid; i < BN; i += EPI_WARPS * 32) bias_s[i] = ep.bias ? tof<T>(ep.bias[n0 + i]) : 0.f;
-      mbar_wait(acc_full(a), (t >> 1) & 1);
-      tc_fence_after();
-      epi_bar_sync();
-      epi.drain(ep, tmem_base + (uint32_t)(a * BN), cstage, bias_s, m0, n0, M, ldc, warp, lane);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_shared(acc_empty(a), 0));
-      epi_bar_sync();
-      epi.copy_out(ep, cstage, C, m0, n0, M, ldc, etid);
+      const uint32_t lead_empty = mapa_shared(acc_empty(a), 0);
+      epi.run_tile(ep, tmem_base + (uint32_t)(a * BN), smem_u32(cstage), smem_u32(bias_s), C, m0, n0, M, ldc, acc_full(a), (t >> 1) & 1,
+                   [&]() { mbar_arrive_cluster(lead_empty); });
     }
   }
   tc_fence_before();
