@@ -179,6 +179,12 @@ struct Epilogue {
   // operand B is a frozen weight (never written on the step's streams): its first tiles may be
   // fetched before the upstream kernel has finished (programmatic dependent launch)
   int b_frozen;
+  // Stream-K workspace (device, zero-initialised once, >= gemm_streamk_ws_bytes(); nullable).  When given,
+  // the CTA-pair kernel may split the K loops of the step's last partial wave of tiles across all SM pairs;
+  // partial accumulators and ready flags live here.  One workspace per stream: two stream-K kernels running
+  // concurrently on different streams must not share it (and only ONE stream may use stream-K at all --
+  // the finishing CTAs of a tile spin on flags set by CTAs that must become resident).
+  void *sk_ws;
 
   // v: f32 accumulator for element (m, n); returns the value to store (already rounded through T
   // at the points where the reference materialises a dtype tensor).
@@ -203,6 +209,7 @@ int gemm_simt(const T *A, long long sam, long long sak, const T *B, long long sb
 template <typename T>
 int gemm_tcgen05(const T *A, long long lda, const T *B, long long ldb, T *C, long long ldc, long long M, int N, int Kd,
                  const Epilogue<T> &ep, cudaStream_t st);
+size_t gemm_streamk_ws_bytes();
 bool gemm_tcgen05_supported(int dtype, long long lda, long long ldb, long long ldc, long long M, int N, int Kd,
                             const void *A, const void *B, const void *C);
 

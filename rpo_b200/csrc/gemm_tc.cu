@@ -147,6 +147,8 @@ struct Epi {
   long long pass_stride;  // elements between the rows of consecutive copy-out passes
   const T *src_row;  // residual / gelu' aux: row (etid / CH) of the tile, column chunk (etid % CH)
   T *dst_row;        // C: same position
+  const float *sk_partial = nullptr;  // stream-K: partial accumulators of the following clusters (this CTA's half)
+  int sk_count = 0;
 
   __device__ __forceinline__ void prefetch(int sc, int r0, uint4 (&pre)[PASSES]) {
     if (!src_row) return;
@@ -169,6 +171,17 @@ struct Epi {
     const int c0 = sc0 + half_id * 32;  // tile-local first column of this warp's 32
     uint32_t acc[32];
     tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
+    for (int p = 0; p < sk_count; ++p) {  // stream-K finisher: add the partial sums, in cluster order
+      const float4 *slot = reinterpret_cast<const float4 *>(sk_partial + (size_t)p * (2 * BM * 256));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 v = __ldcg(slot + (size_t)(c0 / 4 + j) * BM + r_loc);
+        acc[4 * j] = __float_as_uint(__uint_as_float(acc[4 * j]) + v.x);
+        acc[4 * j + 1] = __float_as_uint(__uint_as_float(acc[4 * j + 1]) + v.y);
+        acc[4 * j + 2] = __float_as_uint(__uint_as_float(acc[4 * j + 2]) + v.z);
+        acc[4 * j + 3] = __float_as_uint(__uint_as_float(acc[4 * j + 3]) + v.w);
+      }
+    }
     __align__(16) T2 h[16];
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
@@ -454,6 +467,55 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, u
       : "memory");
 }
 
+// ---- work decomposition of the CTA-pair kernel ---------------------------------------------------------
+// Data-parallel: cluster c owns tiles c, c + NC, ...  Stream-K: the num_tiles * num_kb k-blocks of the whole
+// problem are cut into NC equal contiguous ranges, so every SM pair finishes at the same time instead of
+// 10 pairs running a second full tile while 64 idle (M=7072, N=768: 84 tiles on 74 pairs).  A range is a
+// sequence of segments (tile, k0, k1).  Its first segment may start inside a tile (k0 > 0): the cluster is a
+// CONTRIBUTOR there -- it runs first, writes its f32 partial accumulator to the workspace and raises a flag.
+// The cluster holding k-block 0 of a tile is its FINISHER: it reaches that segment last, adds the partials of
+// the following clusters in cluster order (deterministic) and runs the epilogue.  Contributors never wait, so
+// there is no cyclic dependency; waits are bounded (trap) like every other wait in this file.
+struct Seg {
+  int tile, k0, k1;
+};
+struct Sched {
+  int sk, num_tiles, num_kb, nc, next_tile;
+  long long pos, end;
+  __device__ __forceinline__ void init(int stream_k, int tiles, int kb, int c, int n_clusters) {
+    sk = stream_k; num_tiles = tiles; num_kb = kb; nc = n_clusters; next_tile = c;
+    const long long total = (long long)tiles * kb;
+    pos = total * c / n_clusters;
+    end = total * (c + 1) / n_clusters;
+  }
+  __device__ __forceinline__ bool next(Seg &s) {
+    if (!sk) {
+      if (next_tile >= num_tiles) return false;
+      s.tile = next_tile; s.k0 = 0; s.k1 = num_kb;
+      next_tile += nc;
+      return true;
+    }
+    if (pos >= end) return false;
+    s.tile = (int)(pos / num_kb);
+    s.k0 = (int)(pos % num_kb);
+    const long long rem = end - pos;
+    s.k1 = rem < (long long)(num_kb - s.k0) ? s.k0 + (int)rem : num_kb;
+    pos += s.k1 - s.k0;
+    return true;
+  }
+};
+static constexpr int SK_MAX_CLUSTERS = 128;
+static constexpr size_t SK_FLAG_BYTES = 1024;                                      // [SK_MAX_CLUSTERS][2] ints
+static constexpr size_t SK_SLOT_BYTES = (size_t)2 * BM * 256 * sizeof(float);      // one cluster's partial, BN <= 256
+__device__ __forceinline__ int ld_acquire_gpu(const int *p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int *p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 template <int BN>
 struct Cfg2 {
   static constexpr int STAGES = BN >= 256 ? 6 : 8;
@@ -473,7 +535,7 @@ template <typename T, int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
     gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     T *__restrict__ C, long long ldc, long long M, int N, int Kd, Epilogue<T> ep, int num_n_tiles,
-                    int num_tiles) {
+                    int num_tiles, int stream_k) {
   using C_ = Cfg2<BN>;
   using T2 = typename Pk<T>::T2;
   extern __shared__ uint8_t smem_raw[];
@@ -524,22 +586,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
   if (warp == 0) {
     // ===== TMA producer (both CTAs; transaction bytes of both land on the leader's barrier) =====
     if (lane == 0) {
+      Sched sch;
+      sch.init(stream_k, num_tiles, num_kb, cluster_id, num_clusters);
+      Seg sg;
+      bool have = sch.next(sg);
       uint32_t pre = 0;
-      if (ep.b_frozen && cluster_id < num_tiles) {  // weight tiles ahead of the dependency wait (see gemm_tc_kernel)
-        const int n0 = (cluster_id % num_n_tiles) * BN + (int)rank * (BN / 2);
-        const int npre = num_kb < C_::STAGES ? num_kb : C_::STAGES;
+      if (ep.b_frozen && have) {  // weight tiles ahead of the dependency wait (see gemm_tc_kernel)
+        const int n0 = (sg.tile % num_n_tiles) * BN + (int)rank * (BN / 2);
+        const int nk = sg.k1 - sg.k0;
+        const int npre = nk < C_::STAGES ? nk : C_::STAGES;
         for (; (int)pre < npre; ++pre) {
           if (rank == 0) mbar_arrive_expect_tx(full_bar(pre), 2 * C_::STAGE_BYTES);
           tma_load_2d_pair(smem_base + pre * C_::STAGE_BYTES + C_::A_BYTES, &map_b, mapa_shared(full_bar(pre), 0),
-                           pre * BK, n0);
+                           (sg.k0 + (int)pre) * BK, n0);
         }
       }
       pdl_wait();
       uint32_t it = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m0 = (tile / num_n_tiles) * (2 * BM) + (int)rank * BM;
-        const int n0 = (tile % num_n_tiles) * BN + (int)rank * (BN / 2);
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+      for (; have; have = sch.next(sg)) {
+        const int m0 = (sg.tile / num_n_tiles) * (2 * BM) + (int)rank * BM;
+        const int n0 = (sg.tile % num_n_tiles) * BN + (int)rank * (BN / 2);
+        for (int kb = sg.k0; kb < sg.k1; ++kb, ++it) {
           const int s = it % C_::STAGES;
           const uint32_t ph = (it / C_::STAGES) & 1;
           const uint32_t lead_full = mapa_shared(full_bar(s), 0);
@@ -557,13 +624,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
     // ===== MMA issuer: one thread of the leader CTA drives both SMs' tensor cores =====
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = make_idesc(Num<T>::dtype == RPO_BF16 ? 1 : 0, 2 * BM, BN);
+      Sched sch;
+      sch.init(stream_k, num_tiles, num_kb, cluster_id, num_clusters);
+      Seg sg;
       uint32_t it = 0, t = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++t) {
+      for (; sch.next(sg); ++t) {
         const int a = t & 1;
         mbar_wait(acc_empty(a), ((t >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(a * BN);
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = sg.k0; kb < sg.k1; ++kb, ++it) {
           const int s = it % C_::STAGES;
           const uint32_t ph = (it / C_::STAGES) & 1;
           mbar_wait(full_bar(s), ph);
@@ -573,7 +643,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
           const uint64_t bdesc = make_smem_desc(a_addr + C_::A_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_f16_pair(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0);
+            umma_f16_pair(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb != sg.k0) || (k != 0));
           umma_commit_pair(empty_bar(s));
         }
         umma_commit_pair(acc_full(a));
@@ -582,15 +652,70 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
   } else {
     // ===== epilogue (both CTAs, 128 rows x BN columns each) =====
     Epi<T, BN> epi;
+    Sched sch;
+    sch.init(stream_k, num_tiles, num_kb, cluster_id, num_clusters);
+    Seg sg;
     uint32_t t = 0;
+    int *sk_flags = reinterpret_cast<int *>(ep.sk_ws);
+    float *sk_slots = reinterpret_cast<float *>(reinterpret_cast<char *>(ep.sk_ws) + SK_FLAG_BYTES);
+    const int q = warp & 3, half_id = (warp - 2) >> 2, etid = threadIdx.x - 64;
     pdl_wait();
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++t) {
+    for (; sch.next(sg); ++t) {
       const int a = t & 1;
-      const long long m0 = (long long)(tile / num_n_tiles) * (2 * BM) + (long long)rank * BM;
-      const int n0 = (tile % num_n_tiles) * BN;
+      const long long m0 = (long long)(sg.tile / num_n_tiles) * (2 * BM) + (long long)rank * BM;
+      const int n0 = (sg.tile % num_n_tiles) * BN;
       const uint32_t lead_empty = mapa_shared(acc_empty(a), 0);
-      epi.run_tile(ep, tmem_base + (uint32_t)(a * BN), smem_u32(cstage), smem_u32(bias_s), C, m0, n0, M, ldc, acc_full(a), (t >> 1) & 1,
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BN);
+      if (sg.k0 > 0) {
+        // ---- contributor: f32 partial of this CTA's 128 x BN half -> workspace slot of this cluster ----
+        float4 *slot = reinterpret_cast<float4 *>(sk_slots + ((size_t)cluster_id * 2 + rank) * (BM * 256));
+        mbar_wait(acc_full(a), (t >> 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < BN / 2; cc += 32) {
+          const int c0 = half_id * (BN / 2) + cc;
+          uint32_t acc[32];
+          tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)  // [column group of 4][row]: 32 lanes = 512 contiguous bytes
+            slot[(size_t)(c0 / 4 + j) * BM + q * 32 + lane] =
+                make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]), __uint_as_float(acc[4 * j + 2]),
+                            __uint_as_float(acc[4 * j + 3]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(lead_empty);
+        __threadfence();
+        epi_bar_sync();
+        if (etid == 0) st_release_gpu(sk_flags + cluster_id * 2 + rank, 1);
+        continue;
+      }
+      int n_contrib = 0;
+      if (sg.k1 < num_kb) {
+        // ---- finisher of a split tile: clusters cluster_id+1.. hold the rest of its K range ----
+        const long long tile_end = (long long)(sg.tile + 1) * num_kb, total = (long long)num_tiles * num_kb;
+        long long p = (long long)sg.tile * num_kb + sg.k1;
+        while (p < tile_end) {
+          ++n_contrib;
+          p = total * (cluster_id + n_contrib + 1) / num_clusters;
+        }
+        if (etid < n_contrib) {
+          const int *f = sk_flags + (cluster_id + 1 + etid) * 2 + rank;
+          long long t0 = clock64();
+          while (ld_acquire_gpu(f) == 0) {
+            if (clock64() - t0 > 4000000000LL) __trap();
+          }
+        }
+        epi_bar_sync();
+      }
+      epi.sk_partial = n_contrib ? sk_slots + ((size_t)(cluster_id + 1) * 2 + rank) * (BM * 256) : nullptr;
+      epi.sk_count = n_contrib;
+      epi.run_tile(ep, tmem_acc, smem_u32(cstage), smem_u32(bias_s), C, m0, n0, M, ldc, acc_full(a), (t >> 1) & 1,
                    [&]() { mbar_arrive_cluster(lead_empty); });
+      if (n_contrib) {  // all partial reads are done (they precede the last slab barrier): re-arm the flags
+        epi_bar_sync();
+        if (etid < n_contrib) sk_flags[(cluster_id + 1 + etid) * 2 + rank] = 0;
+      }
     }
   }
   tc_fence_before();
@@ -643,11 +768,29 @@ static int launch_pair(const T *A, long long lda, const T *B, long long ldb, T *
   const int num_n_tiles = N / BN;
   const long long num_tiles = ((M + 2 * BM - 1) / (2 * BM)) * num_n_tiles;
   const int pairs = sm_count() / 2;
-  const int grid = 2 * (int)(num_tiles < pairs ? num_tiles : pairs);
-  prof_tag("gemm2 M=%lld N=%d K=%d BN=%d%s%s%s", M, N, Kd, BN, ep.bias ? " +bias" : "",
-           ep.act == RPO_ACT_QUICKGELU ? " +gelu" : (ep.gelu_grad_aux ? " *gelu'" : ""), ep.residual ? " +res" : "");
+  int grid = 2 * (int)(num_tiles < pairs ? num_tiles : pairs);
+  // stream-K when the data-parallel schedule would leave > 8% of the SM-pair time idle in its last round and
+  // every cluster still gets at least one whole tile's worth of k-blocks (a tile is then split at most in two)
+  int stream_k = 0;
+  // Opt-in (RPO_GEMM_STREAMK=1): measured on B200 it gains 1.5% on the K=3072 GEMM and loses on the K=768 ones
+  // (the partial-accumulator round trip costs more epilogue time than the ragged wave), and splitting a tile's
+  // K range changes the f32 summation order with the row position, which breaks the bit-exact batch-permutation
+  // property the parity tests check.
+  const char *sk_env = getenv("RPO_GEMM_STREAMK");  // read per call: the parity tests switch it on for one case
+  const bool use_sk = sk_env && sk_env[0] == '1';
+  if (ep.sk_ws && use_sk && num_tiles > pairs && pairs <= SK_MAX_CLUSTERS) {
+    const long long rounds = (num_tiles + pairs - 1) / pairs;
+    const double waste = 1.0 - (double)num_tiles / (double)(rounds * pairs);
+    if (waste > 0.08) {
+      stream_k = 1;
+      grid = 2 * pairs;
+    }
+  }
+  prof_tag("gemm2 M=%lld N=%d K=%d BN=%d%s%s%s%s", M, N, Kd, BN, ep.bias ? " +bias" : "",
+           ep.act == RPO_ACT_QUICKGELU ? " +gelu" : (ep.gelu_grad_aux ? " *gelu'" : ""), ep.residual ? " +res" : "",
+           stream_k ? " streamK" : "");
   RPO_CHECK_CUDA(launch_pdl(gemm_tc2_kernel<T, BN>, dim3(grid), dim3(THREADS), C_::SMEM_BYTES, st, map_a, map_b, C, ldc, M, N, Kd,
-                            ep, num_n_tiles, (int)num_tiles));
+                            ep, num_n_tiles, (int)num_tiles, stream_k));
   RPO_LAUNCH_CHECK();
   return RPO_OK;
 }
@@ -695,6 +838,8 @@ static int pick_config(long long M, int N, int Kd) {
 }
 
 }  // namespace tc
+
+size_t gemm_streamk_ws_bytes() { return tc::SK_FLAG_BYTES + (size_t)tc::SK_MAX_CLUSTERS * tc::SK_SLOT_BYTES; }
 
 bool gemm_tcgen05_supported(int dtype, long long lda, long long ldb, long long ldc, long long M, int N, int Kd,
                             const void *A, const void *B, const void *C) {

@@ -86,6 +86,7 @@ def main():
         ("tb.sq", 2400, 512, 512, 0, 0, 0, 0),
     ]
     only = set(a.only.split(",")) if a.only else {"gemm", "attn", "ln"}
+    ws = torch.zeros(lib.rpo_gemm_workspace_bytes(), dtype=torch.uint8, device=dev)  # stream-K workspace (vision stream)
     if "gemm" not in only:
         shapes = []
     for label, M, N, Kd, has_bias, act, has_res, has_aux in shapes:
@@ -100,9 +101,11 @@ def main():
 
         def fn(i):
             j = i % nbuf
-            _lib.check(lib.rpo_gemm_bias_act(A[j].data_ptr(), Kd, W[j].data_ptr(), Kd, Cm[j].data_ptr(), N, M, N, Kd,
-                                             _lib.ptr(bias), act, _lib.ptr(res[j]) if res else None,
-                                             _lib.ptr(aux[j]) if aux else None, None, 0, code, _lib.GEMM_AUTO, _lib.stream_ptr(dev)))
+            _lib.check(lib.rpo_gemm_bias_act_ws(A[j].data_ptr(), Kd, W[j].data_ptr(), Kd, Cm[j].data_ptr(), N, M, N, Kd,
+                                                _lib.ptr(bias), act, _lib.ptr(res[j]) if res else None,
+                                                _lib.ptr(aux[j]) if aux else None, None, 0, code, _lib.GEMM_AUTO,
+                                                ws.data_ptr() if label.startswith("v.") else None,
+                                                _lib.stream_ptr(dev)))
 
         t = timeit(fn)
         fl = 2.0 * M * N * Kd
