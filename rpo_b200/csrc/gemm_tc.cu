@@ -31,16 +31,29 @@ namespace tc {
 static constexpr int BM = 128;
 static constexpr int BK = 64;  // 64 x 2 B = 128 B = one swizzle row
 static constexpr int UMMA_K = 16;
-static constexpr int EPI_WARPS = 8;
-static constexpr int THREADS = 64 + EPI_WARPS * 32;  // producer warp + MMA warp + epilogue warps
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
+// Epilogue warps come in groups of 8 (4 TMEM lane quarters x 2 column halves of a 64-column slab).  Group g
+// takes slabs g, g + GROUPS, ... with its own staging buffer and named barrier.
+static constexpr int GROUP_WARPS = 8;
+static constexpr int GROUP_THREADS = GROUP_WARPS * 32;
+template <int BN>
+struct Thr {
+  // Measured on B200: a second group (16 epilogue warps) is SLOWER (c_fc 33.6 -> 37.8 us): the 576-thread CTA
+  // caps registers at 96 (spills) and adds a tile-level barrier; the machinery stays, the switch is off.
+  static constexpr int GROUPS = 1;
+  static constexpr int EPI_WARPS = GROUPS * GROUP_WARPS;
+  static constexpr int THREADS = 64 + EPI_WARPS * 32;  // producer warp + MMA warp + epilogue warps
+};
+template <int NTHREADS>
+__device__ __forceinline__ void named_bar_sync(int id) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NTHREADS) : "memory");
+}
 
 // output staging geometry of the epilogue (see Epi below)
 template <int BN>
 struct EpiGeo {
   static constexpr int SLAB = BN >= 64 ? 64 : 32;
   static constexpr int NSLAB = BN / SLAB;
-  static constexpr int NBUF = NSLAB > 1 ? 2 : 1;
+  static constexpr int NBUF = NSLAB > 1 ? 2 : 1;  // one staging slab per epilogue warp group
   static constexpr int SLAB_BYTES = BM * SLAB * 2;
   static constexpr int CSTAGE_BYTES = NBUF * SLAB_BYTES;
 };
@@ -133,7 +146,7 @@ struct Epi {
   using G = EpiGeo<BN>;
   static constexpr int SLAB = G::SLAB;
   static constexpr int CH = SLAB / 8;                        // 16-byte chunks per staged row
-  static constexpr int ROWS_PER_PASS = (EPI_WARPS * 32) / CH;
+  static constexpr int ROWS_PER_PASS = GROUP_THREADS / CH;
   static constexpr int PASSES = BM / ROWS_PER_PASS;
   static constexpr int DRAIN_HALVES = SLAB / 32;             // warps with half_id >= this idle in the drain
 
@@ -165,54 +178,59 @@ struct Epi {
   __device__ __forceinline__ void drain(const Epilogue<T> &ep, uint32_t tmem_acc, uint32_t slab, uint32_t bias_s,
                                         long long m0, int n0, int sc0, long long ldc, int warp, int lane) {
     const int q = warp & 3;
-    const int half_id = (warp - 2) >> 2;
+    const int half_id = ((warp - 2) % GROUP_WARPS) >> 2;
     if (half_id >= DRAIN_HALVES) return;
     const int r_loc = q * 32 + lane;
     const int c0 = sc0 + half_id * 32;  // tile-local first column of this warp's 32
-    uint32_t acc[32];
-    tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
-    for (int p = 0; p < sk_count; ++p) {  // stream-K finisher: add the partial sums, in cluster order
-      const float4 *slot = reinterpret_cast<const float4 *>(sk_partial + (size_t)p * (2 * BM * 256));
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 v = __ldcg(slot + (size_t)(c0 / 4 + j) * BM + r_loc);
-        acc[4 * j] = __float_as_uint(__uint_as_float(acc[4 * j]) + v.x);
-        acc[4 * j + 1] = __float_as_uint(__uint_as_float(acc[4 * j + 1]) + v.y);
-        acc[4 * j + 2] = __float_as_uint(__uint_as_float(acc[4 * j + 2]) + v.z);
-        acc[4 * j + 3] = __float_as_uint(__uint_as_float(acc[4 * j + 3]) + v.w);
-      }
-    }
-    __align__(16) T2 h[16];
+    for (int hh = 0; hh < 2; ++hh) {  // two 16-column halves: half the live registers (16 warps share the file)
+      const int ch = c0 + hh * 16;
+      uint32_t acc[16];
+      tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)ch, acc);
+      for (int p = 0; p < sk_count; ++p) {  // stream-K finisher: add the partial sums, in cluster order
+        const float4 *slot = reinterpret_cast<const float4 *>(sk_partial + (size_t)p * (2 * BM * 256));
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      const float4 b4 = lds_f32x4(bias_s + (uint32_t)((c0 + g * 4) * 4));
-      h[2 * g] = Pk<T>::from_floats(__uint_as_float(acc[g * 4]) + b4.x, __uint_as_float(acc[g * 4 + 1]) + b4.y);
-      h[2 * g + 1] = Pk<T>::from_floats(__uint_as_float(acc[g * 4 + 2]) + b4.z, __uint_as_float(acc[g * 4 + 3]) + b4.w);
-    }
-    if (r_loc >= aux_r0 && r_loc < rows_valid) {  // pre-activation of the prompt rows (forward c_fc only)
-      T *ao = ep.aux_out + (m0 + r_loc - ep.aux_row0) * ldc + n0 + c0;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4 *>(ao + g * 8) = *reinterpret_cast<uint4 *>(&h[4 * g]);
-    }
-    if (ep.act == RPO_ACT_QUICKGELU) {
-#pragma unroll
-      for (int e = 0; e < 16; ++e) h[e] = quickgelu2<T>(h[e]);
-    }
-    if (ep.gelu_grad_aux && ep.residual && r_loc < rows_valid) {  // both: the prefetch registers hold the residual
-      const T *ax = ep.gelu_grad_aux + (m0 + r_loc) * ldc + n0 + c0;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        Vec16<T> aux = ld16(ax + g * 8);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const T *hv = reinterpret_cast<const T *>(&h[4 * g + e]);
-          h[4 * g + e] = Pk<T>::from_floats(tof<T>(hv[0]) * quickgelu_grad(tof<T>(aux.v[2 * e])),
-                                            tof<T>(hv[1]) * quickgelu_grad(tof<T>(aux.v[2 * e + 1])));
+        for (int j = 0; j < 4; ++j) {
+          const float4 v = __ldcg(slot + (size_t)(ch / 4 + j) * BM + r_loc);
+          acc[4 * j] = __float_as_uint(__uint_as_float(acc[4 * j]) + v.x);
+          acc[4 * j + 1] = __float_as_uint(__uint_as_float(acc[4 * j + 1]) + v.y);
+          acc[4 * j + 2] = __float_as_uint(__uint_as_float(acc[4 * j + 2]) + v.z);
+          acc[4 * j + 3] = __float_as_uint(__uint_as_float(acc[4 * j + 3]) + v.w);
         }
       }
-    }
+      __align__(16) T2 h[8];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) sts128(slab + st_off(r_loc, half_id * 4 + g), *reinterpret_cast<uint4 *>(&h[4 * g]));
+      for (int g = 0; g < 4; ++g) {
+        const float4 b4 = lds_f32x4(bias_s + (uint32_t)((ch + g * 4) * 4));
+        h[2 * g] = Pk<T>::from_floats(__uint_as_float(acc[g * 4]) + b4.x, __uint_as_float(acc[g * 4 + 1]) + b4.y);
+        h[2 * g + 1] = Pk<T>::from_floats(__uint_as_float(acc[g * 4 + 2]) + b4.z, __uint_as_float(acc[g * 4 + 3]) + b4.w);
+      }
+      if (r_loc >= aux_r0 && r_loc < rows_valid) {  // pre-activation of the prompt rows (forward c_fc only)
+        T *ao = ep.aux_out + (m0 + r_loc - ep.aux_row0) * ldc + n0 + ch;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) *reinterpret_cast<uint4 *>(ao + g * 8) = *reinterpret_cast<uint4 *>(&h[4 * g]);
+      }
+      if (ep.act == RPO_ACT_QUICKGELU) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) h[e] = quickgelu2<T>(h[e]);
+      }
+      if (ep.gelu_grad_aux && ep.residual && r_loc < rows_valid) {  // both: the prefetch registers hold the residual
+        const T *ax = ep.gelu_grad_aux + (m0 + r_loc) * ldc + n0 + ch;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          Vec16<T> aux = ld16(ax + g * 8);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const T *hv = reinterpret_cast<const T *>(&h[4 * g + e]);
+            h[4 * g + e] = Pk<T>::from_floats(tof<T>(hv[0]) * quickgelu_grad(tof<T>(aux.v[2 * e])),
+                                              tof<T>(hv[1]) * quickgelu_grad(tof<T>(aux.v[2 * e + 1])));
+          }
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < 2; ++g)
+        sts128(slab + st_off(r_loc, half_id * 4 + hh * 2 + g), *reinterpret_cast<uint4 *>(&h[4 * g]));
+    }
   }
 
   __device__ __forceinline__ void copy_out(const Epilogue<T> &ep, uint32_t slab, int sc, int r0, int c, uint4 (&pre)[PASSES]) {
@@ -248,8 +266,11 @@ struct Epi {
   __device__ __forceinline__ void run_tile(const Epilogue<T> &ep, uint32_t tmem_acc, uint32_t cstage, uint32_t bias_s,
                                            T *__restrict__ C, long long m0, int n0, long long M, long long ldc,
                                            uint32_t acc_full_bar, uint32_t acc_full_parity, Arrive arrive_acc_empty) {
+    constexpr int GROUPS = Thr<BN>::GROUPS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int etid = threadIdx.x - 64;
+    const int etid_all = threadIdx.x - 64;
+    const int grp = etid_all / GROUP_THREADS;   // warp group: takes slabs grp, grp + GROUPS, ...
+    const int etid = etid_all % GROUP_THREADS;
     const int r0 = etid / CH, c = etid % CH;
     rows_valid = (int)(M - m0 < BM ? M - m0 : BM);
     aux_r0 = BM;
@@ -259,36 +280,37 @@ struct Epi {
     const T *src = ep.residual ? ep.residual : ep.gelu_grad_aux;
     src_row = src ? src + pos : nullptr;
     dst_row = C + pos;
-    uint4 pre[PASSES], nxt[PASSES];
-    prefetch(0, r0, pre);
-    for (int i = etid; i < BN; i += EPI_WARPS * 32) {
+    uint4 pre[PASSES];
+    prefetch(grp * SLAB, r0, pre);
+    if (GROUPS > 1) named_bar_sync<Thr<BN>::EPI_WARPS * 32>(1);  // the other group has left the previous tile's drains
+    for (int i = etid_all; i < BN; i += Thr<BN>::EPI_WARPS * 32) {
       const float bv = ep.bias ? tof<T>(ep.bias[n0 + i]) : 0.f;
       asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + (uint32_t)(i * 4)), "f"(bv) : "memory");
     }
     mbar_wait(acc_full_bar, acc_full_parity);
     tc_fence_after();
-    epi_bar_sync();  // bias visible; the last copy-out of the previous tile is finished
+    named_bar_sync<Thr<BN>::EPI_WARPS * 32>(1);  // bias visible to every epilogue warp
+    const uint32_t slab = cstage + (uint32_t)(grp * G::SLAB_BYTES);
+    constexpr int MY_SLABS = G::NSLAB / GROUPS;
 #pragma unroll 1
-    for (int sl = 0; sl < G::NSLAB; ++sl) {
-      const uint32_t slab = cstage + (uint32_t)((sl % G::NBUF) * G::SLAB_BYTES);
+    for (int i = 0; i < MY_SLABS; ++i) {
+      const int sl = grp + i * GROUPS;
       drain(ep, tmem_acc, slab, bias_s, m0, n0, sl * SLAB, ldc, warp, lane);
-      if (sl == G::NSLAB - 1) {  // accumulator drained: hand it back before the last copy-out
+      if (i == MY_SLABS - 1) {  // this warp has read its last accumulator columns
         tc_fence_before();
         __syncwarp();
         if (lane == 0) arrive_acc_empty();
-      } else {
-        prefetch((sl + 1) * SLAB, r0, nxt);
       }
-      epi_bar_sync();  // slab staged
+      named_bar_sync<GROUP_THREADS>(2 + grp);  // slab staged
       copy_out(ep, slab, sl * SLAB, r0, c, pre);
-#pragma unroll
-      for (int i = 0; i < PASSES; ++i) pre[i] = nxt[i];
+      if (i + 1 < MY_SLABS) prefetch((sl + GROUPS) * SLAB, r0, pre);
+      named_bar_sync<GROUP_THREADS>(2 + grp);  // staging slab free again (also closes the tile for this group)
     }
   }
 };
 
 template <typename T, int BN, bool LIGHT>
-__global__ void __launch_bounds__(THREADS, (Cfg<BN, LIGHT>::MIN_CTAS))
+__global__ void __launch_bounds__(Thr<BN>::THREADS, (Cfg<BN, LIGHT>::MIN_CTAS))
     gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    T *__restrict__ C, long long ldc, long long M, int N, int Kd, Epilogue<T> ep, int num_n_tiles,
                    int num_tiles) {
@@ -322,7 +344,7 @@ __global__ void __launch_bounds__(THREADS, (Cfg<BN, LIGHT>::MIN_CTAS))
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(acc_full(a), 1);
-      mbar_init(acc_empty(a), EPI_WARPS);
+      mbar_init(acc_empty(a), Thr<BN>::EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -441,8 +463,11 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Relaxed: the accumulator hand-off orders TMEM reads through tcgen05.fence::before_thread_sync; a
+// cluster-scope RELEASE here would also wait for every global store the thread has in flight (the previous
+// slabs' copy-out) to be acknowledged, once per tile and warp.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t leader_bar, int c0,
                                                  int c1) {
@@ -532,7 +557,7 @@ struct Cfg2 {
 };
 
 template <typename T, int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
     gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     T *__restrict__ C, long long ldc, long long M, int N, int Kd, Epilogue<T> ep, int num_n_tiles,
                     int num_tiles, int stream_k) {
@@ -544,6 +569,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
   float *bias_s = reinterpret_cast<float *>(cstage + C_::CSTAGE_BYTES);
   uint64_t *bars = reinterpret_cast<uint64_t *>(cstage + C_::CSTAGE_BYTES + C_::BIAS_BYTES);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * C_::STAGES + 4);
+  // tuning experiments (RPO_GEMM_DEBUG): 0x100 = no epilogue work, 0x200 = no MMA issue.  Results are garbage.
+  const int dbg = stream_k & 0xF00;
+  stream_k &= 1;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -566,7 +594,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(acc_full(a), 1);
-      mbar_init(acc_empty(a), 2 * EPI_WARPS);
+      mbar_init(acc_empty(a), 2 * Thr<BN>::EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -641,9 +669,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
           const uint32_t a_addr = smem_base + s * C_::STAGE_BYTES;
           const uint64_t adesc = make_smem_desc(a_addr);
           const uint64_t bdesc = make_smem_desc(a_addr + C_::A_BYTES);
+          if (!(dbg & 0x200)) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_f16_pair(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb != sg.k0) || (k != 0));
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_f16_pair(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb != sg.k0) || (k != 0));
+          }
           umma_commit_pair(empty_bar(s));
         }
         umma_commit_pair(acc_full(a));
@@ -658,7 +688,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
     uint32_t t = 0;
     int *sk_flags = reinterpret_cast<int *>(ep.sk_ws);
     float *sk_slots = reinterpret_cast<float *>(reinterpret_cast<char *>(ep.sk_ws) + SK_FLAG_BYTES);
-    const int q = warp & 3, half_id = (warp - 2) >> 2, etid = threadIdx.x - 64;
+    const int q = warp & 3, part = (warp - 2) >> 2, etid = threadIdx.x - 64;
+    constexpr int PART_COLS = BN / (Thr<BN>::EPI_WARPS / 4);  // accumulator columns per warp in the stream-K partial
     pdl_wait();
     for (; sch.next(sg); ++t) {
       const int a = t & 1;
@@ -672,8 +703,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
         mbar_wait(acc_full(a), (t >> 1) & 1);
         tc_fence_after();
 #pragma unroll 1
-        for (int cc = 0; cc < BN / 2; cc += 32) {
-          const int c0 = half_id * (BN / 2) + cc;
+        for (int cc = 0; cc < PART_COLS; cc += 32) {
+          const int c0 = part * PART_COLS + cc;
           uint32_t acc[32];
           tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
 #pragma unroll
@@ -686,7 +717,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(lead_empty);
         __threadfence();
-        epi_bar_sync();
+        named_bar_sync<Thr<BN>::EPI_WARPS * 32>(1);
         if (etid == 0) st_release_gpu(sk_flags + cluster_id * 2 + rank, 1);
         continue;
       }
@@ -706,14 +737,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
             if (clock64() - t0 > 4000000000LL) __trap();
           }
         }
-        epi_bar_sync();
+        named_bar_sync<Thr<BN>::EPI_WARPS * 32>(1);
+      }
+      if (dbg & 0x100) {
+        mbar_wait(acc_full(a), (t >> 1) & 1);
+        tc_fence_after();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(lead_empty);
+        continue;
       }
       epi.sk_partial = n_contrib ? sk_slots + ((size_t)(cluster_id + 1) * 2 + rank) * (BM * 256) : nullptr;
       epi.sk_count = n_contrib;
       epi.run_tile(ep, tmem_acc, smem_u32(cstage), smem_u32(bias_s), C, m0, n0, M, ldc, acc_full(a), (t >> 1) & 1,
                    [&]() { mbar_arrive_cluster(lead_empty); });
       if (n_contrib) {  // all partial reads are done (they precede the last slab barrier): re-arm the flags
-        epi_bar_sync();
+        named_bar_sync<Thr<BN>::EPI_WARPS * 32>(1);
         if (etid < n_contrib) sk_flags[(cluster_id + 1 + etid) * 2 + rank] = 0;
       }
     }
@@ -746,7 +785,7 @@ static int launch(const T *A, long long lda, const T *B, long long ldb, T *C, lo
   const long long num_tiles = ((M + BM - 1) / BM) * num_n_tiles;
   const long long slots = (long long)sm_count() * C_::MIN_CTAS;
   const int grid = (int)(num_tiles < slots ? num_tiles : slots);
-  RPO_CHECK_CUDA(launch_pdl(gemm_tc_kernel<T, BN, LIGHT>, dim3(grid), dim3(THREADS), C_::SMEM_BYTES, st, map_a, map_b, C, ldc, M, N,
+  RPO_CHECK_CUDA(launch_pdl(gemm_tc_kernel<T, BN, LIGHT>, dim3(grid), dim3(Thr<BN>::THREADS), C_::SMEM_BYTES, st, map_a, map_b, C, ldc, M, N,
                             Kd, ep, num_n_tiles, (int)num_tiles));
   RPO_LAUNCH_CHECK();
   return RPO_OK;
@@ -786,10 +825,11 @@ static int launch_pair(const T *A, long long lda, const T *B, long long ldb, T *
       grid = 2 * pairs;
     }
   }
+  if (const char *d = getenv("RPO_GEMM_DEBUG")) stream_k |= (int)strtol(d, nullptr, 0) & 0xF00;
   prof_tag("gemm2 M=%lld N=%d K=%d BN=%d%s%s%s%s", M, N, Kd, BN, ep.bias ? " +bias" : "",
            ep.act == RPO_ACT_QUICKGELU ? " +gelu" : (ep.gelu_grad_aux ? " *gelu'" : ""), ep.residual ? " +res" : "",
            stream_k ? " streamK" : "");
-  RPO_CHECK_CUDA(launch_pdl(gemm_tc2_kernel<T, BN>, dim3(grid), dim3(THREADS), C_::SMEM_BYTES, st, map_a, map_b, C, ldc, M, N, Kd,
+  RPO_CHECK_CUDA(launch_pdl(gemm_tc2_kernel<T, BN>, dim3(grid), dim3(Thr<BN>::THREADS), C_::SMEM_BYTES, st, map_a, map_b, C, ldc, M, N, Kd,
                             ep, num_n_tiles, (int)num_tiles, stream_k));
   RPO_LAUNCH_CHECK();
   return RPO_OK;
