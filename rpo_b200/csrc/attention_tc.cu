@@ -96,6 +96,7 @@ struct Geo {
   int prompt_tile;  // query tile that holds the prompt rows ...
   int prompt_row;   // ... starting at this row of the tile (== context rows in that tile)
   int H;
+  int tiles;        // query tiles per (group, head)
 };
 
 template <typename T>
@@ -104,12 +105,11 @@ __global__ void __launch_bounds__(THREADS, 2)
                    const __grid_constant__ CUtensorMap map_kvt,    // q|k|v matrix, box 64 x (n16 % 128)
                    const __grid_constant__ CUtensorMap map_qt,     // q|k|v matrix, box 64 x (n % 128)
                    const __grid_constant__ CUtensorMap map_prompt, // prompt-q matrix, box 64 x K
-                   T *__restrict__ out_ctx, T *__restrict__ out_prompt, Geo geo) {
+                   T *__restrict__ out_ctx, T *__restrict__ out_prompt, Geo geo, int num_items, long long *trace) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int n = geo.n, n16 = geo.n16, K = geo.K, H = geo.H;
   const int D = H * HD;
-  const int t = blockIdx.x, h = blockIdx.y, g = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kv_bytes = n16 * ROW_BYTES;
   const int p_bytes = (n16 >> 4) * P_BLOCK_BYTES;
@@ -117,27 +117,29 @@ __global__ void __launch_bounds__(THREADS, 2)
   const uint32_t Ks = smem_u32(smem), Vs = Ks + kv_bytes, QPs = Vs + kv_bytes;
   uint8_t *QP_gen = smem + 2 * kv_bytes;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * kv_bytes + qp_bytes);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 5);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 7);
   float *red_max = reinterpret_cast<float *>(bars + 8);  // [2][QT]
   float *red_sum = red_max + 2 * QT;                      // [2][QT]
-  const uint32_t bar_qk = smem_u32(bars), bar_v = bar_qk + 8, bar_s = bar_qk + 16, bar_p = bar_qk + 24,
-                 bar_o = bar_qk + 32;
-
-  const int q_begin = t * QT;
-  const int c_rows = min(max(n - q_begin, 0), QT);          // context query rows of this tile
-  const int p_rows = (t == geo.prompt_tile) ? K : 0;        // prompt query rows, right behind them
-  const int rows_here = c_rows + p_rows;
+  // one phase of every barrier per work item: K landed, Q landed, V landed, S ready, P stored, O ready, O read
+  const uint32_t bar_k = smem_u32(bars), bar_q = bar_k + 8, bar_v = bar_k + 16, bar_s = bar_k + 24, bar_p = bar_k + 32,
+                 bar_o = bar_k + 40, bar_e = bar_k + 48;
+  const int tiles = geo.tiles;
+  // phase timestamps of the first item of each CTA (tuning aid, RPO_ATTN_TRACE): [cta][8] SM clock values
+  long long *tr = trace ? trace + (size_t)blockIdx.x * 8 : nullptr;
+  if (tr && threadIdx.x == 0) tr[0] = clock64();
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_full)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_kvt)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_qt)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_prompt)) : "memory");
-    mbar_init(bar_qk, 1);
+    mbar_init(bar_k, 1);
+    mbar_init(bar_q, 1);
     mbar_init(bar_v, 1);
     mbar_init(bar_s, 1);
     mbar_init(bar_p, SM_WARPS);
     mbar_init(bar_o, 1);
+    mbar_init(bar_e, SM_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -150,49 +152,86 @@ __global__ void __launch_bounds__(THREADS, 2)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_trigger();
+  if (tr && threadIdx.x == 0) tr[1] = clock64();
+
+  // work items: (query tile, head, image), tile fastest so that the two tiles of a head run side by side
+  // on neighbouring CTAs and share K/V through L2
+  struct Item {
+    int t, h, g, c_rows, p_rows;
+  };
+  auto item_of = [&](int id) {
+    Item it;
+    it.t = id % tiles;
+    it.h = (id / tiles) % H;
+    it.g = id / (tiles * H);
+    it.c_rows = min(max(n - it.t * QT, 0), QT);       // context query rows of this tile
+    it.p_rows = (it.t == geo.prompt_tile) ? K : 0;     // prompt query rows, right behind them
+    return it;
+  };
 
   if (warp == 0) {
     if (lane == 0) {
-      pdl_wait();
-      const int grow0 = g * n;  // first row of this group in the q|k|v matrix
-      // ---- loads: Q tile + K on one barrier (S can start), V on another ----
-      mbar_arrive_expect_tx(bar_qk, (uint32_t)(rows_here * ROW_BYTES + kv_bytes));
-      if (c_rows == QT)
-        tma_load_2d(QPs, &map_full, bar_qk, h * HD, grow0 + q_begin);
-      else if (c_rows > 0)
-        tma_load_2d(QPs, &map_qt, bar_qk, h * HD, grow0 + q_begin);
-      if (p_rows > 0) tma_load_2d(QPs + geo.prompt_row * ROW_BYTES, &map_prompt, bar_qk, h * HD, g * K);
-      for (int r = 0; r < n16; r += 128) {
-        const CUtensorMap *m = (n16 - r >= 128) ? &map_full : &map_kvt;
-        tma_load_2d(Ks + r * ROW_BYTES, m, bar_qk, D + h * HD, grow0 + r);
-      }
-      mbar_arrive_expect_tx(bar_v, (uint32_t)kv_bytes);
-      for (int r = 0; r < n16; r += 128) {
-        const CUtensorMap *m = (n16 - r >= 128) ? &map_full : &map_kvt;
-        tma_load_2d(Vs + r * ROW_BYTES, m, bar_v, 2 * D + h * HD, grow0 + r);
-      }
-      // ---- S = Q K^T ----
+      auto load_k = [&](const Item &it) {
+        mbar_arrive_expect_tx(bar_k, (uint32_t)kv_bytes);
+        for (int r = 0; r < n16; r += 128)
+          tma_load_2d(Ks + r * ROW_BYTES, (n16 - r >= 128) ? &map_full : &map_kvt, bar_k, D + it.h * HD, it.g * n + r);
+      };
+      auto load_qv = [&](const Item &it) {
+        mbar_arrive_expect_tx(bar_q, (uint32_t)((it.c_rows + it.p_rows) * ROW_BYTES));
+        if (it.c_rows == QT)
+          tma_load_2d(QPs, &map_full, bar_q, it.h * HD, it.g * n + it.t * QT);
+        else if (it.c_rows > 0)
+          tma_load_2d(QPs, &map_qt, bar_q, it.h * HD, it.g * n + it.t * QT);
+        if (it.p_rows > 0) tma_load_2d(QPs + geo.prompt_row * ROW_BYTES, &map_prompt, bar_q, it.h * HD, it.g * K);
+        mbar_arrive_expect_tx(bar_v, (uint32_t)kv_bytes);
+        for (int r = 0; r < n16; r += 128)
+          tma_load_2d(Vs + r * ROW_BYTES, (n16 - r >= 128) ? &map_full : &map_kvt, bar_v, 2 * D + it.h * HD, it.g * n + r);
+      };
       const uint32_t fmt = Num<T>::dtype == RPO_BF16 ? 1u : 0u;
-      mbar_wait(bar_qk, 0);
-      tc_fence_after();
-      {
-        const uint32_t idesc = make_idesc((int)fmt, QT, n16);
-        const uint64_t adesc = make_smem_desc(QPs), bdesc = make_smem_desc(Ks);
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_f16(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc, k != 0);
-        umma_commit(bar_s);
+      const uint32_t idesc_s = make_idesc((int)fmt, QT, n16);
+      const uint32_t idesc_o = make_idesc((int)fmt, QT, HD) | (1u << 16);  // B (= V) is MN-major
+      const int nsteps = n16 >> 4;
+      pdl_wait();
+      int id = blockIdx.x;
+      if (id < num_items) {
+        const Item first = item_of(id);
+        load_k(first);
+        load_qv(first);
       }
-      // ---- O = P V (P written by the softmax warps over the Q tile) ----
-      mbar_wait(bar_p, 0);
-      mbar_wait(bar_v, 0);
-      tc_fence_after();
-      {
-        const uint32_t idesc = make_idesc((int)fmt, QT, HD) | (1u << 16);  // B (= V) is MN-major
-        const int nsteps = n16 >> 4;
+      for (uint32_t i = 0; id < num_items; id += gridDim.x, ++i) {
+        const uint32_t par = i & 1;
+        const int next = id + gridDim.x;
+        // ---- S = Q K^T (the previous item's O has been read out of TMEM) ----
+        mbar_wait(bar_k, par);
+        mbar_wait(bar_q, par);
+        if (i > 0) mbar_wait(bar_e, par ^ 1);
+        tc_fence_after();
+        if (tr && i == 0) tr[2] = clock64();
+        {
+          const uint64_t adesc = make_smem_desc(QPs), bdesc = make_smem_desc(Ks);
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k) umma_f16(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc_s, k != 0);
+          umma_commit(bar_s);
+        }
+        // ---- K is free once S is complete: prefetch the next item's K behind this item's softmax ----
+        if (next < num_items) {
+          mbar_wait(bar_s, par);
+          load_k(item_of(next));
+        }
+        // ---- O = P V (P written by the softmax warps over the Q tile) ----
+        mbar_wait(bar_p, par);
+        if (tr && i == 0) tr[5] = clock64();
+        mbar_wait(bar_v, par);
+        tc_fence_after();
         for (int j = 0; j < nsteps; ++j)
           umma_f16(tmem_base, make_smem_desc_sw32(QPs + j * P_BLOCK_BYTES), make_smem_desc(Vs + j * 16 * ROW_BYTES),
-                   idesc, j != 0);
+                   idesc_o, j != 0);
         umma_commit(bar_o);
+        // ---- V and the Q/P region are free once O is complete: next item's Q and V ----
+        if (next < num_items) {
+          mbar_wait(bar_o, par);
+          load_qv(item_of(next));
+        }
       }
     }
   } else {
@@ -200,115 +239,133 @@ __global__ void __launch_bounds__(THREADS, 2)
     const int q = warp & 3;
     const int hf = (warp - 1) >> 2;  // which share of the key blocks / of the output columns
     const int row = q * 32 + lane;
-    const bool warp_valid = q * 32 < rows_here;  // warp-uniform, identical for the two partner warps
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    if (warp_valid) {
-      mbar_wait(bar_s, 0);
-      tc_fence_after();
-      const float sl2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-      const int nblk = n16 >> 4;
-      const int b_mid = (nblk + 1) >> 1;
-      const int b0 = hf ? b_mid : 0, b1 = hf ? nblk : b_mid;  // this thread's 16-key blocks
-      // ---- pass 1: row maximum over this thread's keys ----
-      float mx = -INFINITY;
-      {
-        uint32_t cur[16], nxt[16];
-        tmem_ld16_nowait(taddr + (uint32_t)(b0 * 16), cur);
-        tmem_ld_wait(cur);
-        for (int b = b0; b < b1; ++b) {
-          if (b + 1 < b1) tmem_ld16_nowait(taddr + (uint32_t)((b + 1) * 16), nxt);
-          if (b * 16 + 16 <= n) {
+    const float sl2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+    const int nblk = n16 >> 4;
+    const int b_mid = (nblk + 1) >> 1;
+    const int b0 = hf ? b_mid : 0, b1 = hf ? nblk : b_mid;  // this thread's 16-key blocks
+    const uint32_t sw = (uint32_t)((row >> 2) & 1);  // 32B swizzle: 16-byte chunk index ^= address bit 7
+    uint8_t *prow = QP_gen + row * 32;
+    uint32_t i = 0;
+    for (int id = blockIdx.x; id < num_items; id += gridDim.x, ++i) {
+      const uint32_t par = i & 1;
+      const Item it = item_of(id);
+      const int rows_here = it.c_rows + it.p_rows;
+      const bool warp_valid = q * 32 < rows_here;  // warp-uniform, identical for the two partner warps
+      // every warp waits for S, also those without valid rows: S(i) exists only after all warps arrived for item
+      // i-1, so no warp can arrive twice in one barrier phase
+      mbar_wait(bar_s, par);
+      if (warp_valid) {
+        tc_fence_after();
+        if (tr && i == 0 && threadIdx.x == 32) tr[3] = clock64();
+        // ---- pass 1: row maximum over this thread's keys ----
+        float mx = -INFINITY;
+        {
+          uint32_t cur[16], nxt[16];
+          tmem_ld16_nowait(taddr + (uint32_t)(b0 * 16), cur);
+          tmem_ld_wait(cur);
+          for (int b = b0; b < b1; ++b) {
+            if (b + 1 < b1) tmem_ld16_nowait(taddr + (uint32_t)((b + 1) * 16), nxt);
+            if (b * 16 + 16 <= n) {
 #pragma unroll
-            for (int e = 0; e < 16; e += 2)
-              mx = fmaxf(mx, fmaxf(__uint_as_float(cur[e]), __uint_as_float(cur[e + 1])));
-          } else {
+              for (int e = 0; e < 16; e += 2)
+                mx = fmaxf(mx, fmaxf(__uint_as_float(cur[e]), __uint_as_float(cur[e + 1])));
+            } else {
 #pragma unroll
-            for (int e = 0; e < 16; ++e)
-              if (b * 16 + e < n) mx = fmaxf(mx, __uint_as_float(cur[e]));
-          }
-          if (b + 1 < b1) {
-            tmem_ld_wait(nxt);
-#pragma unroll
-            for (int e = 0; e < 16; ++e) cur[e] = nxt[e];
-          }
-        }
-      }
-      red_max[hf * QT + row] = mx;
-      pair_bar_sync(1 + q);
-      mx = fmaxf(red_max[row], red_max[QT + row]);  // every row sees key 0, so the maximum is finite
-      const float off = mx * sl2;
-      const uint32_t sw = (uint32_t)((row >> 2) & 1);  // 32B swizzle: 16-byte chunk index ^= address bit 7
-      uint8_t *prow = QP_gen + row * 32;
-      // ---- pass 2: probabilities -> P blocks, row sum ----
-      float l = 0.f;
-      {
-        uint32_t cur[16], nxt[16];
-        tmem_ld16_nowait(taddr + (uint32_t)(b0 * 16), cur);
-        tmem_ld_wait(cur);
-        for (int b = b0; b < b1; ++b) {
-          if (b + 1 < b1) tmem_ld16_nowait(taddr + (uint32_t)((b + 1) * 16), nxt);
-          uint32_t pk[8];
-          if (b * 16 + 16 <= n) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float p0 = ex2_approx(fmaf(__uint_as_float(cur[2 * e]), sl2, -off));
-              const float p1 = ex2_approx(fmaf(__uint_as_float(cur[2 * e + 1]), sl2, -off));
-              l += p0 + p1;
-              pk[e] = pack2<T>(p0, p1);
+              for (int e = 0; e < 16; ++e)
+                if (b * 16 + e < n) mx = fmaxf(mx, __uint_as_float(cur[e]));
             }
-          } else {
+            if (b + 1 < b1) {
+              tmem_ld_wait(nxt);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int col = b * 16 + 2 * e;
-              const float p0 = col < n ? ex2_approx(fmaf(__uint_as_float(cur[2 * e]), sl2, -off)) : 0.f;
-              const float p1 = col + 1 < n ? ex2_approx(fmaf(__uint_as_float(cur[2 * e + 1]), sl2, -off)) : 0.f;
-              l += p0 + p1;
-              pk[e] = pack2<T>(p0, p1);
+              for (int e = 0; e < 16; ++e) cur[e] = nxt[e];
             }
           }
-          uint8_t *dst = prow + b * P_BLOCK_BYTES;
-          *reinterpret_cast<uint4 *>(dst + ((0u ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4 *>(dst + ((1u ^ sw) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          if (b + 1 < b1) {
-            tmem_ld_wait(nxt);
+        }
+        red_max[hf * QT + row] = mx;
+        pair_bar_sync(1 + q);
+        if (tr && i == 0 && threadIdx.x == 32) tr[4] = clock64();
+        mx = fmaxf(red_max[row], red_max[QT + row]);  // every row sees key 0, so the maximum is finite
+        const float off = mx * sl2;
+        // ---- pass 2: probabilities -> P blocks, row sum ----
+        float l = 0.f;
+        {
+          uint32_t cur[16], nxt[16];
+          tmem_ld16_nowait(taddr + (uint32_t)(b0 * 16), cur);
+          tmem_ld_wait(cur);
+          for (int b = b0; b < b1; ++b) {
+            if (b + 1 < b1) tmem_ld16_nowait(taddr + (uint32_t)((b + 1) * 16), nxt);
+            uint32_t pk[8];
+            if (b * 16 + 16 <= n) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) cur[e] = nxt[e];
+              for (int e = 0; e < 8; ++e) {
+                const float p0 = ex2_approx(fmaf(__uint_as_float(cur[2 * e]), sl2, -off));
+                const float p1 = ex2_approx(fmaf(__uint_as_float(cur[2 * e + 1]), sl2, -off));
+                l += p0 + p1;
+                pk[e] = pack2<T>(p0, p1);
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int col = b * 16 + 2 * e;
+                const float p0 = col < n ? ex2_approx(fmaf(__uint_as_float(cur[2 * e]), sl2, -off)) : 0.f;
+                const float p1 = col + 1 < n ? ex2_approx(fmaf(__uint_as_float(cur[2 * e + 1]), sl2, -off)) : 0.f;
+                l += p0 + p1;
+                pk[e] = pack2<T>(p0, p1);
+              }
+            }
+            uint8_t *dst = prow + b * P_BLOCK_BYTES;
+            *reinterpret_cast<uint4 *>(dst + ((0u ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4 *>(dst + ((1u ^ sw) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            if (b + 1 < b1) {
+              tmem_ld_wait(nxt);
+#pragma unroll
+              for (int e = 0; e < 16; ++e) cur[e] = nxt[e];
+            }
           }
         }
+        red_sum[hf * QT + row] = l;
+        // make the generic-proxy stores of P visible to the tensor core (async proxy), release S
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
       }
-      red_sum[hf * QT + row] = l;
-      // make the generic-proxy stores of P visible to the tensor core (async proxy), release S
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      tc_fence_before();
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar_p);
-    if (warp_valid) {
-      mbar_wait(bar_o, 0);
-      tc_fence_after();
-      const float inv = 1.0f / (red_sum[row] + red_sum[QT + row]);
-      T *dst = nullptr;
-      if (row < c_rows)
-        dst = out_ctx + ((long long)g * n + q_begin + row) * D + h * HD;
-      else if (row < rows_here)
-        dst = out_prompt + ((long long)g * K + (row - c_rows)) * D + h * HD;
-      uint32_t acc[32];
-      tmem_ld32(taddr + (uint32_t)(hf * 32), acc);  // this thread's 32 of the 64 output columns
-      if (dst) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
+      if (warp_valid) {
+        mbar_wait(bar_o, par);
+        tc_fence_after();
+        if (tr && i == 0 && threadIdx.x == 32) tr[6] = clock64();
+        const float inv = 1.0f / (red_sum[row] + red_sum[QT + row]);
+        T *dst = nullptr;
+        if (row < it.c_rows)
+          dst = out_ctx + ((long long)it.g * n + it.t * QT + row) * D + it.h * HD;
+        else if (row < rows_here)
+          dst = out_prompt + ((long long)it.g * K + (row - it.c_rows)) * D + it.h * HD;
+        uint32_t acc[32];
+        tmem_ld32(taddr + (uint32_t)(hf * 32), acc);  // this thread's 32 of the 64 output columns
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_e);  // O is out of TMEM: the next S may overwrite it
+        if (dst) {
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          uint4 o;
-          o.x = pack2<T>(__uint_as_float(acc[8 * v + 0]) * inv, __uint_as_float(acc[8 * v + 1]) * inv);
-          o.y = pack2<T>(__uint_as_float(acc[8 * v + 2]) * inv, __uint_as_float(acc[8 * v + 3]) * inv);
-          o.z = pack2<T>(__uint_as_float(acc[8 * v + 4]) * inv, __uint_as_float(acc[8 * v + 5]) * inv);
-          o.w = pack2<T>(__uint_as_float(acc[8 * v + 6]) * inv, __uint_as_float(acc[8 * v + 7]) * inv);
-          *reinterpret_cast<uint4 *>(dst + hf * 32 + v * 8) = o;
+          for (int v = 0; v < 4; ++v) {
+            uint4 o;
+            o.x = pack2<T>(__uint_as_float(acc[8 * v + 0]) * inv, __uint_as_float(acc[8 * v + 1]) * inv);
+            o.y = pack2<T>(__uint_as_float(acc[8 * v + 2]) * inv, __uint_as_float(acc[8 * v + 3]) * inv);
+            o.z = pack2<T>(__uint_as_float(acc[8 * v + 4]) * inv, __uint_as_float(acc[8 * v + 5]) * inv);
+            o.w = pack2<T>(__uint_as_float(acc[8 * v + 6]) * inv, __uint_as_float(acc[8 * v + 7]) * inv);
+            *reinterpret_cast<uint4 *>(dst + hf * 32 + v * 8) = o;
+          }
         }
+      } else {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_e);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (tr && threadIdx.x == 0) tr[7] = clock64();
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -336,7 +393,7 @@ int ro_attention_fwd_dense(const T *qkv_ctx, const T *q_prompt, T *out_ctx, T *o
   } else {
     using namespace atc;
     RPO_REQUIRE(ro_attention_fwd_dense_supported(Num<T>::dtype, n, K, H), "tcgen05 attention shape");
-    RPO_REQUIRE(G >= 1 && G <= 65535 && H <= 65535, "grid limits");
+    RPO_REQUIRE(G >= 1, "at least one group");
     RPO_REQUIRE((((uintptr_t)qkv_ctx | (uintptr_t)q_prompt | (uintptr_t)out_ctx | (uintptr_t)out_prompt) & 15) == 0,
                 "attention buffers must be 16-byte aligned");
     const int D = H * HD;
@@ -366,10 +423,16 @@ int ro_attention_fwd_dense(const T *qkv_ctx, const T *q_prompt, T *out_ctx, T *o
       RPO_CHECK_CUDA(cudaFuncSetAttribute(ro_attn_fwd_tc<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       configured = smem;
     }
-    dim3 grid(tiles, H, G);
+    geo.tiles = tiles;
+    const long long items = (long long)tiles * H * G;
+    RPO_REQUIRE(items <= 0x7fffffffLL, "grid limits");
+    const int slots = 2 * sm_count();  // two CTAs per SM (104 KB of shared memory, 256 TMEM columns each)
+    dim3 grid((unsigned)(items < slots ? items : slots));
+    long long *trace = nullptr;
+    if (const char *e = getenv("RPO_ATTN_TRACE")) trace = reinterpret_cast<long long *>(strtoull(e, nullptr, 0));
     prof_tag("attn_fwd_tc G=%d H=%d K=%d n=%d", G, H, K, n);
     RPO_CHECK_CUDA(launch_pdl(ro_attn_fwd_tc<T>, grid, dim3(THREADS), (size_t)smem, st, map_full, map_kvt, map_qt,
-                              map_prompt, out_ctx, out_prompt, geo));
+                              map_prompt, out_ctx, out_prompt, geo, (int)items, trace));
     RPO_LAUNCH_CHECK();
     return RPO_OK;
   }
