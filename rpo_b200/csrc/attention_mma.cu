@@ -615,6 +615,251 @@ static int launch_fwd_flash(const T *qkv_ctx, const T *q_prompt, T *out_ctx, T *
   return RPO_OK;
 }
 
+// ---- backward, key-split form ---------------------------------------------------------------------------
+// The gradient exists for the K prompt queries only (K = 24: two 16-row MMA tiles per (group, head)), so the
+// single-pass kernel above keeps just two warps per CTA busy with a 26-tile score fragment each.  Here the four
+// warps of a CTA split the KEYS as well: warp (mt, ks) owns query tile mt and every KS-th share of the 16-key
+// groups; row maxima, row sums and the dQ partial tiles are exchanged through shared memory.  Half the score
+// registers per warp (three CTAs per SM instead of two) and twice the active warps per CTA.
+template <typename T, int NG>  // NG: 16-key groups per warp (compile-time bound of the fragment arrays)
+__global__ void __launch_bounds__(THREADS)
+    ro_attn_bwd_ks(const T *__restrict__ qkv_ctx, const T *__restrict__ q_prompt, const T *__restrict__ o_prompt,
+                   const T *__restrict__ d_out, T *__restrict__ dq, const int *__restrict__ ctx_off, int K, int H) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  const int g = blockIdx.y, h = blockIdx.x;
+  const int D = H * HD;
+  pdl_wait();
+  pdl_trigger();
+  const int row0 = ctx_off[g];
+  const int n = ctx_off[g + 1] - row0;
+  const int n16 = (n + 15) & ~15;
+  const int q_begin = blockIdx.z * QT;
+  const int rows_here = min(QT, K - q_begin);
+  const int mt_n = (rows_here + 15) >> 4;            // query tiles with rows (1..4)
+  const int mt_slots = mt_n <= 1 ? 1 : (mt_n == 2 ? 2 : 4);
+  const int KS = 4 / mt_slots;                        // key shares per query tile
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = warp / KS, ks = warp % KS;
+  const int ng_total = n16 >> 4;
+  const int ng_per = (ng_total + KS - 1) / KS;        // <= NG (checked by the launcher)
+  const int g_lo = min(ks * ng_per, ng_total), g_hi = min(g_lo + ng_per, ng_total);
+  // [K | V, later the f32 dQ partial tiles][Q][dO][row maxima and sums]
+  const int kv_bytes = 2 * n16 * ROW_BYTES, part_bytes = 4 * 16 * HD * 4;
+  const int q_off = kv_bytes > part_bytes ? kv_bytes : part_bytes;
+  const uint32_t Ks = smem_u32(sm), Vs = Ks + n16 * ROW_BYTES, Qs = Ks + q_off, dOs = Qs + QT * ROW_BYTES;
+  float *red = reinterpret_cast<float *>(sm + q_off + 2 * QT * ROW_BYTES);  // [2][4 shares][QT] max, sum
+  const T *kbase = qkv_ctx + (long long)row0 * 3 * D + D + h * HD;
+  stage_rows<T>(Ks, kbase, 3LL * D, n, n16);
+  stage_rows<T>(Vs, kbase + D, 3LL * D, n, n16);
+  const long long pbase = ((long long)g * K + q_begin) * D + h * HD;
+  stage_rows<T>(Qs, q_prompt + pbase, D, rows_here, QT);
+  stage_rows<T>(dOs, d_out + pbase, D, rows_here, QT);
+  cp_async_wait_all();
+  __syncthreads();
+  const int r_base = mt * 16;
+  const bool active = mt < mt_n;  // warp-uniform; inactive warps only take part in the barriers
+  const int ra = r_base + (lane >> 2), rb = ra + 8;  // this lane's two rows inside the CTA's row block
+  // delta_r = sum_d dO[r,d] * O[r,d]; two lanes per row, 32 columns each
+  float delta_a = 0.f, delta_b = 0.f;
+  if (active) {
+    const int r = r_base + (lane >> 1);
+    float sdl = 0.f;
+    if (r < rows_here) {
+      const T *po = o_prompt + pbase + (long long)r * D + (lane & 1) * 32;
+      const T *pd = d_out + pbase + (long long)r * D + (lane & 1) * 32;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        Vec16<T> a = ld16(po + v * 8), b = ld16(pd + v * 8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sdl += tof<T>(a.v[e]) * tof<T>(b.v[e]);
+      }
+    }
+    sdl += __shfl_xor_sync(0xffffffffu, sdl, 1);
+    delta_a = __shfl_sync(0xffffffffu, sdl, 2 * (lane >> 2));
+    delta_b = __shfl_sync(0xffffffffu, sdl, 2 * ((lane >> 2) + 8));
+  }
+  const int m = lane >> 3;
+  const float sl2 = 0.125f * 1.4426950408889634f;
+  const int c0 = 2 * (lane & 3);
+  float acc[2 * NG][4];
+  uint32_t qf[4][4], df[4][4];
+  if (active) {
+    const int row = r_base + (m & 1) * 8 + (lane & 7);
+#pragma unroll
+    for (int kd = 0; kd < 4; ++kd) {
+      ldsm_x4(Qs + swz(row, kd * 2 + (m >> 1)), qf[kd][0], qf[kd][1], qf[kd][2], qf[kd][3]);
+      ldsm_x4(dOs + swz(row, kd * 2 + (m >> 1)), df[kd][0], df[kd][1], df[kd][2], df[kd][3]);
+    }
+    // S = Q K^T over this warp's key groups; partial row maximum
+    float mxa = -INFINITY, mxb = -INFINITY;
+#pragma unroll
+    for (int gi = 0; gi < NG; ++gi) {
+      acc[2 * gi][0] = acc[2 * gi][1] = acc[2 * gi][2] = acc[2 * gi][3] = 0.f;
+      acc[2 * gi + 1][0] = acc[2 * gi + 1][1] = acc[2 * gi + 1][2] = acc[2 * gi + 1][3] = 0.f;
+      if (g_lo + gi < g_hi) {
+        const int key = (g_lo + gi) * 16 + (m >> 1) * 8 + (lane & 7);
+#pragma unroll
+        for (int kd = 0; kd < 4; ++kd) {
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4(Ks + swz(key, kd * 2 + (m & 1)), b0, b1, b2, b3);
+          mma16816<T>(acc[2 * gi], qf[kd], b0, b1);
+          mma16816<T>(acc[2 * gi + 1], qf[kd], b2, b3);
+        }
+#pragma unroll
+        for (int t2 = 0; t2 < 2; ++t2) {
+          const int col = (g_lo + gi) * 16 + t2 * 8 + c0;
+          float(&a4)[4] = acc[2 * gi + t2];
+          if (col >= n) a4[0] = a4[2] = -INFINITY;
+          if (col + 1 >= n) a4[1] = a4[3] = -INFINITY;
+          mxa = fmaxf(mxa, fmaxf(a4[0], a4[1]));
+          mxb = fmaxf(mxb, fmaxf(a4[2], a4[3]));
+        }
+      }
+    }
+    mxa = quad_max(mxa);
+    mxb = quad_max(mxb);
+    if ((lane & 3) == 0) {
+      red[ks * QT + ra] = mxa;
+      red[ks * QT + rb] = mxb;
+    }
+  }
+  __syncthreads();
+  float sa = 0.f, sb = 0.f, oa = 0.f, ob = 0.f;
+  if (active) {
+    float mxa = -INFINITY, mxb = -INFINITY;
+    for (int k2 = 0; k2 < KS; ++k2) {
+      mxa = fmaxf(mxa, red[k2 * QT + ra]);
+      mxb = fmaxf(mxb, red[k2 * QT + rb]);
+    }
+    oa = mxa * sl2;  // key 0 is visible to every row: the maximum is finite
+    ob = mxb * sl2;
+#pragma unroll
+    for (int gi = 0; gi < NG; ++gi) {
+      if (g_lo + gi < g_hi) {
+#pragma unroll
+        for (int t2 = 0; t2 < 2; ++t2) {
+          float(&a4)[4] = acc[2 * gi + t2];
+          a4[0] = ex2_approx(fmaf(a4[0], sl2, -oa));
+          a4[1] = ex2_approx(fmaf(a4[1], sl2, -oa));
+          a4[2] = ex2_approx(fmaf(a4[2], sl2, -ob));
+          a4[3] = ex2_approx(fmaf(a4[3], sl2, -ob));
+          sa += a4[0] + a4[1];
+          sb += a4[2] + a4[3];
+        }
+      }
+    }
+    sa = quad_sum(sa);
+    sb = quad_sum(sb);
+    if ((lane & 3) == 0) {
+      red[(4 + ks) * QT + ra] = sa;
+      red[(4 + ks) * QT + rb] = sb;
+    }
+  }
+  __syncthreads();
+  // dS is handed to the tensor core in the 16-bit dtype; for fp16 it is pre-scaled by 2^8 (exact) so
+  // that products of small probabilities and small gradients stay out of the subnormal range
+  constexpr float kDs = Num<T>::dtype == RPO_F16 ? 32.0f : 0.125f;
+  constexpr float kUn = Num<T>::dtype == RPO_F16 ? 1.0f / 256.0f : 1.0f;
+  float gq[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) gq[nt][0] = gq[nt][1] = gq[nt][2] = gq[nt][3] = 0.f;
+  if (active) {
+    float la = 0.f, lb = 0.f;
+    for (int k2 = 0; k2 < KS; ++k2) {
+      la += red[(4 + k2) * QT + ra];
+      lb += red[(4 + k2) * QT + rb];
+    }
+    const float ia = 1.0f / la, ib = 1.0f / lb;
+#pragma unroll
+    for (int gi = 0; gi < NG; ++gi) {
+      if (g_lo + gi < g_hi) {
+        float dp0[4] = {0.f, 0.f, 0.f, 0.f}, dp1[4] = {0.f, 0.f, 0.f, 0.f};
+        const int keyn = (g_lo + gi) * 16 + (m >> 1) * 8 + (lane & 7);
+#pragma unroll
+        for (int kd = 0; kd < 4; ++kd) {
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4(Vs + swz(keyn, kd * 2 + (m & 1)), b0, b1, b2, b3);
+          mma16816<T>(dp0, df[kd], b0, b1);
+          mma16816<T>(dp1, df[kd], b2, b3);
+        }
+        // probabilities rounded through T, as the reference materialises them
+        float(&p0)[4] = acc[2 * gi];
+        float(&p1)[4] = acc[2 * gi + 1];
+        uint32_t a[4];
+        a[0] = pack2<T>(rnd<T>(p0[0] * ia) * (dp0[0] - delta_a) * kDs, rnd<T>(p0[1] * ia) * (dp0[1] - delta_a) * kDs);
+        a[1] = pack2<T>(rnd<T>(p0[2] * ib) * (dp0[2] - delta_b) * kDs, rnd<T>(p0[3] * ib) * (dp0[3] - delta_b) * kDs);
+        a[2] = pack2<T>(rnd<T>(p1[0] * ia) * (dp1[0] - delta_a) * kDs, rnd<T>(p1[1] * ia) * (dp1[1] - delta_a) * kDs);
+        a[3] = pack2<T>(rnd<T>(p1[2] * ib) * (dp1[2] - delta_b) * kDs, rnd<T>(p1[3] * ib) * (dp1[3] - delta_b) * kDs);
+        const int keyk = (g_lo + gi) * 16 + (m & 1) * 8 + (lane & 7);
+#pragma unroll
+        for (int dp = 0; dp < 4; ++dp) {
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4_trans(Ks + swz(keyk, dp * 2 + (m >> 1)), b0, b1, b2, b3);
+          mma16816<T>(gq[dp * 2], a, b0, b1);
+          mma16816<T>(gq[dp * 2 + 1], a, b2, b3);
+        }
+      }
+    }
+  }
+  __syncthreads();  // every warp is done with K and V: their space takes the f32 dQ partial tiles
+  float *part = reinterpret_cast<float *>(sm);  // [4 warps][16 rows][64] f32
+  if (active && ks > 0) {
+    float *pw = part + warp * (16 * HD);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      *reinterpret_cast<float2 *>(pw + (lane >> 2) * HD + nt * 8 + c0) = make_float2(gq[nt][0], gq[nt][1]);
+      *reinterpret_cast<float2 *>(pw + ((lane >> 2) + 8) * HD + nt * 8 + c0) = make_float2(gq[nt][2], gq[nt][3]);
+    }
+  }
+  __syncthreads();
+  if (active && ks == 0) {
+    for (int k2 = 1; k2 < KS; ++k2) {
+      const float *pw = part + (warp + k2) * (16 * HD);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float2 va = *reinterpret_cast<const float2 *>(pw + (lane >> 2) * HD + nt * 8 + c0);
+        const float2 vb = *reinterpret_cast<const float2 *>(pw + ((lane >> 2) + 8) * HD + nt * 8 + c0);
+        gq[nt][0] += va.x;
+        gq[nt][1] += va.y;
+        gq[nt][2] += vb.x;
+        gq[nt][3] += vb.y;
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      gq[nt][0] *= kUn;
+      gq[nt][1] *= kUn;
+      gq[nt][2] *= kUn;
+      gq[nt][3] *= kUn;
+    }
+    __syncwarp();
+    uint8_t *Qs_gen = sm + q_off;
+    store_tile<T>(Qs, Qs_gen, r_base, gq, lane, [&](int r) -> T * {
+      return r < rows_here ? dq + pbase + (long long)r * D : nullptr;
+    });
+  }
+}
+
+template <typename T, int NG>
+static int launch_bwd_ks(const T *qkv_ctx, const T *q_prompt, const T *o_prompt, const T *d_out, T *dq,
+                         const int *ctx_off, int G, int K, int H, int max_ctx, cudaStream_t st) {
+  const int n16 = (max_ctx + 15) & ~15;
+  const int kv = 2 * n16 * ROW_BYTES;
+  const int part = 4 * 16 * HD * 4;  // dQ partial tiles reuse the K/V space
+  const int smem = (kv > part ? kv : part) + 2 * QT * ROW_BYTES + 2 * 4 * QT * 4;
+  static int configured = 0;
+  if (smem > configured) {
+    RPO_CHECK_CUDA(cudaFuncSetAttribute(ro_attn_bwd_ks<T, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  dim3 grid(H, G, (K + QT - 1) / QT);
+  prof_tag("attn_bwd G=%d H=%d K=%d max_ctx=%d", G, H, K, max_ctx);
+  RPO_CHECK_CUDA(launch_pdl(ro_attn_bwd_ks<T, NG>, grid, dim3(THREADS), smem, st, qkv_ctx, q_prompt, o_prompt, d_out, dq,
+                            ctx_off, K, H));
+  RPO_LAUNCH_CHECK();
+  return RPO_OK;
+}
+
 template <typename T, int NT>
 static int launch_fwd(const T *qkv_ctx, const T *q_prompt, T *out_ctx, T *out_prompt, const int *ctx_off, int G, int K,
                       int H, int max_ctx, int causal, int do_ctx, cudaStream_t st) {
@@ -680,6 +925,18 @@ int ro_attention_bwd_mma(const T *qkv_ctx, const T *q_prompt, const T *o_prompt,
   RPO_REQUIRE(max_ctx >= 1 && max_ctx <= 288, "at most 288 context rows per group on the tensor-core path");
   RPO_REQUIRE(G <= 65535, "grid limits");
   if (G == 0 || K == 0) return RPO_OK;
+  static const bool single_pass = [] { const char *e = getenv("RPO_ATTN_SINGLEPASS"); return e && e[0] == '1'; }();
+  if (!single_pass && max_ctx > 64) {  // short contexts (text: ~10 keys) are faster in the single-pass kernel
+    // 16-key groups per warp: the groups are shared by KS = 4 / (query tiles, rounded up to 1, 2 or 4) warps
+    const int rows = K < amma::QT ? K : amma::QT;
+    const int mt = (rows + 15) / 16, slots = mt <= 1 ? 1 : (mt == 2 ? 2 : 4), ks = 4 / slots;
+    const int ng = (((max_ctx + 15) / 16) + ks - 1) / ks;
+    if (ng <= 1) return amma::launch_bwd_ks<T, 1>(qkv_ctx, q_prompt, o_prompt, d_out, dq, ctx_off, G, K, H, max_ctx, st);
+    if (ng <= 2) return amma::launch_bwd_ks<T, 2>(qkv_ctx, q_prompt, o_prompt, d_out, dq, ctx_off, G, K, H, max_ctx, st);
+    if (ng <= 4) return amma::launch_bwd_ks<T, 4>(qkv_ctx, q_prompt, o_prompt, d_out, dq, ctx_off, G, K, H, max_ctx, st);
+    if (ng <= 7) return amma::launch_bwd_ks<T, 7>(qkv_ctx, q_prompt, o_prompt, d_out, dq, ctx_off, G, K, H, max_ctx, st);
+    if (ng <= 9) return amma::launch_bwd_ks<T, 9>(qkv_ctx, q_prompt, o_prompt, d_out, dq, ctx_off, G, K, H, max_ctx, st);
+  }
   AMMA_PICK(launch_bwd, qkv_ctx, q_prompt, o_prompt, d_out, dq, ctx_off, G, K, H, max_ctx, st);
 }
 

@@ -197,11 +197,50 @@ __global__ void im2col_kernel(const TI *__restrict__ img, T *__restrict__ out, i
   out[idx] = fromf<T>(v);
 }
 
+// P % 8 == 0 (ViT-B/16, B/32) and no K padding: one thread moves one run of 8 pixels -- 32 (f32) or 16 (16-bit)
+// contiguous bytes in, 16 contiguous bytes out; consecutive threads write consecutive 16-byte chunks of a
+// patch row, so stores are fully coalesced and loads are whole sectors.
+template <typename T, typename TI>
+__global__ void im2col_vec8_kernel(const TI *__restrict__ img, T *__restrict__ out, int res, int P, long long total8) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total8) return;
+  const int G = res / P, runs = P / 8, cols8 = 3 * P * runs;  // 16-byte chunks per patch row
+  const int j = (int)(idx % cols8);
+  const long long row = idx / cols8;
+  const int kx8 = j % runs, ky = (j / runs) % P, c = j / (runs * P);
+  const int p = (int)(row % (G * G));
+  const long long b = row / (G * G);
+  const int py = p / G, px = p % G;
+  const TI *src = img + ((b * 3 + c) * res + (py * P + ky)) * (long long)res + px * P + kx8 * 8;
+  Vec16<T> o;
+  if constexpr (sizeof(TI) == 4) {
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(src)), bq = __ldg(reinterpret_cast<const float4 *>(src) + 1);
+    o.v[0] = fromf<T>(a.x); o.v[1] = fromf<T>(a.y); o.v[2] = fromf<T>(a.z); o.v[3] = fromf<T>(a.w);
+    o.v[4] = fromf<T>(bq.x); o.v[5] = fromf<T>(bq.y); o.v[6] = fromf<T>(bq.z); o.v[7] = fromf<T>(bq.w);
+  } else {
+    o = ld16(reinterpret_cast<const T *>(src));
+  }
+  st16(out + idx * 8, o);
+}
+
 template <typename T>
 int im2col_patches(const void *image, int image_dtype, T *out, int B, int res, int patch, int ld, cudaStream_t st) {
   int G = res / patch;
   long long total = (long long)B * G * G * ld;
   if (total == 0) return RPO_OK;
+  if (sizeof(T) == 2 && patch % 8 == 0 && res % 8 == 0 && ld == 3 * patch * patch && ((uintptr_t)image & 31) == 0 &&
+      ((uintptr_t)out & 15) == 0) {
+    const long long total8 = total / 8;
+    const unsigned grid8 = (unsigned)((total8 + 255) / 256);
+    if (image_dtype == RPO_F32) {
+      im2col_vec8_kernel<T, float><<<grid8, 256, 0, st>>>((const float *)image, out, res, patch, total8);
+    } else {
+      RPO_REQUIRE(image_dtype == Num<T>::dtype, "image must be f32 or the model dtype");
+      im2col_vec8_kernel<T, T><<<grid8, 256, 0, st>>>((const T *)image, out, res, patch, total8);
+    }
+    RPO_LAUNCH_CHECK();
+    return RPO_OK;
+  }
   unsigned grid = (unsigned)((total + 255) / 256);
   if (image_dtype == RPO_F32) {
     im2col_kernel<T, float><<<grid, 256, 0, st>>>((const float *)image, out, B, res, patch, ld, total);
@@ -239,11 +278,58 @@ __global__ void vision_assemble_kernel(const T *__restrict__ patch_emb, const fl
   }
 }
 
+// 8 elements (16 bytes) per thread
+template <typename T>
+__global__ void vision_assemble_vec8_kernel(const T *__restrict__ patch_emb, const float *__restrict__ cls,
+                                            const float *__restrict__ pos, const T *__restrict__ img_prompt,
+                                            T *__restrict__ x_ctx, T *__restrict__ x_prompt, int B, int S, int K, int D) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int D8 = D / 8;
+  const long long n_ctx = (long long)B * S * D8;
+  const long long total = n_ctx + (long long)B * K * D8;
+  if (idx >= total) return;
+  if (idx < n_ctx) {
+    const int d = (int)(idx % D8) * 8;
+    const long long r = idx / D8;
+    const int s = (int)(r % S);
+    const long long b = r / S;
+    float pv[8], ev[8];
+    load_f32<8>(pos + (size_t)s * D + d, pv);
+    if (s == 0) {
+      load_f32<8>(cls + d, ev);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ev[e] = rnd<T>(ev[e]);
+    } else {
+      Vec16<T> pe = ld16(patch_emb + ((size_t)b * (S - 1) + (s - 1)) * D + d);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ev[e] = tof<T>(pe.v[e]);
+    }
+    Vec16<T> o;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o.v[e] = fromf<T>(ev[e] + rnd<T>(pv[e]));
+    st16(x_ctx + idx * 8, o);
+  } else {
+    const long long j = idx - n_ctx;
+    const int d = (int)(j % D8) * 8;
+    const int i = (int)((j / D8) % K);
+    st16(x_prompt + j * 8, ld16(img_prompt + (size_t)i * D + d));
+  }
+}
+
 template <typename T>
 int vision_assemble_lnpre(const T *patch_emb, const float *cls, const float *pos, const float *, const float *,
                           const T *img_prompt, T *x_ctx, T *x_prompt, int B, int S, int K, int D, cudaStream_t st) {
   long long total = (long long)B * (S + K) * D;
   if (total == 0) return RPO_OK;
+  if (sizeof(T) == 2 && D % 8 == 0 &&
+      (((uintptr_t)patch_emb | (uintptr_t)cls | (uintptr_t)pos | (uintptr_t)img_prompt | (uintptr_t)x_ctx |
+        (uintptr_t)x_prompt) & 15) == 0) {
+    const long long total8 = total / 8;
+    vision_assemble_vec8_kernel<T><<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(patch_emb, cls, pos, img_prompt,
+                                                                                    x_ctx, x_prompt, B, S, K, D);
+    RPO_LAUNCH_CHECK();
+    return RPO_OK;
+  }
   vision_assemble_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(patch_emb, cls, pos, img_prompt, x_ctx,
                                                                             x_prompt, B, S, K, D);
   RPO_LAUNCH_CHECK();
