@@ -137,6 +137,9 @@ E2E_CASES = [
     ("small", "fp32", 8, [0, 10, 100, 999], 5),
     ("small", "fp16", 8, [0, 10, 100, 999], 5),
     ("ViT-B/16", "fp16", 24, list(range(0, 1000, 53)), 4),
+    # BASELINE config 3 geometry (ViT-L/14, 257 context rows + 24 prompts, bf16): 588 -> 640 padded patch GEMM,
+    # mma.sync attention (257 keys exceed one tcgen05 N block), 24-layer towers
+    ("ViT-L/14", "bf16", 24, [1, 20, 300], 2),
 ]
 
 

@@ -210,6 +210,32 @@ def test_gemm_streamk(prec, monkeypatch):
     assert int(ws[:1024].to(torch.int32).sum()) == 0  # every flag was re-armed
 
 
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_gemm_cluster_splitk_epilogues(prec):
+    """Long-K, small-M problems take the cluster split-K kernel (partials reduced through distributed shared
+    memory): every epilogue, ragged M, K ranges that do not divide evenly."""
+    dt = DT[prec]
+    tol = TOL[prec] * 3
+    for (M, N, Kd) in [(300, 128, 2048), (768, 768, 3072), (2400, 512, 2048), (77, 64, 2112)]:
+        A = randn(M, Kd, dtype=dt, seed=80)
+        B = randn(N, Kd, dtype=dt, seed=81, scale=Kd ** -0.5)
+        bias = randn(N, dtype=dt, seed=82, scale=0.3)
+        res = randn(M, N, dtype=dt, seed=83)
+        auxg = randn(M, N, dtype=dt, seed=84)
+        out, aux = run_gemm(A, B, prec, _lib.GEMM_TCGEN05, bias=bias, act=1, aux_row0=M // 3)
+        ref, pre = ref_gemm(A, B, bias=bias, act=1)
+        assert relmax(out, ref) <= tol, (M, N, Kd)
+        assert relmax(aux, pre[M // 3:]) <= tol
+        out, _ = run_gemm(A, B, prec, _lib.GEMM_TCGEN05, bias=bias, residual=res)
+        ref, _ = ref_gemm(A, B, bias=bias, residual=res)
+        assert relmax(out, ref) <= tol, (M, N, Kd)
+        out, _ = run_gemm(A, B, prec, _lib.GEMM_TCGEN05, gelu_aux=auxg)
+        ref, _ = ref_gemm(A, B, gelu_aux=auxg)
+        assert relmax(out, ref) <= tol, (M, N, Kd)
+        out2, _ = run_gemm(A, B, prec, _lib.GEMM_TCGEN05, gelu_aux=auxg)
+        assert torch.equal(out, out2)  # fixed reduction order
+
+
 def test_gemm_f32_exact():
     """RPO_F32 uses true fp32 FMAs (no tf32): 1e-5 relative to the fp64 result."""
     M, N, Kd = 257, 130, 777
