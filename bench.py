@@ -36,6 +36,17 @@ def load_peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
 
 
+def ncu_traffic(key):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of a kernel, from the committed
+    `ncu --set full` capture (profiles/ncu_traffic.json, refreshed by tools/profile_step.sh runs); None if absent."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        d = json.load(open(p))[key]
+        return d["dram_read_bytes"] + d["dram_write_bytes"]
+    except Exception:
+        return None
+
+
 def synthetic_tokens(n_cls):
     import numpy as np
     import torch
@@ -180,14 +191,21 @@ def main_reference(args):
 
 # ---------------------------------------------------------------------------------------------------
 def time_kernel(fn, iters, warm=5):
+    """Seconds per launch: `iters` launches captured into one CUDA graph (as the step itself is), so that host-side
+    costs (ctypes, TMA descriptor encoding, launch) stay outside the CUDA-event interval."""
     import torch
     for _ in range(warm):
         fn(0)
     torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(iters):
+            fn(i)
+    g.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(iters):
-        fn(i)
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters * 1e-3  # seconds per launch
@@ -201,7 +219,6 @@ def kernel_rooflines(model, peaks):
     from rpo_b200 import _lib
     lib = _lib.load()
     dev = model.w_mm.device
-    st = _lib.stream_ptr(dev)
     arch, K, B = model.arch, model.K, WORKLOAD["batch_per_gpu"]
     S = (arch.v_res // arch.v_patch) ** 2 + 1
     D, H = arch.v_width, arch.v_heads
@@ -217,7 +234,8 @@ def kernel_rooflines(model, peaks):
     def attn(i):
         j = i % nbuf
         _lib.check(lib.rpo_ro_attention_fwd_dense(qkv[j].data_ptr(), qp[j].data_ptr(), out[j].data_ptr(),
-                                                  out[j].data_ptr() + B * S * D * 2, B, S, K, H, code, st))
+                                                  out[j].data_ptr() + B * S * D * 2, B, S, K, H, code,
+                                                  _lib.stream_ptr(dev)))
 
     t_attn = time_kernel(attn, 48)
     L = S + K
@@ -226,7 +244,7 @@ def kernel_rooflines(model, peaks):
     roof_attn = {
         "kernel": "ro_attn_fwd_tc = rpo_ro_attention_fwd_dense (tcgen05; vision, per layer: 32 images x 12 heads, L=221 queries, S=197 keys)",
         "bound": "hbm", "achieved": attn_bytes / t_attn / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
-        "frac": attn_bytes / t_attn / 1e9 / peaks["hbm"], "traffic": None,
+        "frac": attn_bytes / t_attn / 1e9 / peaks["hbm"], "traffic": ncu_traffic("ro_attn_fwd_tc"),
         "peak_source": f"{peaks['source']} copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
         "us_per_launch": t_attn * 1e6, "algorithmic_bytes_per_launch": attn_bytes,
         "tensor_tflops": attn_flops / t_attn / 1e12, "tensor_frac_of_burst": attn_flops / t_attn / 1e12 / peaks["tf_burst"],
@@ -242,14 +260,15 @@ def kernel_rooflines(model, peaks):
     def gemm(i):
         j = i % 6
         _lib.check(lib.rpo_gemm_bias_act(A[j].data_ptr(), Kd, Wt[j].data_ptr(), Kd, Cm[j].data_ptr(), N, M, N, Kd,
-                                         bias.data_ptr(), 1, None, None, None, 0, code, _lib.GEMM_AUTO, st))
+                                         bias.data_ptr(), 1, None, None, None, 0, code, _lib.GEMM_AUTO,
+                                         _lib.stream_ptr(dev)))
 
     t_gemm = time_kernel(gemm, 48)
     flops = 2.0 * M * N * Kd
     roof_gemm = {
         "kernel": "gemm_tc (c_fc + bias + QuickGELU, M=7072 N=3072 K=768)", "bound": "tensor",
         "achieved": flops / t_gemm / 1e12, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
-        "frac": flops / t_gemm / 1e12 / peaks["tf_burst"], "traffic": None,
+        "frac": flops / t_gemm / 1e12 / peaks["tf_burst"], "traffic": ncu_traffic("gemm_fc"),
         "peak_source": f"{peaks['source']} cuBLAS bf16 burst (MEASURED_PEAKS.json bf16_tflops)",
         "us_per_launch": t_gemm * 1e6,
     }
