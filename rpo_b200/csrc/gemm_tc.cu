@@ -162,6 +162,7 @@ struct Epi {
   T *dst_row;        // C: same position
   const float *sk_partial = nullptr;  // stream-K: partial accumulators of the following clusters (this CTA's half)
   int sk_count = 0;
+  size_t sk_stride = 0;  // floats between the slots of consecutive contributors
 
   __device__ __forceinline__ void prefetch(int sc, int r0, uint4 (&pre)[PASSES]) {
     if (!src_row) return;
@@ -175,8 +176,20 @@ struct Epi {
   }
 
   // 32 accumulator columns of this warp's 32 rows -> staging slab.  sc0: first column of the slab inside the tile
+  // stream-K finisher with ONE contributor (the common case): this thread's share of the partial tile for the slab
+  // starting at tile column sc0, fetched ahead of use (8 x 16 bytes: two 16-column halves x four column groups)
+  __device__ __forceinline__ void load_partial(int sc0, int warp, int lane, float4 (&pp)[8]) {
+    const int q = warp & 3, half_id = ((warp - 2) % GROUP_WARPS) >> 2;
+    if (half_id >= DRAIN_HALVES) return;
+    const float4 *slot = reinterpret_cast<const float4 *>(sk_partial);
+    const int c0 = sc0 + half_id * 32;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pp[j] = __ldcg(slot + (size_t)(c0 / 4 + j) * BM + q * 32 + lane);
+  }
+
   __device__ __forceinline__ void drain(const Epilogue<T> &ep, uint32_t tmem_acc, uint32_t slab, uint32_t bias_s,
-                                        long long m0, int n0, int sc0, long long ldc, int warp, int lane) {
+                                        long long m0, int n0, int sc0, long long ldc, int warp, int lane,
+                                        const float4 (&pp)[8]) {
     const int q = warp & 3;
     const int half_id = ((warp - 2) % GROUP_WARPS) >> 2;
     if (half_id >= DRAIN_HALVES) return;
@@ -187,8 +200,18 @@ struct Epi {
       const int ch = c0 + hh * 16;
       uint32_t acc[16];
       tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)ch, acc);
-      for (int p = 0; p < sk_count; ++p) {  // stream-K finisher: add the partial sums, in cluster order
-        const float4 *slot = reinterpret_cast<const float4 *>(sk_partial + (size_t)p * (2 * BM * 256));
+      if (sk_count == 1) {  // prefetched by load_partial
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 v = pp[hh * 4 + j];
+          acc[4 * j] = __float_as_uint(__uint_as_float(acc[4 * j]) + v.x);
+          acc[4 * j + 1] = __float_as_uint(__uint_as_float(acc[4 * j + 1]) + v.y);
+          acc[4 * j + 2] = __float_as_uint(__uint_as_float(acc[4 * j + 2]) + v.z);
+          acc[4 * j + 3] = __float_as_uint(__uint_as_float(acc[4 * j + 3]) + v.w);
+        }
+      }
+      for (int p = 0; p < (sk_count > 1 ? sk_count : 0); ++p) {  // general case: add the partial sums, in cluster order
+        const float4 *slot = reinterpret_cast<const float4 *>(sk_partial + (size_t)p * sk_stride);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float4 v = __ldcg(slot + (size_t)(ch / 4 + j) * BM + r_loc);
@@ -281,7 +304,9 @@ struct Epi {
     src_row = src ? src + pos : nullptr;
     dst_row = C + pos;
     uint4 pre[PASSES];
+    float4 pp[8];
     prefetch(grp * SLAB, r0, pre);
+    if (sk_count == 1) load_partial(grp * SLAB, warp, lane, pp);
     if (GROUPS > 1) named_bar_sync<Thr<BN>::EPI_WARPS * 32>(1);  // the other group has left the previous tile's drains
     for (int i = etid_all; i < BN; i += Thr<BN>::EPI_WARPS * 32) {
       const float bv = ep.bias ? tof<T>(ep.bias[n0 + i]) : 0.f;
@@ -295,7 +320,8 @@ struct Epi {
 #pragma unroll 1
     for (int i = 0; i < MY_SLABS; ++i) {
       const int sl = grp + i * GROUPS;
-      drain(ep, tmem_acc, slab, bias_s, m0, n0, sl * SLAB, ldc, warp, lane);
+      drain(ep, tmem_acc, slab, bias_s, m0, n0, sl * SLAB, ldc, warp, lane, pp);
+      if (sk_count == 1 && i + 1 < MY_SLABS) load_partial((sl + GROUPS) * SLAB, warp, lane, pp);
       if (i == MY_SLABS - 1) {  // this warp has read its last accumulator columns
         tc_fence_before();
         __syncwarp();
@@ -505,13 +531,25 @@ struct Seg {
   int tile, k0, k1;
 };
 struct Sched {
-  int sk, num_tiles, num_kb, nc, next_tile;
-  long long pos, end;
-  __device__ __forceinline__ void init(int stream_k, int tiles, int kb, int c, int n_clusters) {
+  // stream-K is LANE-ALIGNED: the clusters form groups of `lanes` = num_n_tiles; a group walks a contiguous range of
+  // (m-tile, k-block) units and cluster j of the group computes n-tile j of every unit.  The n-tiles of an m-tile thus
+  // stay in lockstep on neighbouring clusters and share the A tiles through L2 (splitting each tile's K range
+  // independently puts them at different K offsets: every cluster then streams its own copy of A from HBM).
+  int sk, num_tiles, num_kb, nc, next_tile, lanes, grp, lane_id, groups;
+  long long pos, end, total;
+  __device__ __forceinline__ void init(int stream_k, int tiles, int kb, int c, int n_clusters, int num_n_tiles) {
     sk = stream_k; num_tiles = tiles; num_kb = kb; nc = n_clusters; next_tile = c;
-    const long long total = (long long)tiles * kb;
-    pos = total * c / n_clusters;
-    end = total * (c + 1) / n_clusters;
+    lanes = num_n_tiles;
+    groups = n_clusters / lanes;
+    grp = c / lanes;
+    lane_id = c % lanes;
+    total = (long long)(tiles / lanes) * kb;
+    if (sk && grp < groups) {
+      pos = total * grp / groups;
+      end = total * (grp + 1) / groups;
+    } else {
+      pos = end = 0;  // clusters beyond the last full group idle in stream-K mode
+    }
   }
   __device__ __forceinline__ bool next(Seg &s) {
     if (!sk) {
@@ -521,12 +559,23 @@ struct Sched {
       return true;
     }
     if (pos >= end) return false;
-    s.tile = (int)(pos / num_kb);
+    s.tile = (int)(pos / num_kb) * lanes + lane_id;
     s.k0 = (int)(pos % num_kb);
     const long long rem = end - pos;
     s.k1 = rem < (long long)(num_kb - s.k0) ? s.k0 + (int)rem : num_kb;
     pos += s.k1 - s.k0;
     return true;
+  }
+  // number of later groups that hold the rest [k1, num_kb) of the m-tile whose head this group computes
+  __device__ __forceinline__ int contributors(const Seg &s) const {
+    const long long tile_end = (long long)(s.tile / lanes + 1) * num_kb;
+    long long p = (long long)(s.tile / lanes) * num_kb + s.k1;
+    int cnt = 0;
+    while (p < tile_end) {
+      ++cnt;
+      p = total * (grp + cnt + 1) / groups;
+    }
+    return cnt;
   }
 };
 static constexpr int SK_MAX_CLUSTERS = 128;
@@ -543,7 +592,7 @@ __device__ __forceinline__ void st_release_gpu(int *p, int v) {
 
 template <int BN>
 struct Cfg2 {
-  static constexpr int STAGES = BN >= 256 ? 6 : 8;
+  static constexpr int STAGES = BN >= 192 ? 6 : 8;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / 2) * BK * 2;  // this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -615,7 +664,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
     // ===== TMA producer (both CTAs; transaction bytes of both land on the leader's barrier) =====
     if (lane == 0) {
       Sched sch;
-      sch.init(stream_k, num_tiles, num_kb, cluster_id, num_clusters);
+      sch.init(stream_k, num_tiles, num_kb, cluster_id, num_clusters, num_n_tiles);
       Seg sg;
       bool have = sch.next(sg);
       uint32_t pre = 0;
@@ -653,7 +702,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = make_idesc(Num<T>::dtype == RPO_BF16 ? 1 : 0, 2 * BM, BN);
       Sched sch;
-      sch.init(stream_k, num_tiles, num_kb, cluster_id, num_clusters);
+      sch.init(stream_k, num_tiles, num_kb, cluster_id, num_clusters, num_n_tiles);
       Seg sg;
       uint32_t it = 0, t = 0;
       for (; sch.next(sg); ++t) {
@@ -683,7 +732,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
     // ===== epilogue (both CTAs, 128 rows x BN columns each) =====
     Epi<T, BN> epi;
     Sched sch;
-    sch.init(stream_k, num_tiles, num_kb, cluster_id, num_clusters);
+    sch.init(stream_k, num_tiles, num_kb, cluster_id, num_clusters, num_n_tiles);
     Seg sg;
     uint32_t t = 0;
     int *sk_flags = reinterpret_cast<int *>(ep.sk_ws);
@@ -723,15 +772,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
       }
       int n_contrib = 0;
       if (sg.k1 < num_kb) {
-        // ---- finisher of a split tile: clusters cluster_id+1.. hold the rest of its K range ----
-        const long long tile_end = (long long)(sg.tile + 1) * num_kb, total = (long long)num_tiles * num_kb;
-        long long p = (long long)sg.tile * num_kb + sg.k1;
-        while (p < tile_end) {
-          ++n_contrib;
-          p = total * (cluster_id + n_contrib + 1) / num_clusters;
-        }
+        // ---- finisher of a split tile: the same lane of the following group(s) holds the rest of its K range ----
+        n_contrib = sch.contributors(sg);
         if (etid < n_contrib) {
-          const int *f = sk_flags + (cluster_id + 1 + etid) * 2 + rank;
+          const int *f = sk_flags + (cluster_id + (1 + etid) * sch.lanes) * 2 + rank;
           long long t0 = clock64();
           while (ld_acquire_gpu(f) == 0) {
             if (clock64() - t0 > 4000000000LL) __trap();
@@ -747,13 +791,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
         if (lane == 0) mbar_arrive_cluster(lead_empty);
         continue;
       }
-      epi.sk_partial = n_contrib ? sk_slots + ((size_t)(cluster_id + 1) * 2 + rank) * (BM * 256) : nullptr;
+      epi.sk_partial = n_contrib ? sk_slots + ((size_t)(cluster_id + sch.lanes) * 2 + rank) * (BM * 256) : nullptr;
       epi.sk_count = n_contrib;
+      epi.sk_stride = (size_t)sch.lanes * (2 * BM * 256);
       epi.run_tile(ep, tmem_acc, smem_u32(cstage), smem_u32(bias_s), C, m0, n0, M, ldc, acc_full(a), (t >> 1) & 1,
                    [&]() { mbar_arrive_cluster(lead_empty); });
       if (n_contrib) {  // all partial reads are done (they precede the last slab barrier): re-arm the flags
         named_bar_sync<Thr<BN>::EPI_WARPS * 32>(1);
-        if (etid < n_contrib) sk_flags[(cluster_id + 1 + etid) * 2 + rank] = 0;
+        if (etid < n_contrib) sk_flags[(cluster_id + (1 + etid) * sch.lanes) * 2 + rank] = 0;
       }
     }
   }
@@ -817,10 +862,14 @@ static int launch_pair(const T *A, long long lda, const T *B, long long ldb, T *
   // property the parity tests check.
   const char *sk_env = getenv("RPO_GEMM_STREAMK");  // read per call: the parity tests switch it on for one case
   const bool use_sk = sk_env && sk_env[0] == '1';
-  if (ep.sk_ws && use_sk && num_tiles > pairs && pairs <= SK_MAX_CLUSTERS) {
+  if (ep.sk_ws && use_sk && num_tiles > pairs && pairs <= SK_MAX_CLUSTERS && num_n_tiles <= pairs) {
+    const long long m_tiles = num_tiles / num_n_tiles, groups = pairs / num_n_tiles;
     const long long rounds = (num_tiles + pairs - 1) / pairs;
-    const double waste = 1.0 - (double)num_tiles / (double)(rounds * pairs);
-    if (waste > 0.08) {
+    // k-block steps per cluster: data-parallel vs lane-aligned stream-K (clusters beyond the last full group idle)
+    const int num_kb = Kd / BK;
+    const double dp = (double)rounds * num_kb, skc = (double)m_tiles * num_kb / (double)groups;
+    // K >= 2048 only: at K = 768 a tile's main loop is shorter than the partial-tile round trip (measured slower)
+    if (m_tiles >= groups && skc < 0.85 * dp && Kd >= 2048) {
       stream_k = 1;
       grid = 2 * pairs;
     }
@@ -1033,12 +1082,13 @@ static int launch_splitk(const T *A, long long lda, const T *B, long long ldb, T
 // ---- tile configuration --------------------------------------------------------------------------
 // P256/P128: CTA pairs, 256 x BN tiles.  S128/S64/S32: one CTA per SM, 128 x BN tiles, deep ring.
 // L64/L32: light 128 x BN tiles, two CTAs per SM.  RPO_GEMM_FORCE=<name> pins one (tuning sweeps).
-enum { CFG_P256 = 0, CFG_P128, CFG_S128, CFG_S64, CFG_S32, CFG_L64, CFG_L32, CFG_K4, CFG_K2, CFG_COUNT };
-static const char *const kCfgNames[CFG_COUNT] = {"p256", "p128", "s128", "s64", "s32", "l64", "l32", "k4", "k2"};
+enum { CFG_P256 = 0, CFG_P128, CFG_S128, CFG_S64, CFG_S32, CFG_L64, CFG_L32, CFG_K4, CFG_K2, CFG_P192, CFG_COUNT };
+static const char *const kCfgNames[CFG_COUNT] = {"p256", "p128", "s128", "s64", "s32", "l64", "l32", "k4", "k2", "p192"};
 
 static bool cfg_valid(int cfg, int N) {
   switch (cfg) {
     case CFG_P256: return N % 256 == 0;
+    case CFG_P192: return N % 192 == 0;
     case CFG_P128: case CFG_S128: return N % 128 == 0;
     case CFG_S64: case CFG_L64: case CFG_K4: case CFG_K2: return N % 64 == 0;
     default: return N % 32 == 0;
@@ -1107,6 +1157,7 @@ int gemm_tcgen05(const T *A, long long lda, const T *B, long long ldb, T *C, lon
     switch (cfg) {
       case tc::CFG_P256: return tc::launch_pair<T, 256>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);
       case tc::CFG_P128: return tc::launch_pair<T, 128>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);
+      case tc::CFG_P192: return tc::launch_pair<T, 192>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);
       case tc::CFG_S128: return tc::launch<T, 128, false>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);
       case tc::CFG_S64: return tc::launch<T, 64, false>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);
       case tc::CFG_S32: return tc::launch<T, 32, false>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);
