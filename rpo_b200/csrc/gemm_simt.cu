@@ -31,16 +31,27 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const T *__restrict__ A,
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = 0; k0 < Kd; k0 += SBK) {
+  // register double buffer: the global loads of slab k0 + SBK are in flight while slab k0 is multiplied
+  float ra[4], rb[4];
+  auto fetch = [&](int k0) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       int k = k0 + lk + e;
       long long m = m0 + lr;
       int n = n0 + lr;
-      As[lk + e][lr] = (m < M && k < Kd) ? tof<T>(A[m * sam + k * sak]) : 0.f;
-      Bs[lk + e][lr] = (n < N && k < Kd) ? tof<T>(B[n * sbn + k * sbk]) : 0.f;
+      ra[e] = (m < M && k < Kd) ? tof<T>(A[m * sam + k * sak]) : 0.f;
+      rb[e] = (n < N && k < Kd) ? tof<T>(B[n * sbn + k * sbk]) : 0.f;
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < Kd; k0 += SBK) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      As[lk + e][lr] = ra[e];
+      Bs[lk + e][lr] = rb[e];
     }
     __syncthreads();
+    if (k0 + SBK < Kd) fetch(k0 + SBK);
 #pragma unroll
     for (int k = 0; k < SBK; ++k) {
       float4 a = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
