@@ -805,6 +805,9 @@ int rpo_gemm_bias_act_ws(const void *A, int64_t lda, const void *B, int64_t ldb,
              ep.aux_row0 = aux_row0;
              ep.act = act;
              ep.sk_ws = workspace;
+             // benchmarking aid: treat B as a frozen weight (tiles fetched before the PDL dependency wait), as the
+             // towers do.  Only valid when no earlier launch on the stream writes B.
+             if (const char *fz = getenv("RPO_GEMM_ASSUME_FROZEN_B")) ep.b_frozen = fz[0] == '1';
              return gemm_dispatch<T>(backend, (const T *)A, lda, (const T *)B, ldb, (T *)C, ldc, M, N, Kd, ep,
                                      (cudaStream_t)stream);
            }()));

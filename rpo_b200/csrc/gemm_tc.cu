@@ -163,6 +163,7 @@ struct Epi {
   const float *sk_partial = nullptr;  // stream-K: partial accumulators of the following clusters (this CTA's half)
   int sk_count = 0;
   size_t sk_stride = 0;  // floats between the slots of consecutive contributors
+  long long t_acc = 0;   // clock when the accumulator became available (trace only)
 
   __device__ __forceinline__ void prefetch(int sc, int r0, uint4 (&pre)[PASSES]) {
     if (!src_row) return;
@@ -313,6 +314,7 @@ struct Epi {
       asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + (uint32_t)(i * 4)), "f"(bv) : "memory");
     }
     mbar_wait(acc_full_bar, acc_full_parity);
+    t_acc = clock64();
     tc_fence_after();
     named_bar_sync<Thr<BN>::EPI_WARPS * 32>(1);  // bias visible to every epilogue warp
     const uint32_t slab = cstage + (uint32_t)(grp * G::SLAB_BYTES);
@@ -339,8 +341,17 @@ template <typename T, int BN, bool LIGHT>
 __global__ void __launch_bounds__(Thr<BN>::THREADS, (Cfg<BN, LIGHT>::MIN_CTAS))
     gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    T *__restrict__ C, long long ldc, long long M, int N, int Kd, Epilogue<T> ep, int num_n_tiles,
-                   int num_tiles) {
+                   int num_tiles, long long *trace) {
   using C_ = Cfg<BN, LIGHT>;
+  // RPO_GEMM_TRACE (tuning aid): per CTA [globaltimer at entry, clock at entry, after setup, dependency wait passed,
+  // first operands landed, accumulator of the first tile complete, first tile written, exit clock, globaltimer at exit]
+  long long *tr = trace ? trace + (size_t)blockIdx.x * 16 : nullptr;
+  if (tr && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    tr[0] = (long long)gt;
+    tr[1] = clock64();
+  }
   using T2 = typename Pk<T>::T2;
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles need 1024-byte alignment
@@ -381,6 +392,7 @@ __global__ void __launch_bounds__(Thr<BN>::THREADS, (Cfg<BN, LIGHT>::MIN_CTAS))
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_trigger();  // the next kernel on the stream may start its own prologue
+  if (tr && threadIdx.x == 0) tr[2] = clock64();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -395,8 +407,13 @@ __global__ void __launch_bounds__(Thr<BN>::THREADS, (Cfg<BN, LIGHT>::MIN_CTAS))
           mbar_arrive_expect_tx(full_bar(pre), C_::STAGE_BYTES);
           tma_load_2d(smem_base + pre * C_::STAGE_BYTES + C_::A_BYTES, &map_b, full_bar(pre), pre * BK, n0);
         }
+        // ... and the rest of this tile's weight k-blocks go to L2 meanwhile: the weights (250 MB per step) never stay in
+        // L2 from one step to the next, and a 3-stage ring cannot cover HBM latency (measured 480 cycles per k-block
+        // = ring depth x 0.78 us on the small-M GEMMs)
+        for (int kb = npre; kb < num_kb; ++kb) tma_prefetch_l2_2d(&map_b, kb * BK, n0);
       }
       pdl_wait();
+      if (tr) tr[3] = clock64();
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / num_n_tiles) * BM, n0 = (tile % num_n_tiles) * BN;
@@ -427,6 +444,7 @@ __global__ void __launch_bounds__(Thr<BN>::THREADS, (Cfg<BN, LIGHT>::MIN_CTAS))
           const int s = it % C_::STAGES;
           const uint32_t ph = (it / C_::STAGES) & 1;
           mbar_wait(full_bar(s), ph);
+          if (tr && it == 0) tr[4] = clock64();
           tc_fence_after();
           const uint32_t a_addr = smem_base + s * C_::STAGE_BYTES;
           const uint64_t adesc = make_smem_desc(a_addr);
@@ -453,10 +471,20 @@ __global__ void __launch_bounds__(Thr<BN>::THREADS, (Cfg<BN, LIGHT>::MIN_CTAS))
       const uint32_t empty_a = acc_empty(a);
       epi.run_tile(ep, tmem_base + (uint32_t)(a * BN), smem_u32(cstage), smem_u32(bias_s), C, m0, n0, M, ldc, acc_full(a), (t >> 1) & 1,
                    [&]() { mbar_arrive(empty_a); });
+      if (tr && t == 0 && threadIdx.x == 64) {
+        tr[5] = epi.t_acc;
+        tr[6] = clock64();
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (tr && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    tr[7] = clock64();
+    tr[8] = (long long)gt;
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C_::TMEM_COLS);
@@ -828,10 +856,12 @@ static int launch(const T *A, long long lda, const T *B, long long ldb, T *C, lo
   RPO_TRY(make_map(&map_b, Num<T>::dtype, B, N, Kd, ldb, BN));
   const int num_n_tiles = N / BN;
   const long long num_tiles = ((M + BM - 1) / BM) * num_n_tiles;
+  long long *trace = nullptr;
+  if (const char *e = getenv("RPO_GEMM_TRACE")) trace = reinterpret_cast<long long *>(strtoull(e, nullptr, 0));
   const long long slots = (long long)sm_count() * C_::MIN_CTAS;
   const int grid = (int)(num_tiles < slots ? num_tiles : slots);
   RPO_CHECK_CUDA(launch_pdl(gemm_tc_kernel<T, BN, LIGHT>, dim3(grid), dim3(Thr<BN>::THREADS), C_::SMEM_BYTES, st, map_a, map_b, C, ldc, M, N,
-                            Kd, ep, num_n_tiles, (int)num_tiles));
+                            Kd, ep, num_n_tiles, (int)num_tiles, trace));
   RPO_LAUNCH_CHECK();
   return RPO_OK;
 }
