@@ -134,7 +134,10 @@ namespace rpo {
 template <typename T>
 static Epilogue<T> frozen_ep(void *sk_ws = nullptr) {
   Epilogue<T> e{};
-  e.b_frozen = 1;
+  // 1: weight tiles of the first ring fill are fetched ahead of the PDL dependency wait; 2 (RPO_GEMM_L2_PREFETCH=1): the
+  // rest of the first tile's weight k-blocks is also prefetched into L2
+  static const int mode = [] { const char *v = getenv("RPO_GEMM_L2_PREFETCH"); return (v && v[0] == '1') ? 2 : 1; }();
+  e.b_frozen = mode;
   e.sk_ws = sk_ws;
   return e;
 }

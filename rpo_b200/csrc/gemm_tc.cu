@@ -33,12 +33,6 @@ static constexpr int BK = 64;  // 64 x 2 B = 128 B = one swizzle row
 static constexpr int UMMA_K = 16;
 // Epilogue warps come in groups of 8 (4 TMEM lane quarters x 2 column halves of a 64-column slab).  Group g
 // takes slabs g, g + GROUPS, ... with its own staging buffer and named barrier.
-// Warp roles of the persistent kernels: 0 = TMA producer of A, 1 = MMA issuer, 2 = TMA producer of B, 3.. = epilogue.
-// TWO producer threads because one thread sustains only one cp.async.bulk.tensor per ~335 cycles whatever the box
-// size (tools/probe/tma_probe.cu): with both operand loads of a k-block on one thread the main loop could not go
-// below ~670 cycles per k-block -- slower than the tensor core's 256-512.
-static constexpr int FIRST_EPI_WARP = 3;
-static constexpr int NON_EPI_THREADS = FIRST_EPI_WARP * 32;
 static constexpr int GROUP_WARPS = 8;
 static constexpr int GROUP_THREADS = GROUP_WARPS * 32;
 template <int BN>
@@ -47,7 +41,7 @@ struct Thr {
   // caps registers at 96 (spills) and adds a tile-level barrier; the machinery stays, the switch is off.
   static constexpr int GROUPS = 1;
   static constexpr int EPI_WARPS = GROUPS * GROUP_WARPS;
-  static constexpr int THREADS = NON_EPI_THREADS + EPI_WARPS * 32;  // A producer, MMA issuer, B producer, epilogue warps
+  static constexpr int THREADS = 64 + EPI_WARPS * 32;  // producer warp + MMA warp + epilogue warps
 };
 template <int NTHREADS>
 __device__ __forceinline__ void named_bar_sync(int id) {
@@ -186,7 +180,7 @@ struct Epi {
   // stream-K finisher with ONE contributor (the common case): this thread's share of the partial tile for the slab
   // starting at tile column sc0, fetched ahead of use (8 x 16 bytes: two 16-column halves x four column groups)
   __device__ __forceinline__ void load_partial(int sc0, int warp, int lane, float4 (&pp)[8]) {
-    const int q = warp & 3, half_id = ((warp - FIRST_EPI_WARP) % GROUP_WARPS) >> 2;
+    const int q = warp & 3, half_id = ((warp - 2) % GROUP_WARPS) >> 2;
     if (half_id >= DRAIN_HALVES) return;
     const float4 *slot = reinterpret_cast<const float4 *>(sk_partial);
     const int c0 = sc0 + half_id * 32;
@@ -198,7 +192,7 @@ struct Epi {
                                         long long m0, int n0, int sc0, long long ldc, int warp, int lane,
                                         const float4 (&pp)[8]) {
     const int q = warp & 3;
-    const int half_id = ((warp - FIRST_EPI_WARP) % GROUP_WARPS) >> 2;
+    const int half_id = ((warp - 2) % GROUP_WARPS) >> 2;
     if (half_id >= DRAIN_HALVES) return;
     const int r_loc = q * 32 + lane;
     const int c0 = sc0 + half_id * 32;  // tile-local first column of this warp's 32
@@ -298,7 +292,7 @@ struct Epi {
                                            uint32_t acc_full_bar, uint32_t acc_full_parity, Arrive arrive_acc_empty) {
     constexpr int GROUPS = Thr<BN>::GROUPS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int etid_all = threadIdx.x - NON_EPI_THREADS;
+    const int etid_all = threadIdx.x - 64;
     const int grp = etid_all / GROUP_THREADS;   // warp group: takes slabs grp, grp + GROUPS, ...
     const int etid = etid_all % GROUP_THREADS;
     const int r0 = etid / CH, c = etid % CH;
@@ -382,7 +376,7 @@ __global__ void __launch_bounds__(Thr<BN>::THREADS, (Cfg<BN, LIGHT>::MIN_CTAS))
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
     for (int s = 0; s < C_::STAGES; ++s) {
-      mbar_init(full_bar(s), 2);  // one arrival (+ its transaction bytes) per producer thread
+      mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -401,45 +395,39 @@ __global__ void __launch_bounds__(Thr<BN>::THREADS, (Cfg<BN, LIGHT>::MIN_CTAS))
   if (tr && threadIdx.x == 0) tr[2] = clock64();
 
   if (warp == 0) {
-    // ===== TMA producer of A (activations: after the dependency wait) =====
+    // ===== TMA producer =====
     if (lane == 0) {
+      // weight tiles of the first ring fill do not depend on the upstream kernel: fetch them before
+      // the dependency wait, so their HBM latency overlaps the previous kernel's tail
+      uint32_t pre = 0;
+      if (ep.b_frozen && (int)blockIdx.x < num_tiles) {
+        const int n0 = ((int)blockIdx.x % num_n_tiles) * BN;
+        const int npre = num_kb < C_::STAGES ? num_kb : C_::STAGES;
+        for (; (int)pre < npre; ++pre) {
+          mbar_arrive_expect_tx(full_bar(pre), C_::STAGE_BYTES);
+          tma_load_2d(smem_base + pre * C_::STAGE_BYTES + C_::A_BYTES, &map_b, full_bar(pre), pre * BK, n0);
+        }
+        // ... and the rest of this tile's weight k-blocks go to L2 meanwhile: the weights (250 MB per step) never stay in
+        // L2 from one step to the next, and a 3-stage ring cannot cover HBM latency (measured 480 cycles per k-block
+        // = ring depth x 0.78 us on the small-M GEMMs)
+        if (ep.b_frozen > 1)
+          for (int kb = npre; kb < num_kb; ++kb) tma_prefetch_l2_2d(&map_b, kb * BK, n0);
+      }
       pdl_wait();
       if (tr) tr[3] = clock64();
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / num_n_tiles) * BM;
+        const int m0 = (tile / num_n_tiles) * BM, n0 = (tile % num_n_tiles) * BN;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % C_::STAGES;
           const uint32_t ph = (it / C_::STAGES) & 1;
-          mbar_wait(empty_bar(s), ph ^ 1);  // fresh barrier: parity-1 wait passes immediately
-          mbar_arrive_expect_tx(full_bar(s), C_::A_BYTES);
-          tma_load_2d(smem_base + s * C_::STAGE_BYTES, &map_a, full_bar(s), kb * BK, m0);
-        }
-      }
-    }
-  } else if (warp == 2) {
-    // ===== TMA producer of B =====
-    if (lane == 0) {
-      // frozen weights do not depend on the upstream kernel: the ring starts filling with weight tiles before the
-      // dependency wait, and the rest of the first tile's weight k-blocks is pulled into L2 meanwhile (the 250 MB of
-      // weights never survive in L2 from one step to the next)
-      if (ep.b_frozen) {
-        if ((int)blockIdx.x < num_tiles) {
-          const int n0 = ((int)blockIdx.x % num_n_tiles) * BN;
-          for (int kb = C_::STAGES; kb < num_kb; ++kb) tma_prefetch_l2_2d(&map_b, kb * BK, n0);
-        }
-      } else {
-        pdl_wait();
-      }
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n0 = (tile % num_n_tiles) * BN;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % C_::STAGES;
-          const uint32_t ph = (it / C_::STAGES) & 1;
-          mbar_wait(empty_bar(s), ph ^ 1);
-          mbar_arrive_expect_tx(full_bar(s), C_::B_BYTES);
-          tma_load_2d(smem_base + s * C_::STAGE_BYTES + C_::A_BYTES, &map_b, full_bar(s), kb * BK, n0);
+          const uint32_t a_dst = smem_base + s * C_::STAGE_BYTES;
+          if (it >= pre) {
+            mbar_wait(empty_bar(s), ph ^ 1);  // fresh barrier: parity-1 wait passes immediately
+            mbar_arrive_expect_tx(full_bar(s), C_::STAGE_BYTES);
+            tma_load_2d(a_dst + C_::A_BYTES, &map_b, full_bar(s), kb * BK, n0);
+          }
+          tma_load_2d(a_dst, &map_a, full_bar(s), kb * BK, m0);
         }
       }
     }
@@ -484,7 +472,7 @@ __global__ void __launch_bounds__(Thr<BN>::THREADS, (Cfg<BN, LIGHT>::MIN_CTAS))
       const uint32_t empty_a = acc_empty(a);
       epi.run_tile(ep, tmem_base + (uint32_t)(a * BN), smem_u32(cstage), smem_u32(bias_s), C, m0, n0, M, ldc, acc_full(a), (t >> 1) & 1,
                    [&]() { mbar_arrive(empty_a); });
-      if (tr && t == 0 && threadIdx.x == NON_EPI_THREADS) {
+      if (tr && t == 0 && threadIdx.x == 64) {
         tr[5] = epi.t_acc;
         tr[6] = clock64();
       }
@@ -679,7 +667,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
     for (int s = 0; s < C_::STAGES; ++s) {
-      mbar_init(full_bar(s), 2);  // leader only: one arrival per producer thread, bytes of both CTAs
+      mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -702,40 +690,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
   pdl_trigger();
 
   if (warp == 0) {
-    // ===== TMA producer of A (both CTAs; transaction bytes of both land on the leader's barrier) =====
+    // ===== TMA producer (both CTAs; transaction bytes of both land on the leader's barrier) =====
     if (lane == 0) {
       Sched sch;
       sch.init(stream_k, num_tiles, num_kb, cluster_id, num_clusters, num_n_tiles);
       Seg sg;
-      pdl_wait();
-      uint32_t it = 0;
-      while (sch.next(sg)) {
-        const int m0 = (sg.tile / num_n_tiles) * (2 * BM) + (int)rank * BM;
-        for (int kb = sg.k0; kb < sg.k1; ++kb, ++it) {
-          const int s = it % C_::STAGES;
-          const uint32_t ph = (it / C_::STAGES) & 1;
-          mbar_wait(empty_bar(s), ph ^ 1);
-          if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * C_::A_BYTES);
-          tma_load_2d_pair(smem_base + s * C_::STAGE_BYTES, &map_a, mapa_shared(full_bar(s), 0), kb * BK, m0);
+      bool have = sch.next(sg);
+      uint32_t pre = 0;
+      if (ep.b_frozen && have) {  // weight tiles ahead of the dependency wait (see gemm_tc_kernel)
+        const int n0 = (sg.tile % num_n_tiles) * BN + (int)rank * (BN / 2);
+        const int nk = sg.k1 - sg.k0;
+        const int npre = nk < C_::STAGES ? nk : C_::STAGES;
+        for (; (int)pre < npre; ++pre) {
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(pre), 2 * C_::STAGE_BYTES);
+          tma_load_2d_pair(smem_base + pre * C_::STAGE_BYTES + C_::A_BYTES, &map_b, mapa_shared(full_bar(pre), 0),
+                           (sg.k0 + (int)pre) * BK, n0);
         }
       }
-    }
-  } else if (warp == 2) {
-    // ===== TMA producer of B (this CTA's half of the tile's rows of B) =====
-    if (lane == 0) {
-      Sched sch;
-      sch.init(stream_k, num_tiles, num_kb, cluster_id, num_clusters, num_n_tiles);
-      Seg sg;
-      if (!ep.b_frozen) pdl_wait();  // frozen weights: start ahead of the dependency wait (see gemm_tc_kernel)
+      pdl_wait();
       uint32_t it = 0;
-      while (sch.next(sg)) {
+      for (; have; have = sch.next(sg)) {
+        const int m0 = (sg.tile / num_n_tiles) * (2 * BM) + (int)rank * BM;
         const int n0 = (sg.tile % num_n_tiles) * BN + (int)rank * (BN / 2);
         for (int kb = sg.k0; kb < sg.k1; ++kb, ++it) {
           const int s = it % C_::STAGES;
           const uint32_t ph = (it / C_::STAGES) & 1;
-          mbar_wait(empty_bar(s), ph ^ 1);
-          if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * C_::B_BYTES);
-          tma_load_2d_pair(smem_base + s * C_::STAGE_BYTES + C_::A_BYTES, &map_b, mapa_shared(full_bar(s), 0), kb * BK, n0);
+          const uint32_t lead_full = mapa_shared(full_bar(s), 0);
+          const uint32_t a_dst = smem_base + s * C_::STAGE_BYTES;
+          if (it >= pre) {
+            mbar_wait(empty_bar(s), ph ^ 1);
+            if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * C_::STAGE_BYTES);
+            tma_load_2d_pair(a_dst + C_::A_BYTES, &map_b, lead_full, kb * BK, n0);
+          }
+          tma_load_2d_pair(a_dst, &map_a, lead_full, kb * BK, m0);
         }
       }
     }
@@ -779,7 +766,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
     uint32_t t = 0;
     int *sk_flags = reinterpret_cast<int *>(ep.sk_ws);
     float *sk_slots = reinterpret_cast<float *>(reinterpret_cast<char *>(ep.sk_ws) + SK_FLAG_BYTES);
-    const int q = warp & 3, part = (warp - FIRST_EPI_WARP) >> 2, etid = threadIdx.x - NON_EPI_THREADS;
+    const int q = warp & 3, part = (warp - 2) >> 2, etid = threadIdx.x - 64;
     constexpr int PART_COLS = BN / (Thr<BN>::EPI_WARPS / 4);  // accumulator columns per warp in the stream-K partial
     pdl_wait();
     for (; sch.next(sg); ++t) {
