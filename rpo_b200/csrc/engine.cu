@@ -126,6 +126,7 @@ struct RpoHandle {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool overlap = true;
+  int skip = 0;  // diagnostics only (RPO_DEBUG_SKIP): 1 = no text tower launches, 2 = no vision tower launches
 };
 
 namespace rpo {
@@ -263,7 +264,7 @@ static int forward_impl(RpoHandle *hd, const void *image, int image_dtype, int B
       st = hd->side;
     }
     RPO_TRY(broadcast_rows<T>((const T *)text_prompt, (T *)t.x_in + t.Mc * Dt, C, K, Dt, st));
-    RPO_TRY(tower_forward<T>(hd, t, false, true, st));
+    if (hd->skip != 1) RPO_TRY(tower_forward<T>(hd, t, false, true, st));
     T *xt_out = at<T>(t.x_in, (long long)t.layers * t.Mtot_max * Dt) + t.Mc * Dt;
     RPO_TRY(layernorm_fwd<T>(xt_out, hd->w.ln_final_w, hd->w.ln_final_b, (T *)hd->hp_t, Mp_t, Dt, st));
     Epilogue<T> ep = frozen_ep<T>();
@@ -280,7 +281,7 @@ static int forward_impl(RpoHandle *hd, const void *image, int image_dtype, int B
   RPO_TRY(vision_assemble_lnpre<T>((const T *)hd->patch_emb, hd->w.cls_emb, hd->w.v_pos, nullptr, nullptr,
                                    (const T *)img_prompt, x_raw, x_raw + v.Mc * Dv, B, S, K, Dv, st));
   RPO_TRY(layernorm_fwd<T>(x_raw, hd->w.ln_pre_w, hd->w.ln_pre_b, (T *)v.x_in, v.Mc + Mp_v, Dv, st));
-  RPO_TRY(tower_forward<T>(hd, v, true, true, st));
+  if (hd->skip != 2) RPO_TRY(tower_forward<T>(hd, v, true, true, st));
   // img_f = ln_post(x[:, -K:, :]) @ proj                                 (:210)
   T *xv_out = at<T>(v.x_in, (long long)v.layers * v.Mtot_max * Dv) + v.Mc * Dv;
   RPO_TRY(layernorm_fwd<T>(xv_out, hd->w.ln_post_w, hd->w.ln_post_b, (T *)hd->hp_v, Mp_v, Dv, st));
@@ -328,7 +329,7 @@ static int backward_impl(RpoHandle *hd, float *grad_flat, cudaStream_t st) {
                              Dt, E, ep, st));
     T *xt_out = at<T>(t.x_in, (long long)t.layers * t.Mtot_max * Dt) + t.Mc * Dt;
     RPO_TRY(layernorm_bwd<T>((const T *)t.dh, xt_out, hd->w.ln_final_w, nullptr, (T *)t.dx, Mp_t, Dt, st));
-    RPO_TRY(tower_backward<T>(hd, t, st));
+    if (hd->skip != 1) RPO_TRY(tower_backward<T>(hd, t, st));
     // d text_prompt: the prompt is shared by all classes (trainers/rpo.py:176-177)
     RPO_TRY(reduce_groups_f32<T>((const T *)t.dx, grad_flat, C, K, Dt, 1.0f / gs, st));
     if (hd->overlap) RPO_CHECK_CUDA(cudaEventRecord(hd->ev_join, hd->side));
@@ -338,7 +339,7 @@ static int backward_impl(RpoHandle *hd, float *grad_flat, cudaStream_t st) {
                            E, ep, st));
   T *xv_out = at<T>(v.x_in, (long long)v.layers * v.Mtot_max * Dv) + v.Mc * Dv;
   RPO_TRY(layernorm_bwd<T>((const T *)v.dh, xv_out, hd->w.ln_post_w, nullptr, (T *)v.dx, Mp_v, Dv, st));
-  RPO_TRY(tower_backward<T>(hd, v, st));
+  if (hd->skip != 2) RPO_TRY(tower_backward<T>(hd, v, st));
   // d img_prompt: sum over images, then through ln_pre (trainers/rpo.py:204-206)
   RPO_TRY(reduce_groups_f32<T>((const T *)v.dx, hd->dsum_v, B, K, Dv, 1.0f / gs, st));
   RPO_TRY(lnpre_prompt_bwd<T>(hd->dsum_v, (const T *)hd->img_prompt, hd->w.ln_pre_w, grad_flat + (size_t)K * Dt, K, Dv,
@@ -558,6 +559,7 @@ int rpo_create(const RpoConfig *cfg, RpoHandle **out) {
   {
     const char *e = getenv("RPO_SINGLE_STREAM");
     h->overlap = !(e && e[0] == '1');
+    if (const char *sk = getenv("RPO_DEBUG_SKIP")) h->skip = atoi(sk);
   }
   if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
