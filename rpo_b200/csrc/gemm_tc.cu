@@ -111,6 +111,18 @@ __device__ __forceinline__ typename Pk<T>::T2 quickgelu2(typename Pk<T>::T2 x) {
   typename P::T2 s = __hfma2(th, P::splat(0.5f), P::splat(0.5f));
   return __hmul2(x, s);
 }
+// h * d/dz[z sigmoid(1.702 z)] on two packed values, in the dtype's arithmetic like the reference's autograd of the
+// dtype-typed QuickGELU: s = sigmoid(1.702 z) = 0.5 tanh(0.851 z) + 0.5 ; g = s (1 + 1.702 z (1 - s))
+template <typename T>
+__device__ __forceinline__ typename Pk<T>::T2 quickgelu_grad_mul2(typename Pk<T>::T2 h, typename Pk<T>::T2 z) {
+  using P = Pk<T>;
+  const typename P::T2 th = P::tanh2(__hmul2(z, P::splat(0.851f)));
+  const typename P::T2 sg = __hfma2(th, P::splat(0.5f), P::splat(0.5f));
+  const typename P::T2 u = __hmul2(z, P::splat(1.702f));
+  const typename P::T2 w = __hfma2(__hneg2(u), sg, u);  // u (1 - s)
+  const typename P::T2 g = __hfma2(sg, w, sg);           // s (1 + w)
+  return __hmul2(h, g);
+}
 
 // ---- epilogue of one 128 x BN accumulator tile (shared by the single-CTA and the CTA-pair kernel) ------
 // The tile leaves in SLABS of 64 columns through a double-buffered 16 KB staging area, so that shared
@@ -164,6 +176,7 @@ struct Epi {
   int sk_count = 0;
   size_t sk_stride = 0;  // floats between the slots of consecutive contributors
   long long t_acc = 0;   // clock when the accumulator became available (trace only)
+  int dbg_nostore = 0;   // tuning experiment (RPO_GEMM_DEBUG=0x400): skip the copy-out's global stores
 
   __device__ __forceinline__ void prefetch(int sc, int r0, uint4 (&pre)[PASSES]) {
     if (!src_row) return;
@@ -269,17 +282,13 @@ struct Epi {
         T2 *pv = reinterpret_cast<T2 *>(&v), *pp = reinterpret_cast<T2 *>(&pre[i]);
         if (aux_pre) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const T *hv = reinterpret_cast<const T *>(&pv[e]), *av = reinterpret_cast<const T *>(&pp[e]);
-            pv[e] = Pk<T>::from_floats(tof<T>(hv[0]) * quickgelu_grad(tof<T>(av[0])),
-                                       tof<T>(hv[1]) * quickgelu_grad(tof<T>(av[1])));
-          }
+          for (int e = 0; e < 4; ++e) pv[e] = quickgelu_grad_mul2<T>(pv[e], pp[e]);
         }
         if (res) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) pv[e] = __hadd2(pv[e], pp[e]);
         }
-        *reinterpret_cast<uint4 *>(p) = v;
+        if (!dbg_nostore) *reinterpret_cast<uint4 *>(p) = v;
       }
       p += pass_stride;
     }
@@ -820,6 +829,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
         if (lane == 0) mbar_arrive_cluster(lead_empty);
         continue;
       }
+      epi.dbg_nostore = dbg & 0x400;
       epi.sk_partial = n_contrib ? sk_slots + ((size_t)(cluster_id + sch.lanes) * 2 + rank) * (BM * 256) : nullptr;
       epi.sk_count = n_contrib;
       epi.sk_stride = (size_t)sch.lanes * (2 * BM * 256);
