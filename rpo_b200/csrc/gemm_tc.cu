@@ -948,7 +948,8 @@ struct CfgSK {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int PART_BYTES = BM * BN * 4;  // f32 partial tile, reuses the operand ring
+  static constexpr int PART_PITCH = BN + 4;             // floats per partial row (+4: conflict-free 16-byte row stores)
+  static constexpr int PART_BYTES = BM * PART_PITCH * 4;  // f32 partial tile, reuses the operand ring
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES > PART_BYTES ? STAGES * STAGE_BYTES : PART_BYTES;
   static constexpr int SMEM_BYTES = RING_BYTES + 256 + 1024;
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
@@ -1038,7 +1039,7 @@ __global__ void __cluster_dims__(SPLIT, 1, 1) __launch_bounds__(64 + GROUP_THREA
       umma_commit(acc_full);
     }
   } else {
-    // ---- drain: f32 accumulator -> this CTA's partial tile, [column group of 4][row] float4 ----
+    // ---- drain: f32 accumulator -> this CTA's partial tile, row-major f32 with a padded pitch ----
     const int q = warp & 3, half_id = (warp - 2) >> 2;
     pdl_wait();
     mbar_wait(acc_full, 0);  // every MMA has completed: the operand ring is dead and becomes the partial tile
@@ -1050,8 +1051,8 @@ __global__ void __cluster_dims__(SPLIT, 1, 1) __launch_bounds__(64 + GROUP_THREA
         uint32_t acc[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t a = smem_base + (uint32_t)(((c0 / 4 + j) * BM + q * 32 + lane) * 16);
+        for (int j = 0; j < 4; ++j) {  // row-major: the reducing CTA reads whole 256-byte rows
+          const uint32_t a = smem_base + (uint32_t)(((q * 32 + lane) * C_::PART_PITCH + c0 + 4 * j) * 4);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(acc[4 * j]), "r"(acc[4 * j + 1]),
                        "r"(acc[4 * j + 2]), "r"(acc[4 * j + 3])
                        : "memory");
@@ -1073,7 +1074,7 @@ __global__ void __cluster_dims__(SPLIT, 1, 1) __launch_bounds__(64 + GROUP_THREA
       const long long m = (long long)m0 + row;
       if (m >= M) continue;
       float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-      const uint32_t local = smem_base + (uint32_t)((cg * BM + row) * 16);
+      const uint32_t local = smem_base + (uint32_t)((row * C_::PART_PITCH + cg * 4) * 4);
 #pragma unroll
       for (int r2 = 0; r2 < SPLIT; ++r2) {
         const int kq0 = (int)((long long)num_kb * r2 / SPLIT), kq1 = (int)((long long)num_kb * (r2 + 1) / SPLIT);
