@@ -77,6 +77,17 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const T *__restri
   int nv = D / VEC;
   float vals[MAXV * VEC];
   load_row<T, MAXV>(x + row * D, nv, lane, vals);
+  // the affine parameters do not depend on the statistics: fetch them now, so that their latency overlaps the two
+  // warp reductions instead of following them (the kernel is one wave of one row per warp: a pure latency chain)
+  float wv[MAXV * VEC], bv[MAXV * VEC];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int vi = lane + 32 * i;
+    if (vi < nv) {
+      load_f32<VEC>(w + vi * VEC, *reinterpret_cast<float(*)[VEC]>(&wv[i * VEC]));
+      load_f32<VEC>(b + vi * VEC, *reinterpret_cast<float(*)[VEC]>(&bv[i * VEC]));
+    }
+  }
   float mean, rstd;
   row_stats<T, MAXV>(vals, nv, lane, D, mean, rstd);
 #pragma unroll
@@ -84,11 +95,9 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const T *__restri
     int vi = lane + 32 * i;
     if (vi < nv) {
       Vec16<T> o;
-      float wv[VEC], bv[VEC];
-      load_f32<VEC>(w + vi * VEC, wv);
-      load_f32<VEC>(b + vi * VEC, bv);
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) o.v[e] = fromf<T>((vals[i * VEC + e] - mean) * rstd * wv[e] + bv[e]);
+      for (int e = 0; e < VEC; ++e)
+        o.v[e] = fromf<T>((vals[i * VEC + e] - mean) * rstd * wv[i * VEC + e] + bv[i * VEC + e]);
       st16(y + row * D + (size_t)vi * VEC, o);
     }
   }
@@ -110,9 +119,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const T *__restri
   float xv[MAXV * VEC], gv[MAXV * VEC];
   load_row<T, MAXV>(x + row * D, nv, lane, xv);
   load_row<T, MAXV>(dy + row * D, nv, lane, gv);
-  float mean, rstd;
-  row_stats<T, MAXV>(xv, nv, lane, D, mean, rstd);
-  float sg = 0.f, sgx = 0.f;
+  // g = dy * w does not depend on the statistics: form it while the row loads / reductions are in flight
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     int vi = lane + 32 * i;
@@ -120,8 +127,19 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const T *__restri
       float wv[VEC];
       load_f32<VEC>(w + vi * VEC, wv);
 #pragma unroll
+      for (int e = 0; e < VEC; ++e) gv[i * VEC + e] *= wv[e];
+    }
+  }
+  float mean, rstd;
+  row_stats<T, MAXV>(xv, nv, lane, D, mean, rstd);
+  float sg = 0.f, sgx = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int vi = lane + 32 * i;
+    if (vi < nv) {
+#pragma unroll
       for (int e = 0; e < VEC; ++e) {
-        float g = gv[i * VEC + e] * wv[e];
+        float g = gv[i * VEC + e];
         float xh = (xv[i * VEC + e] - mean) * rstd;
         gv[i * VEC + e] = g;
         xv[i * VEC + e] = xh;
