@@ -185,6 +185,13 @@ struct Epilogue {
   // concurrently on different streams must not share it (and only ONE stream may use stream-K at all --
   // the finishing CTAs of a tile spin on flags set by CTAs that must become resident).
   void *sk_ws;
+  // Row split of the output (tcgen05 kernels only): rows >= split_row go to c2[(m - split_row) * ldc2 + n] for
+  // columns n < ncols2 and are dropped for the other columns.  The vision tower's QKV projection uses it to run
+  // over context AND prompt rows in one launch: context rows -> [Mc, 3D] q|k|v, prompt rows -> their q only
+  // (prompts are never keys or values).  Not combinable with residual / gelu' rows / aux_out.  c2 == null: off.
+  T *c2;
+  long long ldc2, split_row;
+  int ncols2;
 
   // v: f32 accumulator for element (m, n); returns the value to store (already rounded through T
   // at the points where the reference materialises a dtype tensor).

@@ -167,12 +167,26 @@ static int tower_forward(RpoHandle *hd, Tower &tw, bool do_ctx, bool do_prompt, 
     // x = x + attn(ln_1(x))                                             clip/model.py:189
     RPO_TRY(layernorm_fwd<T>(x_in + r0 * D, bw.ln1_w, bw.ln1_b, h + r0 * D, rows, D, st));
     Epilogue<T> ep = frozen_ep<T>(tw.sk_ws);
-    if (do_ctx) {
+    // One launch for the in-projection of context AND prompt rows when both are live and the tcgen05 path takes the
+    // shape: the epilogue sends the prompt rows' q third to `qp` and drops their k|v (prompts are never keys or
+    // values) -- 8% more MMA work on this GEMM, one ~6 us kernel and one dependency bubble less per block.
+    static const bool no_fused_q = [] { const char *e = getenv("RPO_NO_FUSED_Q"); return e && e[0] == '1'; }();
+    const bool fused_q = !no_fused_q && do_ctx && do_prompt && sizeof(T) == 2 && backend != RPO_GEMM_SIMT && Mc > 0 && Mp > 0 &&
+                         gemm_tcgen05_supported(Num<T>::dtype, D, D, 3 * D, Mc + Mp, 3 * D, D, h, bw.in_w, qkv);
+    if (fused_q) {
+      ep.bias = (const T *)bw.in_b;
+      ep.c2 = qp;
+      ep.ldc2 = D;
+      ep.split_row = Mc;
+      ep.ncols2 = D;
+      RPO_TRY(gemm_dispatch<T>(backend, h, D, (const T *)bw.in_w, D, qkv, 3 * D, Mc + Mp, 3 * D, D, ep, st));
+    }
+    if (do_ctx && !fused_q) {
       ep = frozen_ep<T>(tw.sk_ws);
       ep.bias = (const T *)bw.in_b;
       RPO_TRY(gemm_dispatch<T>(backend, h, D, (const T *)bw.in_w, D, qkv, 3 * D, Mc, 3 * D, D, ep, st));
     }
-    if (do_prompt) {
+    if (do_prompt && !fused_q) {
       // prompts are queries only: project with the q third of in_proj (rows 0..D-1)
       ep = frozen_ep<T>(tw.sk_ws);
       ep.bias = (const T *)bw.in_b;

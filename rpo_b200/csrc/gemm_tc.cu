@@ -177,6 +177,8 @@ struct Epi {
   size_t sk_stride = 0;  // floats between the slots of consecutive contributors
   long long t_acc = 0;   // clock when the accumulator became available (trace only)
   int dbg_nostore = 0;   // tuning experiment (RPO_GEMM_DEBUG=0x400): skip the copy-out's global stores
+  long long tile_m0 = 0;  // first row / column of the current tile (row-split outputs)
+  int tile_n0 = 0;
 
   __device__ __forceinline__ void prefetch(int sc, int r0, uint4 (&pre)[PASSES]) {
     if (!src_row) return;
@@ -288,7 +290,16 @@ struct Epi {
 #pragma unroll
           for (int e = 0; e < 4; ++e) pv[e] = __hadd2(pv[e], pp[e]);
         }
-        if (!dbg_nostore) *reinterpret_cast<uint4 *>(p) = v;
+        if (ep.c2) {  // row split (see Epilogue::c2); uniform branch
+          const long long mm = tile_m0 + r;
+          const int n = tile_n0 + sc + c * 8;
+          if (mm < ep.split_row)
+            *reinterpret_cast<uint4 *>(p) = v;
+          else if (n < ep.ncols2)
+            *reinterpret_cast<uint4 *>(ep.c2 + (mm - ep.split_row) * ep.ldc2 + n) = v;
+        } else if (!dbg_nostore) {
+          *reinterpret_cast<uint4 *>(p) = v;
+        }
       }
       p += pass_stride;
     }
@@ -306,6 +317,8 @@ struct Epi {
     const int etid = etid_all % GROUP_THREADS;
     const int r0 = etid / CH, c = etid % CH;
     rows_valid = (int)(M - m0 < BM ? M - m0 : BM);
+    tile_m0 = m0;
+    tile_n0 = n0;
     aux_r0 = BM;
     if (ep.aux_out) aux_r0 = ep.aux_row0 > m0 ? (ep.aux_row0 - m0 < BM ? (int)(ep.aux_row0 - m0) : BM) : 0;
     pass_stride = (long long)ROWS_PER_PASS * ldc;
@@ -1195,6 +1208,10 @@ int gemm_tcgen05(const T *A, long long lda, const T *B, long long ldb, T *C, lon
     if (ep.residual) RPO_REQUIRE(((uintptr_t)ep.residual & 15) == 0, "residual must be 16-byte aligned");
     if (ep.gelu_grad_aux) RPO_REQUIRE(((uintptr_t)ep.gelu_grad_aux & 15) == 0, "aux must be 16-byte aligned");
     if (ep.aux_out) RPO_REQUIRE(((uintptr_t)ep.aux_out & 15) == 0, "aux_out must be 16-byte aligned");
+    if (ep.c2)
+      RPO_REQUIRE(!ep.residual && !ep.gelu_grad_aux && !ep.aux_out && ((uintptr_t)ep.c2 & 15) == 0 && ep.ldc2 % 8 == 0 &&
+                      ep.ncols2 % 8 == 0,
+                  "row-split output: plain epilogue, 16-byte aligned");
     const int cfg = tc::pick_config(M, N, Kd);
     switch (cfg) {
       case tc::CFG_P256: return tc::launch_pair<T, 256>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);
