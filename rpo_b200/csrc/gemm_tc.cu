@@ -48,12 +48,124 @@ __device__ __forceinline__ void named_bar_sync(int id) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NTHREADS) : "memory");
 }
 
+// =================================================================================================
+// Tile schedule of the persistent kernels.
+//   static : CTA (or CTA pair) c of a grid of NC takes tiles c, c + NC, ...  Fine while the kernel owns the GPU.
+//   dynamic: the grid has ONE CTA (pair) PER TILE and a running CTA takes over launches that have not started yet
+//            through cluster launch control (clusterlaunchcontrol.try_cancel): the hardware hands it the block index
+//            of a cancelled launch, i.e. its tile.  The step runs the text tower on a second stream; its kernels
+//            hold SMs for 5-15 us at a time, and a statically scheduled GEMM whose CTAs start late on those SMs
+//            finishes late by the same amount.  With the dynamic schedule late starters simply take fewer tiles,
+//            and SMs that free up mid-kernel still pick up pending launches.  Which CTA computes a tile does not
+//            change the tile's arithmetic, so results stay bit-identical.
+// Protocol (ring of CLC_SLOTS 16-byte responses): the SCHEDULER -- the TMA producer thread of the (leader) CTA --
+// requests the tile after the one it is about to load, so the round trip hides behind a whole tile of loads; the
+// response is written (multicast for a pair) into every CTA's ring slot and completes full[slot] there.  Every other
+// role (MMA thread, epilogue warps, the pair's second producer) waits on its CTA's full[slot], decodes the response
+// and releases the slot on the scheduler's empty[slot].  A failed request ends every role's loop; no request is
+// issued after a failure (undefined by the PTX ISA).
+// =================================================================================================
+static constexpr int CLC_SLOTS = 4;
+static constexpr int CLC_BYTES = CLC_SLOTS * 16 + 2 * CLC_SLOTS * 8;
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank);
+struct TileFeed {
+  enum { SCHEDULER = 0, THREAD = 1, WARP = 2 };
+  int dyn, tile, stride, limit, pair, role;
+  bool started;
+  uint32_t base, rel, nr, nf;
+  __device__ __forceinline__ uint32_t resp(uint32_t s) const { return base + 16u * s; }
+  __device__ __forceinline__ uint32_t full(uint32_t s) const { return base + 16u * CLC_SLOTS + 8u * s; }
+  __device__ __forceinline__ uint32_t empty(uint32_t s) const { return base + 24u * CLC_SLOTS + 8u * s; }
+  // `first` = this CTA's (pair's) first tile; static mode continues with first + step, ... < count
+  __device__ __forceinline__ void init(int dynamic, int first, int step, int count, uint32_t clc_base, int is_pair,
+                                       int who) {
+    dyn = dynamic; tile = first; stride = step; limit = count; pair = is_pair; role = who;
+    started = false;
+    base = clc_base;
+    nr = nf = 0;
+    rel = empty(0);
+    if (is_pair) rel = mapa_shared(rel, 0);
+  }
+  // one thread, once: consumers per slot = MMA thread + epilogue warps (+ second producer + its epilogue warps)
+  __device__ __forceinline__ static void init_barriers(uint32_t clc_base, int consumers) {
+    for (int s = 0; s < CLC_SLOTS; ++s) {
+      mbar_init(clc_base + 16u * CLC_SLOTS + 8u * s, 1);
+      mbar_init(clc_base + 24u * CLC_SLOTS + 8u * s, consumers);
+    }
+  }
+  // scheduler only: ask for the tile after the current one
+  __device__ __forceinline__ void request() {
+    if (!dyn) return;
+    const uint32_t s = nf % CLC_SLOTS, ph = (nf / CLC_SLOTS) & 1;
+    mbar_wait(empty(s), ph ^ 1);
+    mbar_arrive_expect_tx(full(s), 16);
+    if (pair) {
+      asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(
+                       mapa_shared(full(s), 1)),
+                   "r"(16u)
+                   : "memory");
+      asm volatile(
+          "clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 "
+          "[%0], [%1];" ::"r"(resp(s)),
+          "r"(full(s))
+          : "memory");
+    } else {
+      asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];" ::"r"(
+                       resp(s)),
+                   "r"(full(s))
+                   : "memory");
+    }
+    ++nf;
+  }
+  __device__ __forceinline__ bool next(int &out) {
+    if (!dyn) {
+      if (started) tile += stride;
+      started = true;
+      out = tile;
+      return tile < limit;
+    }
+    if (!started) {  // the launch's own tile (grid == tile count)
+      started = true;
+      out = tile;
+      return true;
+    }
+    const uint32_t s = nr % CLC_SLOTS, ph = (nr / CLC_SLOTS) & 1;
+    mbar_wait(full(s), ph);
+    uint32_t ok, x;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b128 r;\n\t"
+        "ld.shared.b128 r, [%2];\n\t"
+        "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p, r;\n\t"
+        "selp.u32 %1, 1, 0, p;\n\t"
+        "mov.u32 %0, 0;\n\t"
+        "@p clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, _, _, _}, r;\n\t}"
+        : "=r"(x), "=r"(ok)
+        : "r"(resp(s))
+        : "memory");
+    // The slot is rewritten through the async proxy only after every consumer released it.  The response has been
+    // consumed (ok / x are register values) when the arrive below issues, so a RELAXED arrive is enough; a
+    // cluster-scope release would also wait for the acknowledgement of every global store this thread still has in
+    // flight (the previous tile's copy-out: measured +9 % on c_fc).
+    if (role == WARP) {
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0 && (ok | x) != 0xFFFFFFFFu)
+        asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(rel + 8u * s) : "memory");
+    } else if (role == THREAD) {
+      if ((ok | x) != 0xFFFFFFFFu)
+        asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(rel + 8u * s) : "memory");
+    }
+    ++nr;
+    out = (int)(pair ? x >> 1 : x);
+    return ok != 0;
+  }
+};
+
 // output staging geometry of the epilogue (see Epi below)
 template <int BN>
 struct EpiGeo {
   static constexpr int SLAB = BN >= 64 ? 64 : 32;
   static constexpr int NSLAB = BN / SLAB;
-  static constexpr int NBUF = NSLAB > 1 ? 2 : 1;  // one staging slab per epilogue warp group
+  static constexpr int NBUF = BN >= 64 ? 2 : 1;   // staging slabs: consecutive slabs alternate between two buffers
   static constexpr int SLAB_BYTES = BM * SLAB * 2;
   static constexpr int CSTAGE_BYTES = NBUF * SLAB_BYTES;
 };
@@ -70,7 +182,7 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int CSTAGE_BYTES = EpiGeo<BN>::CSTAGE_BYTES;  // output slab staging (16-bit)
   static constexpr int BIAS_BYTES = BN * 4;
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int BAR_BYTES = 256 + CLC_BYTES;  // pipeline barriers + TMEM slot, then the CLC ring
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + CSTAGE_BYTES + BIAS_BYTES + BAR_BYTES + 1024;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulators
   static_assert(STAGE_BYTES % 1024 == 0, "stages must stay 1024-byte aligned");
@@ -135,8 +247,10 @@ __device__ __forceinline__ typename Pk<T>::T2 quickgelu_grad_mul2(typename Pk<T>
 //              packed 16-bit math, 16-byte stores into the XOR-swizzled staging slab
 //   copy-out : 16-byte coalesced global stores (full 128-byte row segments), applying gelu'(aux) in f32 /
 //              adding the residual from the prefetched registers.
-// One named barrier per slab: slab s+2 reuses the buffer of slab s, and every thread has left copy-out(s)
-// before it arrives at the barrier after drain(s+1).
+// One named barrier per slab (between drain and copy-out): slab s+2 reuses the buffer of slab s, and every thread
+// has left copy-out(s) before it arrives at the barrier after drain(s+1) -- so a warp may already drain slab s+1
+// while others still copy slab s out.  The slab counter runs across tiles.  (128 x 32 tiles keep one buffer and a
+// second barrier: their light configuration has no shared memory to spare.)
 
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4 &v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -179,6 +293,7 @@ struct Epi {
   int dbg_nostore = 0;   // tuning experiment (RPO_GEMM_DEBUG=0x400): skip the copy-out's global stores
   long long tile_m0 = 0;  // first row / column of the current tile (row-split outputs)
   int tile_n0 = 0;
+  uint32_t slab_seq = 0;  // slabs this thread has processed (selects the staging buffer)
 
   __device__ __forceinline__ void prefetch(int sc, int r0, uint4 (&pre)[PASSES]) {
     if (!src_row) return;
@@ -194,7 +309,7 @@ struct Epi {
   // 32 accumulator columns of this warp's 32 rows -> staging slab.  sc0: first column of the slab inside the tile
   // stream-K finisher with ONE contributor (the common case): this thread's share of the partial tile for the slab
   // starting at tile column sc0, fetched ahead of use (8 x 16 bytes: two 16-column halves x four column groups)
-  __device__ __forceinline__ void load_partial(int sc0, int warp, int lane, float4 (&pp)[8]) {
+  __device__ __forceinline__ void load_partial(int sc0, int warp, int lane, float4 (&pp)[8]) {  // SK only
     const int q = warp & 3, half_id = ((warp - 2) % GROUP_WARPS) >> 2;
     if (half_id >= DRAIN_HALVES) return;
     const float4 *slot = reinterpret_cast<const float4 *>(sk_partial);
@@ -203,38 +318,43 @@ struct Epi {
     for (int j = 0; j < 8; ++j) pp[j] = __ldcg(slot + (size_t)(c0 / 4 + j) * BM + q * 32 + lane);
   }
 
+  template <bool SK>  // SK: stream-K finisher (adds the partial tiles of the contributing clusters)
   __device__ __forceinline__ void drain(const Epilogue<T> &ep, uint32_t tmem_acc, uint32_t slab, uint32_t bias_s,
                                         long long m0, int n0, int sc0, long long ldc, int warp, int lane,
-                                        const float4 (&pp)[8]) {
+                                        const float4 (&pp)[SK ? 8 : 1]) {
     const int q = warp & 3;
     const int half_id = ((warp - 2) % GROUP_WARPS) >> 2;
     if (half_id >= DRAIN_HALVES) return;
     const int r_loc = q * 32 + lane;
     const int c0 = sc0 + half_id * 32;  // tile-local first column of this warp's 32
+    // Two 16-column halves.  (One 32-column load with all 16 packed chains in flight was measured SLOWER: c_fc 39.5 ->
+    // 41.2 us -- the epilogue warps are bound by the register file they share with the 168-register cap, not by ILP.)
 #pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {  // two 16-column halves: half the live registers (16 warps share the file)
+    for (int hh = 0; hh < 2; ++hh) {
       const int ch = c0 + hh * 16;
       uint32_t acc[16];
       tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)ch, acc);
-      if (sk_count == 1) {  // prefetched by load_partial
+      if constexpr (SK) {
+        if (sk_count == 1) {  // prefetched by load_partial
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 v = pp[hh * 4 + j];
-          acc[4 * j] = __float_as_uint(__uint_as_float(acc[4 * j]) + v.x);
-          acc[4 * j + 1] = __float_as_uint(__uint_as_float(acc[4 * j + 1]) + v.y);
-          acc[4 * j + 2] = __float_as_uint(__uint_as_float(acc[4 * j + 2]) + v.z);
-          acc[4 * j + 3] = __float_as_uint(__uint_as_float(acc[4 * j + 3]) + v.w);
+          for (int j = 0; j < 4; ++j) {
+            const float4 v = pp[hh * 4 + j];
+            acc[4 * j] = __float_as_uint(__uint_as_float(acc[4 * j]) + v.x);
+            acc[4 * j + 1] = __float_as_uint(__uint_as_float(acc[4 * j + 1]) + v.y);
+            acc[4 * j + 2] = __float_as_uint(__uint_as_float(acc[4 * j + 2]) + v.z);
+            acc[4 * j + 3] = __float_as_uint(__uint_as_float(acc[4 * j + 3]) + v.w);
+          }
         }
-      }
-      for (int p = 0; p < (sk_count > 1 ? sk_count : 0); ++p) {  // general case: add the partial sums, in cluster order
-        const float4 *slot = reinterpret_cast<const float4 *>(sk_partial + (size_t)p * sk_stride);
+        for (int p = 0; p < (sk_count > 1 ? sk_count : 0); ++p) {  // general case: add the partial sums, in cluster order
+          const float4 *slot = reinterpret_cast<const float4 *>(sk_partial + (size_t)p * sk_stride);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 v = __ldcg(slot + (size_t)(ch / 4 + j) * BM + r_loc);
-          acc[4 * j] = __float_as_uint(__uint_as_float(acc[4 * j]) + v.x);
-          acc[4 * j + 1] = __float_as_uint(__uint_as_float(acc[4 * j + 1]) + v.y);
-          acc[4 * j + 2] = __float_as_uint(__uint_as_float(acc[4 * j + 2]) + v.z);
-          acc[4 * j + 3] = __float_as_uint(__uint_as_float(acc[4 * j + 3]) + v.w);
+          for (int j = 0; j < 4; ++j) {
+            const float4 v = __ldcg(slot + (size_t)(ch / 4 + j) * BM + r_loc);
+            acc[4 * j] = __float_as_uint(__uint_as_float(acc[4 * j]) + v.x);
+            acc[4 * j + 1] = __float_as_uint(__uint_as_float(acc[4 * j + 1]) + v.y);
+            acc[4 * j + 2] = __float_as_uint(__uint_as_float(acc[4 * j + 2]) + v.z);
+            acc[4 * j + 3] = __float_as_uint(__uint_as_float(acc[4 * j + 3]) + v.w);
+          }
         }
       }
       __align__(16) T2 h[8];
@@ -272,6 +392,7 @@ struct Epi {
     }
   }
 
+  template <bool FULL>  // FULL: all 128 rows of the tile are inside M (no per-pass row test)
   __device__ __forceinline__ void copy_out(const Epilogue<T> &ep, uint32_t slab, int sc, int r0, int c, uint4 (&pre)[PASSES]) {
     const bool aux_pre = ep.gelu_grad_aux && !ep.residual;
     const bool res = ep.residual != nullptr;
@@ -279,7 +400,7 @@ struct Epi {
 #pragma unroll
     for (int i = 0; i < PASSES; ++i) {
       const int r = r0 + i * ROWS_PER_PASS;
-      if (r < rows_valid) {
+      if (FULL || r < rows_valid) {
         uint4 v = lds128(slab + st_off(r, c));
         T2 *pv = reinterpret_cast<T2 *>(&v), *pp = reinterpret_cast<T2 *>(&pre[i]);
         if (aux_pre) {
@@ -306,7 +427,7 @@ struct Epi {
   }
 
   // Whole tile.  `arrive_acc_empty` hands the accumulator back to the MMA warp (called by one lane per warp).
-  template <typename Arrive>
+  template <bool SK, typename Arrive>
   __device__ __forceinline__ void run_tile(const Epilogue<T> &ep, uint32_t tmem_acc, uint32_t cstage, uint32_t bias_s,
                                            T *__restrict__ C, long long m0, int n0, long long M, long long ldc,
                                            uint32_t acc_full_bar, uint32_t acc_full_parity, Arrive arrive_acc_empty) {
@@ -327,9 +448,11 @@ struct Epi {
     src_row = src ? src + pos : nullptr;
     dst_row = C + pos;
     uint4 pre[PASSES];
-    float4 pp[8];
+    float4 pp[SK ? 8 : 1];
     prefetch(grp * SLAB, r0, pre);
-    if (sk_count == 1) load_partial(grp * SLAB, warp, lane, pp);
+    if constexpr (SK) {
+      if (sk_count == 1) load_partial(grp * SLAB, warp, lane, pp);
+    }
     if (GROUPS > 1) named_bar_sync<Thr<BN>::EPI_WARPS * 32>(1);  // the other group has left the previous tile's drains
     for (int i = etid_all; i < BN; i += Thr<BN>::EPI_WARPS * 32) {
       const float bv = ep.bias ? tof<T>(ep.bias[n0 + i]) : 0.f;
@@ -339,22 +462,28 @@ struct Epi {
     t_acc = clock64();
     tc_fence_after();
     named_bar_sync<Thr<BN>::EPI_WARPS * 32>(1);  // bias visible to every epilogue warp
-    const uint32_t slab = cstage + (uint32_t)(grp * G::SLAB_BYTES);
+    static_assert(GROUPS == 1, "the alternating staging buffers assume one epilogue warp group");
     constexpr int MY_SLABS = G::NSLAB / GROUPS;
 #pragma unroll 1
-    for (int i = 0; i < MY_SLABS; ++i) {
+    for (int i = 0; i < MY_SLABS; ++i, ++slab_seq) {
+      const uint32_t slab = cstage + (G::NBUF == 2 ? (slab_seq & 1u) * (uint32_t)G::SLAB_BYTES : 0u);
       const int sl = grp + i * GROUPS;
-      drain(ep, tmem_acc, slab, bias_s, m0, n0, sl * SLAB, ldc, warp, lane, pp);
-      if (sk_count == 1 && i + 1 < MY_SLABS) load_partial((sl + GROUPS) * SLAB, warp, lane, pp);
+      drain<SK>(ep, tmem_acc, slab, bias_s, m0, n0, sl * SLAB, ldc, warp, lane, pp);
+      if constexpr (SK) {
+        if (sk_count == 1 && i + 1 < MY_SLABS) load_partial((sl + GROUPS) * SLAB, warp, lane, pp);
+      }
       if (i == MY_SLABS - 1) {  // this warp has read its last accumulator columns
         tc_fence_before();
         __syncwarp();
         if (lane == 0) arrive_acc_empty();
       }
       named_bar_sync<GROUP_THREADS>(2 + grp);  // slab staged
-      copy_out(ep, slab, sl * SLAB, r0, c, pre);
+      if (rows_valid == BM)
+        copy_out<true>(ep, slab, sl * SLAB, r0, c, pre);
+      else
+        copy_out<false>(ep, slab, sl * SLAB, r0, c, pre);
       if (i + 1 < MY_SLABS) prefetch((sl + GROUPS) * SLAB, r0, pre);
-      named_bar_sync<GROUP_THREADS>(2 + grp);  // staging slab free again (also closes the tile for this group)
+      if (G::NBUF == 1) named_bar_sync<GROUP_THREADS>(2 + grp);  // single buffer: staging slab free again
     }
   }
 };
@@ -363,7 +492,7 @@ template <typename T, int BN, bool LIGHT>
 __global__ void __launch_bounds__(Thr<BN>::THREADS, (Cfg<BN, LIGHT>::MIN_CTAS))
     gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    T *__restrict__ C, long long ldc, long long M, int N, int Kd, Epilogue<T> ep, int num_n_tiles,
-                   int num_tiles, long long *trace) {
+                   int num_tiles, long long *trace, int dyn) {
   using C_ = Cfg<BN, LIGHT>;
   // RPO_GEMM_TRACE (tuning aid): per CTA [globaltimer at entry, clock at entry, after setup, dependency wait passed,
   // first operands landed, accumulator of the first tile complete, first tile written, exit clock, globaltimer at exit]
@@ -393,6 +522,7 @@ __global__ void __launch_bounds__(Thr<BN>::THREADS, (Cfg<BN, LIGHT>::MIN_CTAS))
   auto empty_bar = [&](int s) { return bar_base + 8u * (C_::STAGES + s); };
   auto acc_full = [&](int a) { return bar_base + 8u * (2 * C_::STAGES + a); };
   auto acc_empty = [&](int a) { return bar_base + 8u * (2 * C_::STAGES + 2 + a); };
+  const uint32_t clc_base = bar_base + 256;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
@@ -405,6 +535,7 @@ __global__ void __launch_bounds__(Thr<BN>::THREADS, (Cfg<BN, LIGHT>::MIN_CTAS))
       mbar_init(acc_full(a), 1);
       mbar_init(acc_empty(a), Thr<BN>::EPI_WARPS);
     }
+    TileFeed::init_barriers(clc_base, 1 + Thr<BN>::EPI_WARPS);  // slot releases: MMA thread + epilogue warps
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -438,7 +569,11 @@ __global__ void __launch_bounds__(Thr<BN>::THREADS, (Cfg<BN, LIGHT>::MIN_CTAS))
       pdl_wait();
       if (tr) tr[3] = clock64();
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      TileFeed feed;
+      feed.init(dyn, blockIdx.x, gridDim.x, num_tiles, clc_base, 0, TileFeed::SCHEDULER);
+      int tile;
+      for (bool have = feed.next(tile); have; have = feed.next(tile)) {
+        feed.request();
         const int m0 = (tile / num_n_tiles) * BM, n0 = (tile % num_n_tiles) * BN;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % C_::STAGES;
@@ -458,7 +593,10 @@ __global__ void __launch_bounds__(Thr<BN>::THREADS, (Cfg<BN, LIGHT>::MIN_CTAS))
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(Num<T>::dtype == RPO_BF16 ? 1 : 0, BM, BN);
       uint32_t it = 0, t = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      TileFeed feed;
+      feed.init(dyn, blockIdx.x, gridDim.x, num_tiles, clc_base, 0, TileFeed::THREAD);
+      int tile;
+      for (bool have = feed.next(tile); have; have = feed.next(tile), ++t) {
         const int a = t & 1;
         mbar_wait(acc_empty(a), ((t >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
@@ -487,13 +625,16 @@ __global__ void __launch_bounds__(Thr<BN>::THREADS, (Cfg<BN, LIGHT>::MIN_CTAS))
     Epi<T, BN> epi;
     uint32_t t = 0;
     pdl_wait();  // residual / aux rows come from upstream kernels; C may still be read by them
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+    TileFeed feed;
+    feed.init(dyn, blockIdx.x, gridDim.x, num_tiles, clc_base, 0, TileFeed::WARP);
+    int tile;
+    for (bool have = feed.next(tile); have; have = feed.next(tile), ++t) {
       const int a = t & 1;
       const long long m0 = (long long)(tile / num_n_tiles) * BM;
       const int n0 = (tile % num_n_tiles) * BN;
       const uint32_t empty_a = acc_empty(a);
-      epi.run_tile(ep, tmem_base + (uint32_t)(a * BN), smem_u32(cstage), smem_u32(bias_s), C, m0, n0, M, ldc, acc_full(a), (t >> 1) & 1,
-                   [&]() { mbar_arrive(empty_a); });
+      epi.template run_tile<false>(ep, tmem_base + (uint32_t)(a * BN), smem_u32(cstage), smem_u32(bias_s), C, m0, n0, M, ldc,
+                                   acc_full(a), (t >> 1) & 1, [&]() { mbar_arrive(empty_a); });
       if (tr && t == 0 && threadIdx.x == 64) {
         tr[5] = epi.t_acc;
         tr[6] = clock64();
@@ -586,10 +727,13 @@ struct Sched {
   // (m-tile, k-block) units and cluster j of the group computes n-tile j of every unit.  The n-tiles of an m-tile thus
   // stay in lockstep on neighbouring clusters and share the A tiles through L2 (splitting each tile's K range
   // independently puts them at different K offsets: every cluster then streams its own copy of A from HBM).
-  int sk, num_tiles, num_kb, nc, next_tile, lanes, grp, lane_id, groups;
+  int sk, num_tiles, num_kb, nc, lanes, grp, lane_id, groups;
   long long pos, end, total;
-  __device__ __forceinline__ void init(int stream_k, int tiles, int kb, int c, int n_clusters, int num_n_tiles) {
-    sk = stream_k; num_tiles = tiles; num_kb = kb; nc = n_clusters; next_tile = c;
+  TileFeed feed;  // whole-tile schedules (static round-robin or cluster launch control)
+  __device__ __forceinline__ void init(int stream_k, int tiles, int kb, int c, int n_clusters, int num_n_tiles,
+                                       int dynamic, uint32_t clc_base, int role) {
+    sk = stream_k; num_tiles = tiles; num_kb = kb; nc = n_clusters;
+    feed.init(dynamic, c, n_clusters, tiles, clc_base, 1, role);
     lanes = num_n_tiles;
     groups = n_clusters / lanes;
     grp = c / lanes;
@@ -604,9 +748,8 @@ struct Sched {
   }
   __device__ __forceinline__ bool next(Seg &s) {
     if (!sk) {
-      if (next_tile >= num_tiles) return false;
-      s.tile = next_tile; s.k0 = 0; s.k1 = num_kb;
-      next_tile += nc;
+      if (!feed.next(s.tile)) return false;
+      s.k0 = 0; s.k1 = num_kb;
       return true;
     }
     if (pos >= end) return false;
@@ -649,7 +792,7 @@ struct Cfg2 {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int CSTAGE_BYTES = EpiGeo<BN>::CSTAGE_BYTES;
   static constexpr int BIAS_BYTES = BN * 4;
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int BAR_BYTES = 256 + CLC_BYTES;  // pipeline barriers + TMEM slot, then the CLC ring
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + CSTAGE_BYTES + BIAS_BYTES + BAR_BYTES + 1024;
   static constexpr int TMEM_COLS = 2 * BN <= 256 ? 256 : 512;
   static_assert(STAGE_BYTES % 1024 == 0 && A_BYTES % 1024 == 0, "operand tiles must stay 1024-byte aligned");
@@ -671,6 +814,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * C_::STAGES + 4);
   // tuning experiments (RPO_GEMM_DEBUG): 0x100 = no epilogue work, 0x200 = no MMA issue.  Results are garbage.
   const int dbg = stream_k & 0xF00;
+  const int dyn = (stream_k >> 1) & 1;  // one pair per tile, cluster launch control (see TileFeed)
   stream_k &= 1;
 
   const int warp = threadIdx.x >> 5;
@@ -684,6 +828,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
   auto empty_bar = [&](int s) { return bar_base + 8u * (C_::STAGES + s); };
   auto acc_full = [&](int a) { return bar_base + 8u * (2 * C_::STAGES + a); };
   auto acc_empty = [&](int a) { return bar_base + 8u * (2 * C_::STAGES + 2 + a); };
+  const uint32_t clc_base = bar_base + 256;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
@@ -696,6 +841,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
       mbar_init(acc_full(a), 1);
       mbar_init(acc_empty(a), 2 * Thr<BN>::EPI_WARPS);
     }
+    // slot releases: MMA thread + second producer + the epilogue warps of both CTAs
+    TileFeed::init_barriers(clc_base, 2 + 2 * Thr<BN>::EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -715,7 +862,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
     // ===== TMA producer (both CTAs; transaction bytes of both land on the leader's barrier) =====
     if (lane == 0) {
       Sched sch;
-      sch.init(stream_k, num_tiles, num_kb, cluster_id, num_clusters, num_n_tiles);
+      sch.init(stream_k, num_tiles, num_kb, cluster_id, num_clusters, num_n_tiles, dyn, clc_base,
+               rank == 0 ? TileFeed::SCHEDULER : TileFeed::THREAD);
       Seg sg;
       bool have = sch.next(sg);
       uint32_t pre = 0;
@@ -732,6 +880,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
       pdl_wait();
       uint32_t it = 0;
       for (; have; have = sch.next(sg)) {
+        if (rank == 0) sch.feed.request();
         const int m0 = (sg.tile / num_n_tiles) * (2 * BM) + (int)rank * BM;
         const int n0 = (sg.tile % num_n_tiles) * BN + (int)rank * (BN / 2);
         for (int kb = sg.k0; kb < sg.k1; ++kb, ++it) {
@@ -753,7 +902,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = make_idesc(Num<T>::dtype == RPO_BF16 ? 1 : 0, 2 * BM, BN);
       Sched sch;
-      sch.init(stream_k, num_tiles, num_kb, cluster_id, num_clusters, num_n_tiles);
+      sch.init(stream_k, num_tiles, num_kb, cluster_id, num_clusters, num_n_tiles, dyn, clc_base, TileFeed::THREAD);
       Seg sg;
       uint32_t it = 0, t = 0;
       for (; sch.next(sg); ++t) {
@@ -783,7 +932,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
     // ===== epilogue (both CTAs, 128 rows x BN columns each) =====
     Epi<T, BN> epi;
     Sched sch;
-    sch.init(stream_k, num_tiles, num_kb, cluster_id, num_clusters, num_n_tiles);
+    sch.init(stream_k, num_tiles, num_kb, cluster_id, num_clusters, num_n_tiles, dyn, clc_base, TileFeed::WARP);
     Seg sg;
     uint32_t t = 0;
     int *sk_flags = reinterpret_cast<int *>(ep.sk_ws);
@@ -846,8 +995,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
       epi.sk_partial = n_contrib ? sk_slots + ((size_t)(cluster_id + sch.lanes) * 2 + rank) * (BM * 256) : nullptr;
       epi.sk_count = n_contrib;
       epi.sk_stride = (size_t)sch.lanes * (2 * BM * 256);
-      epi.run_tile(ep, tmem_acc, smem_u32(cstage), smem_u32(bias_s), C, m0, n0, M, ldc, acc_full(a), (t >> 1) & 1,
-                   [&]() { mbar_arrive_cluster(lead_empty); });
+      if (n_contrib)
+        epi.template run_tile<true>(ep, tmem_acc, smem_u32(cstage), smem_u32(bias_s), C, m0, n0, M, ldc, acc_full(a),
+                                    (t >> 1) & 1, [&]() { mbar_arrive_cluster(lead_empty); });
+      else
+        epi.template run_tile<false>(ep, tmem_acc, smem_u32(cstage), smem_u32(bias_s), C, m0, n0, M, ldc, acc_full(a),
+                                     (t >> 1) & 1, [&]() { mbar_arrive_cluster(lead_empty); });
       if (n_contrib) {  // all partial reads are done (they precede the last slab barrier): re-arm the flags
         named_bar_sync<Thr<BN>::EPI_WARPS * 32>(1);
         if (etid < n_contrib) sk_flags[(cluster_id + (1 + etid) * sch.lanes) * 2 + rank] = 0;
@@ -864,6 +1017,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
 }
 
 // ---- host side ---------------------------------------------------------------------------------
+
+// RPO_GEMM_DYNAMIC: bit 0 = CTA-pair kernel, bit 1 = single-CTA kernel (128 x BN tiles, one CTA per SM).
+// Measured on B200 (same box, whole step): static 3.383 ms, pair only 3.397, single only 3.361, both 3.369 -- alone,
+// a dynamically scheduled kernel is ~2 % slower (tools/ab_dynamic.sh), next to the text tower's stream the 128-wide
+// single-CTA GEMMs gain slightly.  Default 2.
+static int dynamic_tiles() {
+  const char *e = getenv("RPO_GEMM_DYNAMIC");  // read per call: the parity tests compare both schedules
+  return e ? (int)strtol(e, nullptr, 0) : 2;
+}
 
 template <typename T, int BN, bool LIGHT>
 static int launch(const T *A, long long lda, const T *B, long long ldb, T *C, long long ldc, long long M, int N,
@@ -883,9 +1045,11 @@ static int launch(const T *A, long long lda, const T *B, long long ldb, T *C, lo
   long long *trace = nullptr;
   if (const char *e = getenv("RPO_GEMM_TRACE")) trace = reinterpret_cast<long long *>(strtoull(e, nullptr, 0));
   const long long slots = (long long)sm_count() * C_::MIN_CTAS;
-  const int grid = (int)(num_tiles < slots ? num_tiles : slots);
+  // more tiles than SMs (one-CTA-per-SM configurations): one CTA per tile, taken over dynamically (see TileFeed)
+  const int dyn = (!LIGHT && num_tiles > slots && (dynamic_tiles() & 2)) ? 1 : 0;
+  const int grid = (int)(num_tiles < slots || dyn ? num_tiles : slots);
   RPO_CHECK_CUDA(launch_pdl(gemm_tc_kernel<T, BN, LIGHT>, dim3(grid), dim3(Thr<BN>::THREADS), C_::SMEM_BYTES, st, map_a, map_b, C, ldc, M, N,
-                            Kd, ep, num_n_tiles, (int)num_tiles, trace));
+                            Kd, ep, num_n_tiles, (int)num_tiles, trace, dyn));
   RPO_LAUNCH_CHECK();
   return RPO_OK;
 }
@@ -928,10 +1092,15 @@ static int launch_pair(const T *A, long long lda, const T *B, long long ldb, T *
       grid = 2 * pairs;
     }
   }
+  // more tiles than SM pairs: one pair per tile, taken over dynamically by the running pairs (see TileFeed)
+  if (!stream_k && num_tiles > pairs && (dynamic_tiles() & 1)) {
+    stream_k = 2;
+    grid = 2 * (int)num_tiles;
+  }
   if (const char *d = getenv("RPO_GEMM_DEBUG")) stream_k |= (int)strtol(d, nullptr, 0) & 0xF00;
   prof_tag("gemm2 M=%lld N=%d K=%d BN=%d%s%s%s%s", M, N, Kd, BN, ep.bias ? " +bias" : "",
            ep.act == RPO_ACT_QUICKGELU ? " +gelu" : (ep.gelu_grad_aux ? " *gelu'" : ""), ep.residual ? " +res" : "",
-           stream_k ? " streamK" : "");
+           stream_k & 1 ? " streamK" : (stream_k & 2 ? " dyn" : ""));
   RPO_CHECK_CUDA(launch_pdl(gemm_tc2_kernel<T, BN>, dim3(grid), dim3(Thr<BN>::THREADS), C_::SMEM_BYTES, st, map_a, map_b, C, ldc, M, N, Kd,
                             ep, num_n_tiles, (int)num_tiles, stream_k));
   RPO_LAUNCH_CHECK();
