@@ -10,3 +10,7 @@ for i in 1 2; do
   timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/${TAG}_bench_${i}.log 2>&1
   grep -o '"ms_per_step": [0-9.]*' gpurun_out/${TAG}_bench_${i}.log | head -1
 done
+if [ -n "$FULL" ]; then
+  timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_full.log 2>&1
+  tail -3 gpurun_out/${TAG}_pytest_full.log
+fi
