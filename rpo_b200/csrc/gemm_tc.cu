@@ -286,6 +286,11 @@ struct Epi {
   static constexpr int PASSES = BM / ROWS_PER_PASS;
   static constexpr int DRAIN_HALVES = SLAB / 32;             // warps with half_id >= this idle in the drain
 
+  // Tile-local output column of TMEM slab sl.  BN = 384 (CTA pairs only) is computed as three N = 128 MMAs, each of
+  // which takes 64 B rows from either CTA of the pair: accumulator columns [128 j, 128 j + 64) are output columns
+  // [64 j, 64 j + 64) and [128 j + 64, 128 j + 128) are [192 + 64 j, ...): a permutation of whole slabs.
+  static __device__ __forceinline__ int gcol(int sl) { return BN == 384 ? 64 * (sl >> 1) + 192 * (sl & 1) : sl * SLAB; }
+
   static __device__ __forceinline__ uint32_t st_off(int r, int c) {
     return (uint32_t)(r * (SLAB * 2) + ((c ^ (r & (CH - 1))) << 4));
   }
@@ -342,8 +347,8 @@ struct Epi {
 
   template <bool SK>  // SK: stream-K finisher (adds the partial tiles of the contributing clusters)
   __device__ __forceinline__ void drain(const Epilogue<T> &ep, uint32_t tmem_acc, uint32_t slab, uint32_t bias_s,
-                                        long long m0, int n0, int sc0, long long ldc, int warp, int lane,
-                                        const float4 (&pp)[SK ? 8 : 1]) {
+                                        long long m0, int n0, int sc0, int gsc0, long long ldc, int warp, int lane,
+                                        const float4 (&pp)[SK ? 8 : 1]) {  // sc0 / gsc0: TMEM / output column of the slab
     const int q = warp & 3;
     const int half_id = ((warp - 2) % GROUP_WARPS) >> 2;
     if (half_id >= DRAIN_HALVES) return;
@@ -353,7 +358,8 @@ struct Epi {
     // 41.2 us -- the epilogue warps are bound by the register file they share with the 168-register cap, not by ILP.)
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
-      const int ch = c0 + hh * 16;
+      const int ch = c0 + hh * 16;                      // accumulator column
+      const int gch = gsc0 + half_id * 32 + hh * 16;    // tile-local output column
       uint32_t acc[16];
       tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)ch, acc);
       if constexpr (SK) {
@@ -382,12 +388,12 @@ struct Epi {
       __align__(16) T2 h[8];
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        const float4 b4 = lds_f32x4(bias_s + (uint32_t)((ch + g * 4) * 4));
+        const float4 b4 = lds_f32x4(bias_s + (uint32_t)((gch + g * 4) * 4));
         h[2 * g] = Pk<T>::from_floats(__uint_as_float(acc[g * 4]) + b4.x, __uint_as_float(acc[g * 4 + 1]) + b4.y);
         h[2 * g + 1] = Pk<T>::from_floats(__uint_as_float(acc[g * 4 + 2]) + b4.z, __uint_as_float(acc[g * 4 + 3]) + b4.w);
       }
       if (r_loc >= aux_r0 && r_loc < rows_valid) {  // pre-activation of the prompt rows (forward c_fc only)
-        T *ao = ep.aux_out + (m0 + r_loc - ep.aux_row0) * ldc + n0 + ch;
+        T *ao = ep.aux_out + (m0 + r_loc - ep.aux_row0) * ldc + n0 + gch;
 #pragma unroll
         for (int g = 0; g < 2; ++g) *reinterpret_cast<uint4 *>(ao + g * 8) = *reinterpret_cast<uint4 *>(&h[4 * g]);
       }
@@ -396,7 +402,7 @@ struct Epi {
         for (int e = 0; e < 8; ++e) h[e] = quickgelu2<T>(h[e]);
       }
       if (ep.gelu_grad_aux && ep.residual && r_loc < rows_valid) {  // both: the prefetch registers hold the residual
-        const T *ax = ep.gelu_grad_aux + (m0 + r_loc) * ldc + n0 + ch;
+        const T *ax = ep.gelu_grad_aux + (m0 + r_loc) * ldc + n0 + gch;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           Vec16<T> aux = ld16(ax + g * 8);
@@ -474,7 +480,7 @@ struct Epi {
     dst_row = C + pos;
     uint4 pre[PASSES];
     float4 pp[SK ? 8 : 1];
-    prefetch(grp * SLAB, r0, pre);
+    prefetch(gcol(grp), r0, pre);
     if constexpr (TMA_OUT) use_tma = !src;  // launch-uniform
     if constexpr (SK) {
       if (sk_count == 1) load_partial(grp * SLAB, warp, lane, pp);
@@ -495,7 +501,7 @@ struct Epi {
     for (int i = 0; i < MY_SLABS; ++i, ++slab_seq) {
       const uint32_t slab = cstage + (G::NBUF == 2 ? (slab_seq & 1u) * (uint32_t)G::SLAB_BYTES : 0u);
       const int sl = grp + i * GROUPS;
-      drain<SK>(ep, tmem_acc, slab, bias_s, m0, n0, sl * SLAB, ldc, warp, lane, pp);
+      drain<SK>(ep, tmem_acc, slab, bias_s, m0, n0, sl * SLAB, gcol(sl), ldc, warp, lane, pp);
       if constexpr (SK) {
         if (sk_count == 1 && i + 1 < MY_SLABS) load_partial((sl + GROUPS) * SLAB, warp, lane, pp);
       }
@@ -512,9 +518,9 @@ struct Epi {
         if (straddle) {
           // the one tile of a row-split output that holds rows of both destinations leaves through plain stores
           // (a TMA store cannot start at a negative row of the second destination)
-          copy_out<false>(ep, slab, sl * SLAB, r0, c, pre);
+          copy_out<false>(ep, slab, gcol(sl), r0, c, pre);
         } else if (etid_all == 0 && !dbg_nostore) {
-          const int col = n0 + sl * SLAB;
+          const int col = n0 + gcol(sl);
           if (!ep.c2 || m0 < ep.split_row)
             tma_store_2d(map_c, slab, col, (int)m0);  // map_c ends at M, or at split_row for a row-split output
           else if (col < ep.ncols2)
@@ -524,10 +530,10 @@ struct Epi {
       } else {
         named_bar_sync<GROUP_THREADS>(2 + grp);  // slab staged
         if (rows_valid == BM)
-          copy_out<true>(ep, slab, sl * SLAB, r0, c, pre);
+          copy_out<true>(ep, slab, gcol(sl), r0, c, pre);
         else
-          copy_out<false>(ep, slab, sl * SLAB, r0, c, pre);
-        if (i + 1 < MY_SLABS) prefetch((sl + GROUPS) * SLAB, r0, pre);
+          copy_out<false>(ep, slab, gcol(sl), r0, c, pre);
+        if (i + 1 < MY_SLABS) prefetch(gcol(sl + GROUPS), r0, pre);
         if (G::NBUF == 1) named_bar_sync<GROUP_THREADS>(2 + grp);  // single buffer: staging slab free again
       }
     }
@@ -843,7 +849,12 @@ __device__ __forceinline__ void st_release_gpu(int *p, int v) {
 
 template <int BN>
 struct Cfg2 {
-  static constexpr int STAGES = BN >= 192 ? 6 : 8;
+  static constexpr int STAGES = BN == 384 ? 4 : (BN >= 192 ? 6 : 8);
+  // BN = 384: ONE accumulator of 384 TMEM columns, three N = 128 MMAs per k-step -- for problems whose 256 x 384
+  // tiles all fit in one round of SM pairs (no next tile to overlap the epilogue with anyway)
+  static constexpr int ACC_BUFS = BN == 384 ? 1 : 2;
+  static constexpr int NMMA = BN == 384 ? 3 : 1;
+  static constexpr int MMA_N = BN / NMMA;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / 2) * BK * 2;  // this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -851,7 +862,8 @@ struct Cfg2 {
   static constexpr int BIAS_BYTES = BN * 4;
   static constexpr int BAR_BYTES = 256 + CLC_BYTES;  // pipeline barriers + TMEM slot, then the CLC ring
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + CSTAGE_BYTES + BIAS_BYTES + BAR_BYTES + 1024;
-  static constexpr int TMEM_COLS = 2 * BN <= 256 ? 256 : 512;
+  static constexpr int TMEM_COLS = ACC_BUFS * BN <= 256 ? 256 : 512;
+  static_assert(ACC_BUFS * BN <= 512, "accumulators must fit the tensor memory");
   static_assert(STAGE_BYTES % 1024 == 0 && A_BYTES % 1024 == 0, "operand tiles must stay 1024-byte aligned");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
@@ -959,14 +971,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
   } else if (warp == 1) {
     // ===== MMA issuer: one thread of the leader CTA drives both SMs' tensor cores =====
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = make_idesc(Num<T>::dtype == RPO_BF16 ? 1 : 0, 2 * BM, BN);
+      constexpr uint32_t idesc = make_idesc(Num<T>::dtype == RPO_BF16 ? 1 : 0, 2 * BM, C_::MMA_N);
       Sched sch;
       sch.init(stream_k, num_tiles, num_kb, cluster_id, num_clusters, num_n_tiles, dyn, clc_base, TileFeed::THREAD);
       Seg sg;
       uint32_t it = 0, t = 0;
       for (; sch.next(sg); ++t) {
-        const int a = t & 1;
-        mbar_wait(acc_empty(a), ((t >> 1) & 1) ^ 1);
+        const int a = C_::ACC_BUFS == 2 ? (int)(t & 1) : 0;
+        mbar_wait(acc_empty(a), ((C_::ACC_BUFS == 2 ? t >> 1 : t) & 1) ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(a * BN);
         for (int kb = sg.k0; kb < sg.k1; ++kb, ++it) {
@@ -980,7 +992,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
           if (!(dbg & 0x200)) {
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)
-              umma_f16_pair(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb != sg.k0) || (k != 0));
+#pragma unroll
+              for (int j = 0; j < C_::NMMA; ++j)  // B rows [MMA_N/2 * j, +MMA_N/2) of either CTA: 128-byte rows
+                umma_f16_pair(tmem_d + (uint32_t)(j * C_::MMA_N), adesc + 2u * k,
+                              bdesc + 2u * k + (uint32_t)(j * (C_::MMA_N / 2) * 128 / 16), idesc, (kb != sg.k0) || (k != 0));
           }
           umma_commit_pair(empty_bar(s));
         }
@@ -1002,7 +1017,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
     constexpr int PART_COLS = BN / (Thr<BN>::EPI_WARPS / 4);  // accumulator columns per warp in the stream-K partial
     pdl_wait();
     for (; sch.next(sg); ++t) {
-      const int a = t & 1;
+      const int a = C_::ACC_BUFS == 2 ? (int)(t & 1) : 0;
+      const uint32_t acc_par = (C_::ACC_BUFS == 2 ? t >> 1 : t) & 1;
       const long long m0 = (long long)(sg.tile / num_n_tiles) * (2 * BM) + (long long)rank * BM;
       const int n0 = (sg.tile % num_n_tiles) * BN;
       const uint32_t lead_empty = mapa_shared(acc_empty(a), 0);
@@ -1010,7 +1026,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
       if (sg.k0 > 0) {
         // ---- contributor: f32 partial of this CTA's 128 x BN half -> workspace slot of this cluster ----
         float4 *slot = reinterpret_cast<float4 *>(sk_slots + ((size_t)cluster_id * 2 + rank) * (BM * 256));
-        mbar_wait(acc_full(a), (t >> 1) & 1);
+        mbar_wait(acc_full(a), acc_par);
         tc_fence_after();
 #pragma unroll 1
         for (int cc = 0; cc < PART_COLS; cc += 32) {
@@ -1045,7 +1061,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
         named_bar_sync<Thr<BN>::EPI_WARPS * 32>(1);
       }
       if (dbg & 0x100) {
-        mbar_wait(acc_full(a), (t >> 1) & 1);
+        mbar_wait(acc_full(a), acc_par);
         tc_fence_after();
         tc_fence_before();
         __syncwarp();
@@ -1058,10 +1074,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
       epi.sk_stride = (size_t)sch.lanes * (2 * BM * 256);
       if (n_contrib)
         epi.template run_tile<true>(ep, tmem_acc, smem_u32(cstage), smem_u32(bias_s), C, m0, n0, M, ldc, acc_full(a),
-                                    (t >> 1) & 1, [&]() { mbar_arrive_cluster(lead_empty); });
+                                    acc_par, [&]() { mbar_arrive_cluster(lead_empty); });
       else
         epi.template run_tile<false>(ep, tmem_acc, smem_u32(cstage), smem_u32(bias_s), C, m0, n0, M, ldc, acc_full(a),
-                                     (t >> 1) & 1, [&]() { mbar_arrive_cluster(lead_empty); });
+                                     acc_par, [&]() { mbar_arrive_cluster(lead_empty); });
       if (n_contrib) {  // all partial reads are done (they precede the last slab barrier): re-arm the flags
         named_bar_sync<Thr<BN>::EPI_WARPS * 32>(1);
         if (etid < n_contrib) sk_flags[(cluster_id + (1 + etid) * sch.lanes) * 2 + rank] = 0;
@@ -1389,11 +1405,17 @@ static int launch_splitk(const T *A, long long lda, const T *B, long long ldb, T
 // ---- tile configuration --------------------------------------------------------------------------
 // P256/P128: CTA pairs, 256 x BN tiles.  S128/S64/S32: one CTA per SM, 128 x BN tiles, deep ring.
 // L64/L32: light 128 x BN tiles, two CTAs per SM.  RPO_GEMM_FORCE=<name> pins one (tuning sweeps).
-enum { CFG_P256 = 0, CFG_P128, CFG_S128, CFG_S64, CFG_S32, CFG_L64, CFG_L32, CFG_K4, CFG_K2, CFG_P192, CFG_COUNT };
-static const char *const kCfgNames[CFG_COUNT] = {"p256", "p128", "s128", "s64", "s32", "l64", "l32", "k4", "k2", "p192"};
+enum { CFG_P256 = 0, CFG_P128, CFG_S128, CFG_S64, CFG_S32, CFG_L64, CFG_L32, CFG_K4, CFG_K2, CFG_P192, CFG_P384, CFG_COUNT };
+static const char *const kCfgNames[CFG_COUNT] = {"p256", "p128", "s128", "s64", "s32", "l64",
+                                                 "l32",  "k4",   "k2",   "p192", "p384"};
 
-static bool cfg_valid(int cfg, int N) {
+// P384 has a single accumulator: only for problems whose 256 x 384 tiles fit in one round of SM pairs
+static bool p384_fits(long long M, int N) {
+  return N % 384 == 0 && ((M + 2 * BM - 1) / (2 * BM)) * (N / 384) <= sm_count() / 2;
+}
+static bool cfg_valid(int cfg, long long M, int N) {
   switch (cfg) {
+    case CFG_P384: return p384_fits(M, N);
     case CFG_P256: return N % 256 == 0;
     case CFG_P192: return N % 192 == 0;
     case CFG_P128: case CFG_S128: return N % 128 == 0;
@@ -1410,7 +1432,7 @@ static int pick_config(long long M, int N, int Kd) {
         if (strcmp(e, kCfgNames[i]) == 0) return i;
     return -1;
   }();
-  if (forced >= 0 && cfg_valid(forced, N)) return forced;
+  if (forced >= 0 && cfg_valid(forced, M, N)) return forced;
   // Measured on B200 over the step's shapes (tools/kernel_bench.py with RPO_GEMM_FORCE, profiles/r01_gemm_config_sweep.txt):
   //  * M >= 5120 (the vision tower's all-row GEMMs): operand traffic from L2 is the limiter, so CTA pairs
   //    (256 x 256, half the bytes per FLOP) win whenever N or K is long enough to amortise their 2-round tail;
@@ -1420,6 +1442,10 @@ static int pick_config(long long M, int N, int Kd) {
   //    few-tile problems get 128 x 32 tiles to put more SMs on the serial K loop.
   const long long mt = (M + BM - 1) / BM;
   if (mt >= 40) {
+    // (N = 768 -- out-proj, c_proj, patch embedding: 84 tiles of 256 x 256 are 2 rounds on 74 SM pairs, the second 14 %
+    // full, while 56 tiles of 256 x 384 are ONE round.  Measured SLOWER all the same -- out-proj 17.1 -> 18.9 us, c_proj
+    // 39.1 -> 41.0, patch 12.3 -> 15.6, step 3.27 -> 3.51 ms: a single accumulator leaves the 6-slab epilogue, 6-12 k
+    // cycles per tile (tools/gemm_trace.py), with no main loop to hide behind.  RPO_GEMM_FORCE=p384 keeps it reachable.)
     if (N % 256 == 0 && (N >= 2048 || Kd >= 2048)) return CFG_P256;
     if (N % 128 == 0) return CFG_S128;
     if (N % 64 == 0) return CFG_S64;
@@ -1469,6 +1495,7 @@ int gemm_tcgen05(const T *A, long long lda, const T *B, long long ldb, T *C, lon
       case tc::CFG_P256: return tc::launch_pair<T, 256>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);
       case tc::CFG_P128: return tc::launch_pair<T, 128>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);
       case tc::CFG_P192: return tc::launch_pair<T, 192>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);
+      case tc::CFG_P384: return tc::launch_pair<T, 384>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);
       case tc::CFG_S128: return tc::launch<T, 128, false>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);
       case tc::CFG_S64: return tc::launch<T, 64, false>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);
       case tc::CFG_S32: return tc::launch<T, 32, false>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);

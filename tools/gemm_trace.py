@@ -13,12 +13,16 @@ nb = 6
 A = [torch.randn(M, Kd, generator=g).half().to(dev) for _ in range(nb)]
 W = [(torch.randn(N, Kd, generator=g) * Kd ** -0.5).half().to(dev) for _ in range(nb)]
 Cm = [torch.empty(M, N, dtype=torch.float16, device=dev) for _ in range(nb)]
-trace = torch.zeros(512, 16, dtype=torch.int64, device=dev)
+trace = torch.zeros(4096, 16, dtype=torch.int64, device=dev)
+RES = [torch.randn(M, N, generator=g).half().to(dev) for _ in range(nb)] if os.environ.get("TRACE_RES") else None
+BIAS = torch.randn(N, generator=g).half().to(dev)
+ACT = int(os.environ.get("TRACE_ACT", "0"))
 
 
 def call(j):
-    _lib.check(lib.rpo_gemm_bias_act(A[j].data_ptr(), Kd, W[j].data_ptr(), Kd, Cm[j].data_ptr(), N, M, N, Kd, None, 0,
-                                     None, None, None, 0, 1, _lib.GEMM_AUTO, _lib.stream_ptr(dev)))
+    _lib.check(lib.rpo_gemm_bias_act(A[j].data_ptr(), Kd, W[j].data_ptr(), Kd, Cm[j].data_ptr(), N, M, N, Kd, BIAS.data_ptr(),
+                                     ACT, RES[j].data_ptr() if RES else None, None, None, 0, 1, _lib.GEMM_AUTO,
+                                     _lib.stream_ptr(dev)))
 
 
 for j in range(nb):
