@@ -30,7 +30,8 @@ extern "C" {
 
 /* element type of activations and of the Linear/Conv/projection weights
  * (clip/model.py:379-400 convert_weights; LayerNorm params, embeddings, logit_scale are always f32) */
-enum { RPO_F32 = 0, RPO_F16 = 1, RPO_BF16 = 2 };
+enum { RPO_F32 = 0, RPO_F16 = 1, RPO_BF16 = 2,
+       RPO_U8 = 3 /* image_dtype of rpo_forward only: raw pixels, normalised on the GPU */ };
 
 /* GEMM backends: tcgen05 (TMA + UMMA + TMEM, 16-bit types) or the generic SIMT kernel (any type,
  * exact fp32 FMA; the only backend for RPO_F32).  AUTO picks tcgen05 whenever the shape allows. */
@@ -100,12 +101,20 @@ int rpo_bind_weights(RpoHandle *h, const RpoWeights *w, void *stream);
 int rpo_set_classes(RpoHandle *h, const void *text_x, const int32_t *len_prompts, void *stream);
 
 /* CustomCLIP.forward (trainers/rpo.py:161-232).  image: device [B,3,res,res], f32 (image_dtype =
- * RPO_F32, cast to dtype inside like `image.type(self.dtype)`, :198) or already `dtype`.
+ * RPO_F32, cast to dtype inside like `image.type(self.dtype)`, :198), already `dtype`, or uint8
+ * (RPO_U8: raw pixels; ToTensor + Normalize of clip/clip.py:75-78 are applied in f32 inside the patch
+ * extraction, constants from rpo_set_image_norm -- a quarter of the host-to-device bytes).
  * text_prompt [K,Dt], img_prompt [K,Dv]: device, dtype (PromptLearner.forward, :89-90).
  * label: device int64 [B] or NULL.  logits: device f32 [B,C] or NULL.  loss: device f32 scalar or
- * NULL (requires label).  Saves what rpo_backward needs inside the handle. */
+ * NULL (requires label).  Saves what rpo_backward needs inside the handle.
+ * text_prompt == NULL (inference only: label must be NULL) reuses the text features of the last call
+ * that was given a text prompt: at test time the reference runs the whole text tower again for every
+ * batch (trainers/rpo.py:173-192 under TrainerX.test) although the prompts no longer change. */
 int rpo_forward(RpoHandle *h, const void *image, int32_t image_dtype, int32_t B, const void *text_prompt,
                 const void *img_prompt, const int64_t *label, float *logits, float *loss, void *stream);
+
+/* Per-channel mean / std of the uint8 image path (defaults: the CLIP constants of clip/clip.py:77). */
+int rpo_set_image_norm(RpoHandle *h, const float mean[3], const float std[3]);
 
 /* loss.backward() of trainers/rpo.py:308 restricted to what has a gradient (:258-260): writes
  * d loss / d text_prompt into grad_flat[0 : K*Dt] and d loss / d img_prompt into

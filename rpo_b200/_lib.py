@@ -11,13 +11,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "librpo_b200.so")
 
 RPO_F32, RPO_F16, RPO_BF16 = 0, 1, 2
+RPO_U8 = 3  # image dtype of rpo_forward only
 GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = 0, 1, 2
 ACT_NONE, ACT_QUICKGELU = 0, 1
 
 # every symbol include/rpo_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "rpo_last_error", "rpo_version", "rpo_create", "rpo_destroy", "rpo_device_bytes", "rpo_bind_weights",
-    "rpo_set_classes", "rpo_forward", "rpo_backward", "rpo_sgd_step", "rpo_layernorm_fwd", "rpo_layernorm_bwd",
+    "rpo_set_classes", "rpo_set_image_norm", "rpo_forward", "rpo_backward", "rpo_sgd_step", "rpo_layernorm_fwd", "rpo_layernorm_bwd",
     "rpo_gemm_bias_act", "rpo_gemm_bias_act_ws", "rpo_gemm_workspace_bytes", "rpo_ro_attention_fwd", "rpo_ro_attention_fwd_dense", "rpo_ro_attention_bwd", "rpo_logits_ce_fwd", "rpo_logits_ce_bwd",
     "rpo_debug_fetch", "rpo_launch_count", "rpo_profile_begin", "rpo_profile_end",
 ]
@@ -68,6 +69,7 @@ def load():
     lib.rpo_bind_weights.argtypes = [vp, C.POINTER(RpoWeights), vp]
     lib.rpo_set_classes.argtypes = [vp, vp, C.POINTER(i32), vp]
     lib.rpo_forward.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]
+    lib.rpo_set_image_norm.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.rpo_backward.argtypes = [vp, vp, vp]
     lib.rpo_sgd_step.argtypes = [vp, i32, vp, vp, i64, vp, f32, f32, f32, vp, vp]
     lib.rpo_layernorm_fwd.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp]

@@ -253,8 +253,12 @@ int logits_ce_bwd(const float *dlogits, const T *img_feat, const T *text_feat, c
                   float grad_scale, cudaStream_t st);
 
 // embedding / glue kernels (elementwise.cu)
+struct PixelNorm {  // per-channel Normalize of uint8 images (clip/clip.py:77)
+  float mean[3], std[3];
+};
 template <typename T>
-int im2col_patches(const void *image, int image_dtype, T *out, int B, int res, int patch, int ld, cudaStream_t st);
+int im2col_patches(const void *image, int image_dtype, T *out, int B, int res, int patch, int ld, const PixelNorm &nm,
+                   cudaStream_t st);
 template <typename T>
 int vision_assemble_lnpre(const T *patch_emb, const float *cls, const float *pos, const float *w, const float *b,
                           const T *img_prompt, T *x_ctx, T *x_prompt, int B, int S, int K, int D, cudaStream_t st);

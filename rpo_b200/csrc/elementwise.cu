@@ -195,9 +195,16 @@ int layernorm_bwd(const T *dy, const T *x, const float *w, const T *dres, T *dx,
 
 // ---- patch extraction: conv1 with stride == kernel (clip/model.py:215) is a GEMM over patches ----
 // out[(b*NP + py*G + px), c*P*P + ky*P + kx] = T(image[b, c, py*P+ky, px*P+kx])
+// uint8 pixels: ToTensor (x / 255) and Normalize ((x - mean[c]) / std[c]) of clip/clip.py:75-78 in f32, operation for
+// operation (true divisions, no fused multiply-add), then the cast to the model dtype of trainers/rpo.py:198 -- the same
+// value the reference's data pipeline + `image.type(self.dtype)` produce, from a quarter of the bytes over PCIe.
+__device__ __forceinline__ float pixel_norm(uint8_t v, float mean, float std) {
+  return __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.0f), mean), std);
+}
+
 template <typename T, typename TI>
 __global__ void im2col_kernel(const TI *__restrict__ img, T *__restrict__ out, int B, int res, int P, int ld,
-                              long long total) {
+                              long long total, PixelNorm nm) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   int G = res / P;
@@ -211,7 +218,12 @@ __global__ void im2col_kernel(const TI *__restrict__ img, T *__restrict__ out, i
   int p = (int)(row % (G * G));
   int b = (int)(row / (G * G));
   int py = p / G, px = p % G;
-  float v = Num<TI>::to_f(img[(((size_t)b * 3 + c) * res + (py * P + ky)) * res + (px * P + kx)]);
+  const TI raw = img[(((size_t)b * 3 + c) * res + (py * P + ky)) * res + (px * P + kx)];
+  float v;
+  if constexpr (sizeof(TI) == 1)
+    v = pixel_norm(raw, nm.mean[c], nm.std[c]);
+  else
+    v = Num<TI>::to_f(raw);
   out[idx] = fromf<T>(v);
 }
 
@@ -219,7 +231,8 @@ __global__ void im2col_kernel(const TI *__restrict__ img, T *__restrict__ out, i
 // contiguous bytes in, 16 contiguous bytes out; consecutive threads write consecutive 16-byte chunks of a
 // patch row, so stores are fully coalesced and loads are whole sectors.
 template <typename T, typename TI>
-__global__ void im2col_vec8_kernel(const TI *__restrict__ img, T *__restrict__ out, int res, int P, long long total8) {
+__global__ void im2col_vec8_kernel(const TI *__restrict__ img, T *__restrict__ out, int res, int P, long long total8,
+                                   PixelNorm nm) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total8) return;
   const int G = res / P, runs = P / 8, cols8 = 3 * P * runs;  // 16-byte chunks per patch row
@@ -235,6 +248,14 @@ __global__ void im2col_vec8_kernel(const TI *__restrict__ img, T *__restrict__ o
     const float4 a = __ldg(reinterpret_cast<const float4 *>(src)), bq = __ldg(reinterpret_cast<const float4 *>(src) + 1);
     o.v[0] = fromf<T>(a.x); o.v[1] = fromf<T>(a.y); o.v[2] = fromf<T>(a.z); o.v[3] = fromf<T>(a.w);
     o.v[4] = fromf<T>(bq.x); o.v[5] = fromf<T>(bq.y); o.v[6] = fromf<T>(bq.z); o.v[7] = fromf<T>(bq.w);
+  } else if constexpr (sizeof(TI) == 1) {
+    const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(src));  // 8 pixels
+    const float mean = nm.mean[c], std = nm.std[c];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      o.v[e] = fromf<T>(pixel_norm((uint8_t)(raw.x >> (8 * e)), mean, std));
+      o.v[4 + e] = fromf<T>(pixel_norm((uint8_t)(raw.y >> (8 * e)), mean, std));
+    }
   } else {
     o = ld16(reinterpret_cast<const T *>(src));
   }
@@ -242,30 +263,33 @@ __global__ void im2col_vec8_kernel(const TI *__restrict__ img, T *__restrict__ o
 }
 
 template <typename T>
-int im2col_patches(const void *image, int image_dtype, T *out, int B, int res, int patch, int ld, cudaStream_t st) {
+int im2col_patches(const void *image, int image_dtype, T *out, int B, int res, int patch, int ld, const PixelNorm &nm,
+                   cudaStream_t st) {
   int G = res / patch;
   long long total = (long long)B * G * G * ld;
   if (total == 0) return RPO_OK;
+  RPO_REQUIRE(image_dtype == RPO_F32 || image_dtype == RPO_U8 || image_dtype == Num<T>::dtype,
+              "image must be f32, uint8 or the model dtype");
   if (sizeof(T) == 2 && patch % 8 == 0 && res % 8 == 0 && ld == 3 * patch * patch && ((uintptr_t)image & 31) == 0 &&
       ((uintptr_t)out & 15) == 0) {
     const long long total8 = total / 8;
     const unsigned grid8 = (unsigned)((total8 + 255) / 256);
-    if (image_dtype == RPO_F32) {
-      im2col_vec8_kernel<T, float><<<grid8, 256, 0, st>>>((const float *)image, out, res, patch, total8);
-    } else {
-      RPO_REQUIRE(image_dtype == Num<T>::dtype, "image must be f32 or the model dtype");
-      im2col_vec8_kernel<T, T><<<grid8, 256, 0, st>>>((const T *)image, out, res, patch, total8);
-    }
+    if (image_dtype == RPO_F32)
+      im2col_vec8_kernel<T, float><<<grid8, 256, 0, st>>>((const float *)image, out, res, patch, total8, nm);
+    else if (image_dtype == RPO_U8)
+      im2col_vec8_kernel<T, uint8_t><<<grid8, 256, 0, st>>>((const uint8_t *)image, out, res, patch, total8, nm);
+    else
+      im2col_vec8_kernel<T, T><<<grid8, 256, 0, st>>>((const T *)image, out, res, patch, total8, nm);
     RPO_LAUNCH_CHECK();
     return RPO_OK;
   }
   unsigned grid = (unsigned)((total + 255) / 256);
-  if (image_dtype == RPO_F32) {
-    im2col_kernel<T, float><<<grid, 256, 0, st>>>((const float *)image, out, B, res, patch, ld, total);
-  } else {
-    RPO_REQUIRE(image_dtype == Num<T>::dtype, "image must be f32 or the model dtype");
-    im2col_kernel<T, T><<<grid, 256, 0, st>>>((const T *)image, out, B, res, patch, ld, total);
-  }
+  if (image_dtype == RPO_F32)
+    im2col_kernel<T, float><<<grid, 256, 0, st>>>((const float *)image, out, B, res, patch, ld, total, nm);
+  else if (image_dtype == RPO_U8)
+    im2col_kernel<T, uint8_t><<<grid, 256, 0, st>>>((const uint8_t *)image, out, B, res, patch, ld, total, nm);
+  else
+    im2col_kernel<T, T><<<grid, 256, 0, st>>>((const T *)image, out, B, res, patch, ld, total, nm);
   RPO_LAUNCH_CHECK();
   return RPO_OK;
 }
@@ -520,7 +544,7 @@ int sgd_step(T *p, const float *g, float *buf, long long n, const float *lr, flo
 #define INSTANTIATE(T)                                                                                              \
   template int layernorm_fwd<T>(const T *, const float *, const float *, T *, long long, int, cudaStream_t);        \
   template int layernorm_bwd<T>(const T *, const T *, const float *, const T *, T *, long long, int, cudaStream_t); \
-  template int im2col_patches<T>(const void *, int, T *, int, int, int, int, cudaStream_t);                              \
+  template int im2col_patches<T>(const void *, int, T *, int, int, int, int, const PixelNorm &, cudaStream_t);                              \
   template int vision_assemble_lnpre<T>(const T *, const float *, const float *, const float *, const float *,      \
                                         const T *, T *, T *, int, int, int, int, cudaStream_t);                     \
   template int text_gather_ctx<T>(const T *, const int *, const int *, const int *, T *, long long, int, int,       \

@@ -106,6 +106,8 @@ struct RpoHandle {
   std::vector<void *> owned;  // separately cudaMalloc'ed blocks
   RpoWeights w{};
   bool bound = false, classes_set = false, fwd_has_grad = false;
+  bool text_feat_valid = false;  // text_feat holds the features of the last text prompt given to rpo_forward
+  PixelNorm norm = {{0.48145466f, 0.4578275f, 0.40821073f}, {0.26862954f, 0.26130258f, 0.27577711f}};
   int B = 0;
   // vision front end
   char *patches = nullptr, *patch_emb = nullptr, *x_raw = nullptr;
@@ -270,7 +272,8 @@ static int forward_impl(RpoHandle *hd, const void *image, int image_dtype, int B
   // ---- text tower, prompt rows only (context K/V cached by rpo_set_classes) (:173-191) ----
   cudaStream_t st_main = st;
   const long long Mp_t = (long long)C * K;
-  {
+  const bool run_text = text_prompt != nullptr;  // else: cached text features (inference)
+  if (run_text) {
     cudaStream_t st = st_main;  // launch sites below refer to `st`
     if (hd->overlap) {
       RPO_CHECK_CUDA(cudaEventRecord(hd->ev_fork, st_main));
@@ -286,7 +289,7 @@ static int forward_impl(RpoHandle *hd, const void *image, int image_dtype, int B
                              E, Dt, ep, st));
     if (hd->overlap) RPO_CHECK_CUDA(cudaEventRecord(hd->ev_join, hd->side));
   }
-  RPO_TRY(im2col_patches<T>(image, image_dtype, (T *)hd->patches, B, c.v_res, c.v_patch, hd->pk_pad, st));
+  RPO_TRY(im2col_patches<T>(image, image_dtype, (T *)hd->patches, B, c.v_res, c.v_patch, hd->pk_pad, hd->norm, st));
   Epilogue<T> ep = frozen_ep<T>(v.sk_ws);
   const int pk = hd->pk_pad;
   RPO_TRY(gemm_dispatch<T>(backend, (const T *)hd->patches, pk, (const T *)hd->conv_w_eff, pk, (T *)hd->patch_emb, Dv,
@@ -301,7 +304,8 @@ static int forward_impl(RpoHandle *hd, const void *image, int image_dtype, int B
   RPO_TRY(layernorm_fwd<T>(xv_out, hd->w.ln_post_w, hd->w.ln_post_b, (T *)hd->hp_v, Mp_v, Dv, st));
   RPO_TRY(gemm_dispatch<T>(backend, (const T *)hd->hp_v, Dv, (const T *)hd->v_projT, Dv, (T *)hd->img_feat, E, Mp_v, E,
                            Dv, ep, st));
-  if (hd->overlap) RPO_CHECK_CUDA(cudaStreamWaitEvent(st_main, hd->ev_join, 0));
+  if (hd->overlap && run_text) RPO_CHECK_CUDA(cudaStreamWaitEvent(st_main, hd->ev_join, 0));
+  if (run_text) hd->text_feat_valid = true;
   // ---- logits + CE (:215-230) ----
   float *lg = logits ? logits : hd->logits_f;
   RPO_TRY(logits_ce_fwd<T>((const T *)hd->img_feat, (const T *)hd->text_feat, hd->w.logit_scale, label, B, C, K, E,
@@ -674,13 +678,16 @@ int rpo_set_classes(RpoHandle *h, const void *text_x, const int32_t *len_prompts
     default: s = set_classes_impl<__nv_bfloat16>(h, text_x, st); break;
   }
   if (s == RPO_OK) h->classes_set = true;
+  h->text_feat_valid = false;
   return s;
 }
 
 int rpo_forward(RpoHandle *h, const void *image, int32_t image_dtype, int32_t B, const void *text_prompt,
                 const void *img_prompt, const int64_t *label, float *logits, float *loss, void *stream) {
-  RPO_REQUIRE(h && image && text_prompt && img_prompt, "null argument");
+  RPO_REQUIRE(h && image && img_prompt, "null argument");
   RPO_REQUIRE(h->bound && h->classes_set, "rpo_bind_weights and rpo_set_classes must be called first");
+  RPO_REQUIRE(text_prompt || (h->text_feat_valid && !label),
+              "text_prompt may only be NULL for inference after a call that computed the text features");
   RPO_REQUIRE(B >= 1 && B <= h->cfg.max_batch, "batch size exceeds max_batch");
   RPO_REQUIRE(!loss || label, "loss requires labels");
   cudaStream_t st = (cudaStream_t)stream;
@@ -689,6 +696,16 @@ int rpo_forward(RpoHandle *h, const void *image, int32_t image_dtype, int32_t B,
     case RPO_F16: return forward_impl<__half>(h, image, image_dtype, B, text_prompt, img_prompt, label, logits, loss, st);
     default: return forward_impl<__nv_bfloat16>(h, image, image_dtype, B, text_prompt, img_prompt, label, logits, loss, st);
   }
+}
+
+int rpo_set_image_norm(RpoHandle *h, const float mean[3], const float std[3]) {
+  RPO_REQUIRE(h && mean && std, "null argument");
+  for (int c = 0; c < 3; ++c) {
+    RPO_REQUIRE(std[c] > 0.f, "std must be positive");
+    h->norm.mean[c] = mean[c];
+    h->norm.std[c] = std[c];
+  }
+  return RPO_OK;
 }
 
 int rpo_backward(RpoHandle *h, float *grad_flat, void *stream) {

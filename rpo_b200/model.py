@@ -88,16 +88,22 @@ class Engine:
             raise _lib.RpoError(f"image is on {image.device}, engine on {self.device}")
         if image.dtype == torch.float32:
             idt = _lib.RPO_F32
+        elif image.dtype == torch.uint8:
+            idt = _lib.RPO_U8  # raw pixels: ToTensor + Normalize (clip/clip.py:75-78) happen inside the patch extraction
         elif image.dtype == self.dtype:
             idt = _lib.dtype_code(self.dtype)
         else:
-            raise _lib.RpoError(f"image dtype {image.dtype} must be float32 or {self.dtype}")
+            raise _lib.RpoError(f"image dtype {image.dtype} must be float32, uint8 or {self.dtype}")
         res = self.arch.v_res
         if tuple(image.shape[1:]) != (3, res, res):
             raise _lib.RpoError(f"image must be [B,3,{res},{res}], got {tuple(image.shape)}")
         if B > self.max_batch:
             raise _lib.RpoError(f"batch {B} exceeds max_batch {self.max_batch}")
+        if text_prompt is None and label is not None:
+            raise _lib.RpoError("cached text features are for inference only (label must be None)")
         for t, n in ((text_prompt, self.arch.t_width), (img_prompt, self.arch.v_width)):
+            if t is None and n == self.arch.t_width:
+                continue  # reuse the text features of the last call that was given a text prompt
             if t.dtype != self.dtype or tuple(t.shape) != (self.K, n) or t.device != self.device:
                 raise _lib.RpoError("prompt tensors must be [K, width] in the model dtype on the engine device")
         if label is not None and (label.dtype != torch.int64 or label.shape[0] != B or label.device != self.device):
@@ -106,10 +112,18 @@ class Engine:
         logits = self.logits[:B] if (want_logits or label is None) else None
         with torch.cuda.device(self.device):
             _lib.check(self.lib.rpo_forward(
-                self.handle, _lib.ptr(image), idt, B, _lib.ptr(text_prompt.detach().contiguous()),
+                self.handle, _lib.ptr(image), idt, B,
+                _lib.ptr(text_prompt.detach().contiguous()) if text_prompt is not None else None,
                 _lib.ptr(img_prompt.detach().contiguous()), _lib.ptr(label), _lib.ptr(logits),
                 _lib.ptr(self.loss) if label is not None else None, _lib.stream_ptr(self.device)))
         return (self.loss if label is not None else None), logits
+
+    def set_image_norm(self, mean, std):
+        """Per-channel mean / std of the uint8 image path (default: the CLIP constants, clip/clip.py:77)."""
+        import ctypes
+        m = (ctypes.c_float * 3)(*[float(x) for x in mean])
+        sd = (ctypes.c_float * 3)(*[float(x) for x in std])
+        _lib.check(self.lib.rpo_set_image_norm(self.handle, m, sd))
 
     def backward(self):
         """Enqueues the prompt-gradient pass; returns the flat f32 gradient [K*Dt + K*Dv]."""
@@ -225,6 +239,12 @@ class CustomCLIP(nn.Module):
         self.register_buffer("w_mm", w_mm, persistent=False)
         self.register_buffer("w_f32", w_f32, persistent=False)
         self._engine = None
+        self._text_key = None     # (engine, prompt storage, prompt version, epoch) of the cached text features
+        self._prompt_epoch = 0    # bumped by whatever changes the prompts behind autograd's back (fused SGD step)
+
+    def invalidate_text_features(self):
+        self._prompt_epoch += 1
+        self._text_key = None
 
     def make_prompts(self, classnames, prompt, sd, tokens=None, tokenizer=None):
         # trainers/rpo.py:132-138 (class-name substitution keeps underscores inside names, H13)
@@ -266,11 +286,19 @@ class CustomCLIP(nn.Module):
         eng = self.engine(image.shape[0])
         text_prompt, image_prompt = self.prompt_learner()
         if self.prompt_learner.training:
+            self._text_key = None
             if label is None:
                 raise ValueError("label is required in training mode (F.cross_entropy(logits, label))")
             if torch.is_grad_enabled() and (text_prompt.requires_grad or image_prompt.requires_grad):
                 return _RpoLoss.apply(text_prompt, image_prompt, eng, image, label)
             loss, _ = eng.forward(image, text_prompt, image_prompt, label)
             return loss.clone()
-        _, logits = eng.forward(image, text_prompt, image_prompt, None)
+        # Inference (Dassl TrainerX.test -> model_inference): the reference recomputes the whole text tower for every
+        # test batch (trainers/rpo.py:173-192); the text features only depend on text_prompt, so they are computed once
+        # per (engine, prompt version) and reused.  Any training-mode forward, optimiser step through
+        # StepRunner, load_state_dict or in-place edit of the parameter invalidates the cache.
+        key = (id(eng), text_prompt.data_ptr(), text_prompt._version, self._prompt_epoch)
+        cached = self._text_key == key
+        _, logits = eng.forward(image, None if cached else text_prompt, image_prompt, None)
+        self._text_key = key
         return logits.clone()

@@ -12,7 +12,7 @@ from . import _lib
 
 class StepRunner:
     def __init__(self, model, batch, lr=0.01, momentum=0.9, weight_decay=5e-4, use_graph=True, process_group=None,
-                 world_size=1):
+                 world_size=1, image_dtype=torch.float32):
         self.model = model
         self.B = int(batch)
         self.device = model.w_mm.device
@@ -21,7 +21,9 @@ class StepRunner:
         self.momentum, self.wd = float(momentum), float(weight_decay)
         self.eng = model.engine(self.B)
         res = model.arch.v_res
-        self.image = torch.zeros(self.B, 3, res, res, dtype=torch.float32, device=self.device)
+        # float32 = what the reference's DataLoader hands over (trainers/rpo.py:318-323); torch.uint8 = raw pixels,
+        # normalised inside the patch extraction (a quarter of the host-to-device bytes)
+        self.image = torch.zeros(self.B, 3, res, res, dtype=image_dtype, device=self.device)
         self.label = torch.zeros(self.B, dtype=torch.int64, device=self.device)
         self.lr = torch.tensor(float(lr), dtype=torch.float32, device=self.device)
         self.first = torch.ones(1, dtype=torch.int32, device=self.device)
@@ -80,6 +82,7 @@ class StepRunner:
 
     def step(self):
         """Enqueues one step on the current stream.  Inputs are whatever self.image / self.label hold."""
+        self.model.invalidate_text_features()  # the fused SGD kernel rewrites the prompts in place
         if self.graph is not None:
             self.graph.replay()
             if self.world > 1:

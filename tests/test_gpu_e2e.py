@@ -230,3 +230,73 @@ def test_errors_are_loud():
         long_tokens[0, 1:76] = 320  # push the EOT token (the argmax) to the last position
         long_tokens[0, 76] = 49407
         build_model("tiny", "fp16", 4, long_tokens)
+
+
+@pytest.mark.parametrize("arch_name,prec", [("tiny", "fp16"), ("ViT-B/16", "fp16"), ("tiny", "fp32"), ("ViT-B/16", "bf16")])
+def test_uint8_images_match_the_float_pipeline(arch_name, prec):
+    """raw uint8 pixels, ToTensor + Normalize (clip/clip.py:75-78) applied inside the patch extraction,
+    against the same preprocessing done on the host in IEEE f32 (numpy: true divisions) and uploaded as float32 --
+    the reference's data path (DataLoader tensor -> `.to(device)` -> `image.type(self.dtype)`).  Bit-identical."""
+    tokens = class_tokens([3, 14, 159])
+    model, arch, _ = build_model(arch_name, prec, 4, tokens)
+    res = arch.image_resolution
+    rng = np.random.default_rng(5)
+    img_u8 = rng.integers(0, 256, size=(3, 3, res, res), dtype=np.uint8)
+    img_u8[0, :, 0, :8] = [[0, 1, 2, 127, 128, 253, 254, 255]] * 3  # range ends
+    mean = np.array([0.48145466, 0.4578275, 0.40821073], dtype=np.float32).reshape(1, 3, 1, 1)
+    std = np.array([0.26862954, 0.26130258, 0.27577711], dtype=np.float32).reshape(1, 3, 1, 1)
+    img_f32 = (img_u8.astype(np.float32) / np.float32(255.0) - mean) / std
+    assert img_f32.dtype == np.float32
+    a = eval_logits(model, torch.from_numpy(img_u8).to("cuda:0"))
+    b = eval_logits(model, torch.from_numpy(img_f32).to("cuda:0"))
+    assert torch.isfinite(a).all()
+    assert torch.equal(a, b)
+    # other constants go through rpo_set_image_norm
+    model.engine(3).set_image_norm([0.5, 0.5, 0.5], [0.25, 0.5, 1.0])
+    m2 = np.array([0.5, 0.5, 0.5], dtype=np.float32).reshape(1, 3, 1, 1)
+    s2 = np.array([0.25, 0.5, 1.0], dtype=np.float32).reshape(1, 3, 1, 1)
+    c = eval_logits(model, torch.from_numpy(img_u8).to("cuda:0"))
+    d = eval_logits(model, torch.from_numpy((img_u8.astype(np.float32) / np.float32(255.0) - m2) / s2).to("cuda:0"))
+    assert torch.equal(c, d) and not torch.equal(a, c)
+    # training step from uint8 pixels
+    label = torch.tensor([0, 1, 2], device="cuda:0")
+    l8, gt8, gi8 = step(model, torch.from_numpy(img_u8).to("cuda:0"), label)
+    lf, gtf, gif = step(model, torch.from_numpy((img_u8.astype(np.float32) / np.float32(255.0) - m2) / s2).to("cuda:0"), label)
+    assert torch.equal(l8, lf) and torch.equal(gt8, gtf) and torch.equal(gi8, gif)
+
+
+def test_eval_reuses_text_features():
+    """at test time the text features depend on the prompts only; they are computed once and reused
+    until the prompts change (the reference reruns the text tower per batch, trainers/rpo.py:173-192)."""
+    tokens = class_tokens([1, 20, 300, 4])
+    model, arch, _ = build_model("tiny", "fp16", 4, tokens)
+    res = arch.image_resolution
+    g = torch.Generator().manual_seed(3)
+    img1 = torch.randn(2, 3, res, res, generator=g).to("cuda:0")
+    img2 = torch.randn(3, 3, res, res, generator=g).to("cuda:0")
+    eng = model.engine(3)
+    first = eval_logits(model, img1)
+    n_full = eng.launch_count()
+    cached = eval_logits(model, img2)          # second batch: text tower skipped
+    n_cached = eng.launch_count()
+    assert n_cached < n_full
+    model._text_key = None
+    fresh = eval_logits(model, img2)
+    assert eng.launch_count() == n_full
+    assert torch.equal(cached, fresh)
+    # the cache follows the prompts: in-place edit, training-mode forward, fused optimiser step
+    with torch.no_grad():
+        model.prompt_learner.text_prompt.add_(0.05)
+    moved = eval_logits(model, img2)
+    assert eng.launch_count() == n_full and not torch.equal(moved, fresh)
+    again = eval_logits(model, img2)
+    assert eng.launch_count() == n_cached and torch.equal(again, moved)
+    step(model, img1, torch.tensor([0, 1], device="cuda:0"))
+    eval_logits(model, img2)
+    n_recomputed = eng.launch_count()          # (the count now also holds the backward launches of the step)
+    eval_logits(model, img2)
+    assert n_recomputed - eng.launch_count() == n_full - n_cached
+    # C ABI contract: cached features are for inference only
+    with pytest.raises(_lib.RpoError):
+        eng.forward(img1, None, model.prompt_learner.img_prompt.data, torch.tensor([0, 1], device="cuda:0"))
+    assert first.shape == (2, 4)
