@@ -325,6 +325,9 @@ def main_own(args):
                        tokens=synthetic_tokens(C), max_batch=B).to(dev)
     model.prompt_learner.train()
     pg = dist.group.WORLD if world > 1 else None
+    shard_text = world > 1 and args.shard_text
+    if shard_text:
+        model.shard_text(rank, world, pg)  # each rank runs ceil(C / world) class prompts
     runner = StepRunner(model, B, lr=0.01, momentum=0.9, weight_decay=5e-4, use_graph=not args.no_graph,
                         process_group=pg, world_size=world)
 
@@ -430,7 +433,9 @@ def main_own(args):
                 **WORKLOAD, "global_batch": B * world, "parallelism": f"dp{world}",
                 "l2_policy": "inputs rotate through 8 distinct batches (154 MB > 126 MB L2); a step touches ~1.5 GB "
                              "of activations",
-                "cuda_graph": runner.graph is not None,
+                "cuda_graph": runner.graph is not None or (runner.segments is not None and not args.no_graph),
+                "text_tower": (f"class-sharded over {world} ranks (all-gather of text features + reduce-scatter of "
+                               f"their gradient)") if shard_text else "replicated on every rank (as the reference)",
             },
             "images_per_sec_per_gpu": imgs / t_dev / world,
             "clocks": clocks,
@@ -468,6 +473,8 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard-text", action="store_true",
+                    help="N > 1: class-shard the text tower over the ranks (default: replicated, as the reference)")
     a = ap.parse_args()
     if a.impl == "reference":
         main_reference(a)

@@ -54,7 +54,14 @@ typedef struct {
   int32_t t_width, t_layers, t_heads;
   int32_t max_batch;    /* largest B rpo_forward will be called with (workspace is sized for it) */
   int32_t gemm_backend; /* RPO_GEMM_* */
-  int32_t reserved[3];
+  /* Class shard of the text tower (data-parallel ranks each run C/G of the class prompts that
+   * trainers/rpo.py:180-192 runs in full on every GPU).  cls_local == 0: the handle owns all n_cls classes.
+   * Otherwise this handle's text tower covers classes [cls_first, cls_first + cls_local) only: rpo_set_classes
+   * takes the text_x / len_prompts of those classes, and the step is driven through the stage entry points below
+   * with an all-gather of the text features and a reduce-scatter of their gradient in between.  Logits, loss and
+   * the image side always span all n_cls classes. */
+  int32_t cls_first, cls_local;
+  int32_t reserved[1];
 } RpoConfig;
 
 /* One ResidualAttentionBlock (clip/model.py:167-191).  ln_* are f32 [D]; the rest are `dtype`:
@@ -97,7 +104,8 @@ int rpo_bind_weights(RpoHandle *h, const RpoWeights *w, void *stream);
  * the prompt-independent part of the text tower call (:180-181): runs the n_c = len_prompts[c]
  * readable context tokens of every class through the text transformer once and caches their
  * per-layer K/V.  text_x: device [C, T, Dt] dtype (token + positional embedding);
- * len_prompts: HOST int32 [C], each in [1, T-K].  Synchronises `stream`. */
+ * len_prompts: HOST int32 [C], each in [1, T-K].  Synchronises `stream`.
+ * With a class shard (RpoConfig.cls_local > 0) both arrays hold the cls_local classes of the handle only. */
 int rpo_set_classes(RpoHandle *h, const void *text_x, const int32_t *len_prompts, void *stream);
 
 /* CustomCLIP.forward (trainers/rpo.py:161-232).  image: device [B,3,res,res], f32 (image_dtype =
@@ -121,6 +129,32 @@ int rpo_set_image_norm(RpoHandle *h, const float mean[3], const float std[3]);
  * grad_flat[K*Dt : K*Dt + K*Dv] (f32, contiguous: all-reduce ready).  Must follow an rpo_forward
  * that was given a label. */
 int rpo_backward(RpoHandle *h, float *grad_flat, void *stream);
+
+/* Stage entry points ------------------------------------------------------------------------------
+ * rpo_forward == rpo_forward_text (on a side stream) || rpo_forward_image, then rpo_forward_logits;
+ * rpo_backward == rpo_backward_logits, then rpo_backward_text (side stream) || rpo_backward_image.
+ * They exist so that a class-sharded text tower (RpoConfig.cls_local) can put its two collectives between the
+ * stages: text features are all-gathered after rpo_forward_text, their gradient is reduce-scattered (sum) after
+ * rpo_backward_logits.  Each call only enqueues kernels on `stream`; ordering between streams is the caller's
+ * (events).  The exchange buffers are caller-owned so that the collective library can address them:
+ * text_feat and d_text_feat, both [C_pad, K, E] `dtype` with C_pad >= n_cls (rows >= n_cls are never touched by
+ * the library: keep them zero).  rpo_forward_text writes rows [cls_first*K, (cls_first+cls_local)*K) of
+ * text_feat; rpo_forward_logits reads rows [0, n_cls*K); rpo_backward_logits writes rows [0, n_cls*K) of
+ * d_text_feat (the contribution of THIS rank's images); rpo_backward_text reads rows
+ * [cls_first*K, (cls_first+cls_local)*K) of d_text_feat and writes grad_flat[0 : K*Dt] (sum over the local
+ * classes); rpo_backward_image writes grad_flat[K*Dt : K*Dt + K*Dv]. */
+int rpo_bind_text_exchange(RpoHandle *h, void *text_feat, void *d_text_feat);
+/* trainers/rpo.py:173-192 for the handle's classes: splice, text tower (prompt rows), ln_final, gather, projection */
+int rpo_forward_text(RpoHandle *h, const void *text_prompt, void *stream);
+/* trainers/rpo.py:198-211: patch embedding, prompt concat, ln_pre, vision tower, ln_post, projection */
+int rpo_forward_image(RpoHandle *h, const void *image, int32_t image_dtype, int32_t B, const void *img_prompt,
+                      void *stream);
+/* trainers/rpo.py:215-230: normalise, K-pair logits, cross-entropy (same argument rules as rpo_forward) */
+int rpo_forward_logits(RpoHandle *h, const int64_t *label, float *logits, float *loss, void *stream);
+/* d loss / d img_feat and d loss / d text_feat (all n_cls classes, this rank's images) */
+int rpo_backward_logits(RpoHandle *h, void *stream);
+int rpo_backward_text(RpoHandle *h, float *grad_flat, void *stream);
+int rpo_backward_image(RpoHandle *h, float *grad_flat, void *stream);
 
 /* optim.step() of trainers/rpo.py:309 for torch.optim.SGD semantics (momentum, dampening 0, L2
  * weight decay, no nesterov) applied to one parameter in `dtype` with an f32 gradient:
@@ -206,7 +240,7 @@ int rpo_logits_ce_bwd(const float *dlogits, const void *img_feat, const void *te
  * `cap` elements (dtype) to `dst` (device).  layer = -1 means the tower input. */
 int64_t rpo_debug_fetch(RpoHandle *h, int32_t which, int32_t layer, void *dst, int64_t cap, void *stream);
 
-/* number of kernel launches issued by the last rpo_forward + rpo_backward pair */
+/* number of kernel launches issued by the last rpo_forward + rpo_backward pair (or the last call of each stage) */
 int64_t rpo_launch_count(const RpoHandle *h);
 
 /* Launch profiler (diagnostics; not for use inside CUDA-graph capture).  Between rpo_profile_begin and

@@ -21,13 +21,16 @@ SYMBOLS = [
     "rpo_set_classes", "rpo_set_image_norm", "rpo_forward", "rpo_backward", "rpo_sgd_step", "rpo_layernorm_fwd", "rpo_layernorm_bwd",
     "rpo_gemm_bias_act", "rpo_gemm_bias_act_ws", "rpo_gemm_workspace_bytes", "rpo_ro_attention_fwd", "rpo_ro_attention_fwd_dense", "rpo_ro_attention_bwd", "rpo_logits_ce_fwd", "rpo_logits_ce_bwd",
     "rpo_debug_fetch", "rpo_launch_count", "rpo_profile_begin", "rpo_profile_end",
+    "rpo_bind_text_exchange", "rpo_forward_text", "rpo_forward_image", "rpo_forward_logits", "rpo_backward_logits",
+    "rpo_backward_text", "rpo_backward_image",
 ]
 
 
 class RpoConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "dtype", "K", "n_cls", "ctx_len", "embed_dim", "v_width", "v_layers", "v_heads", "v_patch", "v_res",
-        "t_width", "t_layers", "t_heads", "max_batch", "gemm_backend")] + [("reserved", C.c_int32 * 3)]
+        "t_width", "t_layers", "t_heads", "max_batch", "gemm_backend", "cls_first", "cls_local")] + \
+        [("reserved", C.c_int32 * 1)]
 
 
 class RpoBlockWeights(C.Structure):
@@ -71,6 +74,13 @@ def load():
     lib.rpo_forward.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.rpo_set_image_norm.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.rpo_backward.argtypes = [vp, vp, vp]
+    lib.rpo_bind_text_exchange.argtypes = [vp, vp, vp]
+    lib.rpo_forward_text.argtypes = [vp, vp, vp]
+    lib.rpo_forward_image.argtypes = [vp, vp, i32, i32, vp, vp]
+    lib.rpo_forward_logits.argtypes = [vp, vp, vp, vp, vp]
+    lib.rpo_backward_logits.argtypes = [vp, vp]
+    lib.rpo_backward_text.argtypes = [vp, vp, vp]
+    lib.rpo_backward_image.argtypes = [vp, vp, vp]
     lib.rpo_sgd_step.argtypes = [vp, i32, vp, vp, i64, vp, f32, f32, f32, vp, vp]
     lib.rpo_layernorm_fwd.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp]
     lib.rpo_layernorm_bwd.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, vp]

@@ -109,6 +109,8 @@ struct RpoHandle {
   bool text_feat_valid = false;  // text_feat holds the features of the last text prompt given to rpo_forward
   PixelNorm norm = {{0.48145466f, 0.4578275f, 0.40821073f}, {0.26862954f, 0.26130258f, 0.27577711f}};
   int B = 0;
+  int c0 = 0, Cl = 0;  // class shard of the text tower: classes [c0, c0 + Cl) of cfg.n_cls (Cl == n_cls: all of them)
+  bool have_image = false, have_logits_bwd = false;
   // vision front end
   char *patches = nullptr, *patch_emb = nullptr, *x_raw = nullptr;
   // heads
@@ -122,7 +124,7 @@ struct RpoHandle {
   // text context gather maps
   int *row_cls = nullptr, *row_pos = nullptr;
   const void *img_prompt = nullptr;  // from the last forward (needed by the ln_pre backward)
-  int64_t launches_fwd = 0, launches_bwd = 0;
+  int64_t launches[6] = {0, 0, 0, 0, 0, 0};  // per stage: text / image / logits forward, logits / text / image backward
   // The text tower (C*K prompt rows: many short, latency-bound kernels) runs on a side stream next to
   // the vision tower, fork/joined with events so that the pair stays capturable into one CUDA graph.
   cudaStream_t side = nullptr;
@@ -257,38 +259,41 @@ static int tower_backward(RpoHandle *hd, Tower &tw, cudaStream_t st) {
   return RPO_OK;
 }
 
+// ---- stages of one step.  rpo_forward / rpo_backward chain them with the text stages forked onto the side
+// stream; a class-sharded caller (RpoConfig.cls_local) runs them one by one with its collectives in between.
+
+// text tower, prompt rows of the handle's classes only (context K/V cached by rpo_set_classes) (:173-191)
 template <typename T>
-static int forward_impl(RpoHandle *hd, const void *image, int image_dtype, int B, const void *text_prompt,
-                        const void *img_prompt, const int64_t *label, float *logits, float *loss, cudaStream_t st) {
+static int text_forward_stage(RpoHandle *hd, const void *text_prompt, cudaStream_t st) {
   const RpoConfig &c = hd->cfg;
-  Tower &v = hd->vis, &t = hd->txt;
-  const int K = c.K, C = c.n_cls, E = c.embed_dim, Dv = c.v_width, Dt = c.t_width, S = hd->S;
+  Tower &t = hd->txt;
+  const int K = c.K, E = c.embed_dim, Dt = c.t_width, Cl = hd->Cl;
+  const long long Mp_t = (long long)Cl * K;
+  g_launch_count = 0;
+  RPO_TRY(broadcast_rows<T>((const T *)text_prompt, (T *)t.x_in + t.Mc * Dt, Cl, K, Dt, st));
+  if (hd->skip != 1) RPO_TRY(tower_forward<T>(hd, t, false, true, st));
+  T *xt_out = at<T>(t.x_in, (long long)t.layers * t.Mtot_max * Dt) + t.Mc * Dt;
+  RPO_TRY(layernorm_fwd<T>(xt_out, hd->w.ln_final_w, hd->w.ln_final_b, (T *)hd->hp_t, Mp_t, Dt, st));
+  Epilogue<T> ep = frozen_ep<T>();
+  RPO_TRY(gemm_dispatch<T>(c.gemm_backend, (const T *)hd->hp_t, Dt, (const T *)hd->t_projT, Dt,
+                           (T *)hd->text_feat + (long long)hd->c0 * K * E, E, Mp_t, E, Dt, ep, st));
+  hd->text_feat_valid = true;
+  hd->launches[0] = g_launch_count;
+  return RPO_OK;
+}
+
+// vision front end and tower (trainers/rpo.py:198-211)
+template <typename T>
+static int image_forward_stage(RpoHandle *hd, const void *image, int image_dtype, int B, const void *img_prompt,
+                               cudaStream_t st) {
+  const RpoConfig &c = hd->cfg;
+  Tower &v = hd->vis;
+  const int K = c.K, E = c.embed_dim, Dv = c.v_width, S = hd->S;
   const int backend = c.gemm_backend;
   g_launch_count = 0;
-  // ---- vision front end (trainers/rpo.py:198-206) ----
   v.G = B;
   v.Mc = (long long)B * S;
   const long long Mp_v = (long long)B * K;
-  // ---- text tower, prompt rows only (context K/V cached by rpo_set_classes) (:173-191) ----
-  cudaStream_t st_main = st;
-  const long long Mp_t = (long long)C * K;
-  const bool run_text = text_prompt != nullptr;  // else: cached text features (inference)
-  if (run_text) {
-    cudaStream_t st = st_main;  // launch sites below refer to `st`
-    if (hd->overlap) {
-      RPO_CHECK_CUDA(cudaEventRecord(hd->ev_fork, st_main));
-      RPO_CHECK_CUDA(cudaStreamWaitEvent(hd->side, hd->ev_fork, 0));
-      st = hd->side;
-    }
-    RPO_TRY(broadcast_rows<T>((const T *)text_prompt, (T *)t.x_in + t.Mc * Dt, C, K, Dt, st));
-    if (hd->skip != 1) RPO_TRY(tower_forward<T>(hd, t, false, true, st));
-    T *xt_out = at<T>(t.x_in, (long long)t.layers * t.Mtot_max * Dt) + t.Mc * Dt;
-    RPO_TRY(layernorm_fwd<T>(xt_out, hd->w.ln_final_w, hd->w.ln_final_b, (T *)hd->hp_t, Mp_t, Dt, st));
-    Epilogue<T> ep = frozen_ep<T>();
-    RPO_TRY(gemm_dispatch<T>(backend, (const T *)hd->hp_t, Dt, (const T *)hd->t_projT, Dt, (T *)hd->text_feat, E, Mp_t,
-                             E, Dt, ep, st));
-    if (hd->overlap) RPO_CHECK_CUDA(cudaEventRecord(hd->ev_join, hd->side));
-  }
   RPO_TRY(im2col_patches<T>(image, image_dtype, (T *)hd->patches, B, c.v_res, c.v_patch, hd->pk_pad, hd->norm, st));
   Epilogue<T> ep = frozen_ep<T>(v.sk_ws);
   const int pk = hd->pk_pad;
@@ -304,66 +309,124 @@ static int forward_impl(RpoHandle *hd, const void *image, int image_dtype, int B
   RPO_TRY(layernorm_fwd<T>(xv_out, hd->w.ln_post_w, hd->w.ln_post_b, (T *)hd->hp_v, Mp_v, Dv, st));
   RPO_TRY(gemm_dispatch<T>(backend, (const T *)hd->hp_v, Dv, (const T *)hd->v_projT, Dv, (T *)hd->img_feat, E, Mp_v, E,
                            Dv, ep, st));
-  if (hd->overlap && run_text) RPO_CHECK_CUDA(cudaStreamWaitEvent(st_main, hd->ev_join, 0));
-  if (run_text) hd->text_feat_valid = true;
-  // ---- logits + CE (:215-230) ----
-  float *lg = logits ? logits : hd->logits_f;
-  RPO_TRY(logits_ce_fwd<T>((const T *)hd->img_feat, (const T *)hd->text_feat, hd->w.logit_scale, label, B, C, K, E,
-                           (T *)hd->img_n, (T *)hd->img_s, (T *)hd->text_n, hd->img_norm, hd->text_norm, (T *)hd->pair,
-                           lg, label ? (loss ? loss : hd->loss_f) : nullptr, hd->dlogits, st));
   hd->B = B;
-  hd->fwd_has_grad = label != nullptr;
   hd->img_prompt = img_prompt;
-  hd->launches_fwd = g_launch_count;
+  hd->have_image = true;
+  hd->fwd_has_grad = false;
+  hd->have_logits_bwd = false;
+  hd->launches[1] = g_launch_count;
+  return RPO_OK;
+}
+
+// logits + CE over all n_cls classes (:215-230)
+template <typename T>
+static int logits_forward_stage(RpoHandle *hd, const int64_t *label, float *logits, float *loss, cudaStream_t st) {
+  const RpoConfig &c = hd->cfg;
+  g_launch_count = 0;
+  float *lg = logits ? logits : hd->logits_f;
+  RPO_TRY(logits_ce_fwd<T>((const T *)hd->img_feat, (const T *)hd->text_feat, hd->w.logit_scale, label, hd->B, c.n_cls,
+                           c.K, c.embed_dim, (T *)hd->img_n, (T *)hd->img_s, (T *)hd->text_n, hd->img_norm,
+                           hd->text_norm, (T *)hd->pair, lg, label ? (loss ? loss : hd->loss_f) : nullptr, hd->dlogits,
+                           st));
+  hd->fwd_has_grad = label != nullptr;
+  hd->have_logits_bwd = false;
+  hd->launches[2] = g_launch_count;
+  return RPO_OK;
+}
+
+// fp16 gradients of this path sit around 1e-5 .. 1e-3, i.e. in the subnormal range of the format: the
+// backward runs on gradients scaled by 2^12 (exact) and the f32 reductions at the end divide it out
+static float grad_prescale(const RpoConfig &c) { return (c.dtype == RPO_F16) ? 4096.0f : 1.0f; }
+
+template <typename T>
+static int logits_backward_stage(RpoHandle *hd, cudaStream_t st) {
+  const RpoConfig &c = hd->cfg;
+  g_launch_count = 0;
+  RPO_TRY(logits_ce_bwd<T>(hd->dlogits, (const T *)hd->img_feat, (const T *)hd->text_feat, (const T *)hd->img_n,
+                           (const T *)hd->img_s, (const T *)hd->text_n, hd->img_norm, hd->text_norm, hd->w.logit_scale,
+                           hd->B, c.n_cls, c.K, c.embed_dim, (T *)hd->dl_t, (T *)hd->d_img_s, (T *)hd->d_text_n,
+                           (T *)hd->d_img_feat, (T *)hd->d_text_feat, grad_prescale(c), st));
+  hd->have_logits_bwd = true;
+  hd->launches[3] = g_launch_count;
+  return RPO_OK;
+}
+
+// text head + text tower backward over the handle's classes
+template <typename T>
+static int text_backward_stage(RpoHandle *hd, float *grad_flat, cudaStream_t st) {
+  const RpoConfig &c = hd->cfg;
+  Tower &t = hd->txt;
+  const int K = c.K, E = c.embed_dim, Dt = c.t_width, Cl = hd->Cl;
+  const long long Mp_t = (long long)Cl * K;
+  g_launch_count = 0;
+  Epilogue<T> ep = frozen_ep<T>();
+  RPO_TRY(gemm_dispatch<T>(c.gemm_backend, (const T *)hd->d_text_feat + (long long)hd->c0 * K * E, E,
+                           (const T *)hd->w.t_proj, E, (T *)t.dh, Dt, Mp_t, Dt, E, ep, st));
+  T *xt_out = at<T>(t.x_in, (long long)t.layers * t.Mtot_max * Dt) + t.Mc * Dt;
+  RPO_TRY(layernorm_bwd<T>((const T *)t.dh, xt_out, hd->w.ln_final_w, nullptr, (T *)t.dx, Mp_t, Dt, st));
+  if (hd->skip != 1) RPO_TRY(tower_backward<T>(hd, t, st));
+  // d text_prompt: the prompt is shared by all classes (trainers/rpo.py:176-177)
+  RPO_TRY(reduce_groups_f32<T>((const T *)t.dx, grad_flat, Cl, K, Dt, 1.0f / grad_prescale(c), st));
+  hd->launches[4] = g_launch_count;
   return RPO_OK;
 }
 
 template <typename T>
-static int backward_impl(RpoHandle *hd, float *grad_flat, cudaStream_t st) {
+static int image_backward_stage(RpoHandle *hd, float *grad_flat, cudaStream_t st) {
   const RpoConfig &c = hd->cfg;
-  Tower &v = hd->vis, &t = hd->txt;
-  const int K = c.K, C = c.n_cls, E = c.embed_dim, Dv = c.v_width, Dt = c.t_width, B = hd->B;
-  const int backend = c.gemm_backend;
+  Tower &v = hd->vis;
+  const int K = c.K, E = c.embed_dim, Dv = c.v_width, Dt = c.t_width, B = hd->B;
+  const long long Mp_v = (long long)B * K;
   g_launch_count = 0;
-  // fp16 gradients of this path sit around 1e-5 .. 1e-3, i.e. in the subnormal range of the format: the
-  // backward runs on gradients scaled by 2^12 (exact) and the f32 reduction at the end divides it out
-  const float gs = (c.dtype == RPO_F16) ? 4096.0f : 1.0f;
-  RPO_TRY(logits_ce_bwd<T>(hd->dlogits, (const T *)hd->img_feat, (const T *)hd->text_feat, (const T *)hd->img_n,
-                           (const T *)hd->img_s, (const T *)hd->text_n, hd->img_norm, hd->text_norm, hd->w.logit_scale,
-                           B, C, K, E, (T *)hd->dl_t, (T *)hd->d_img_s, (T *)hd->d_text_n, (T *)hd->d_img_feat,
-                           (T *)hd->d_text_feat, gs, st));
   Epilogue<T> ep = frozen_ep<T>();
-  const long long Mp_v = (long long)B * K, Mp_t = (long long)C * K;
-  {
-    // text head + text tower backward, on the side stream next to the vision backward
-    cudaStream_t st_main = st;
-    cudaStream_t st = st_main;
-    if (hd->overlap) {
-      RPO_CHECK_CUDA(cudaEventRecord(hd->ev_fork, st_main));
-      RPO_CHECK_CUDA(cudaStreamWaitEvent(hd->side, hd->ev_fork, 0));
-      st = hd->side;
-    }
-    RPO_TRY(gemm_dispatch<T>(backend, (const T *)hd->d_text_feat, E, (const T *)hd->w.t_proj, E, (T *)t.dh, Dt, Mp_t,
-                             Dt, E, ep, st));
-    T *xt_out = at<T>(t.x_in, (long long)t.layers * t.Mtot_max * Dt) + t.Mc * Dt;
-    RPO_TRY(layernorm_bwd<T>((const T *)t.dh, xt_out, hd->w.ln_final_w, nullptr, (T *)t.dx, Mp_t, Dt, st));
-    if (hd->skip != 1) RPO_TRY(tower_backward<T>(hd, t, st));
-    // d text_prompt: the prompt is shared by all classes (trainers/rpo.py:176-177)
-    RPO_TRY(reduce_groups_f32<T>((const T *)t.dx, grad_flat, C, K, Dt, 1.0f / gs, st));
-    if (hd->overlap) RPO_CHECK_CUDA(cudaEventRecord(hd->ev_join, hd->side));
-  }
   // vision head: d ln_post-out = d img_feat . proj^T  (B operand = proj [Dv,E] itself, K-major in E)
-  RPO_TRY(gemm_dispatch<T>(backend, (const T *)hd->d_img_feat, E, (const T *)hd->w.v_proj, E, (T *)v.dh, Dv, Mp_v, Dv,
-                           E, ep, st));
+  RPO_TRY(gemm_dispatch<T>(c.gemm_backend, (const T *)hd->d_img_feat, E, (const T *)hd->w.v_proj, E, (T *)v.dh, Dv,
+                           Mp_v, Dv, E, ep, st));
   T *xv_out = at<T>(v.x_in, (long long)v.layers * v.Mtot_max * Dv) + v.Mc * Dv;
   RPO_TRY(layernorm_bwd<T>((const T *)v.dh, xv_out, hd->w.ln_post_w, nullptr, (T *)v.dx, Mp_v, Dv, st));
   if (hd->skip != 2) RPO_TRY(tower_backward<T>(hd, v, st));
   // d img_prompt: sum over images, then through ln_pre (trainers/rpo.py:204-206)
-  RPO_TRY(reduce_groups_f32<T>((const T *)v.dx, hd->dsum_v, B, K, Dv, 1.0f / gs, st));
+  RPO_TRY(reduce_groups_f32<T>((const T *)v.dx, hd->dsum_v, B, K, Dv, 1.0f / grad_prescale(c), st));
   RPO_TRY(lnpre_prompt_bwd<T>(hd->dsum_v, (const T *)hd->img_prompt, hd->w.ln_pre_w, grad_flat + (size_t)K * Dt, K, Dv,
                               st));
+  hd->launches[5] = g_launch_count;
+  return RPO_OK;
+}
+
+template <typename T>
+static int forward_impl(RpoHandle *hd, const void *image, int image_dtype, int B, const void *text_prompt,
+                        const void *img_prompt, const int64_t *label, float *logits, float *loss, cudaStream_t st) {
+  const bool run_text = text_prompt != nullptr;  // else: cached text features (inference)
+  hd->launches[0] = 0;
+  if (run_text) {
+    // the text tower (C*K prompt rows: short, latency-bound kernels) runs on the side stream next to the vision tower
+    cudaStream_t ts = st;
+    if (hd->overlap) {
+      RPO_CHECK_CUDA(cudaEventRecord(hd->ev_fork, st));
+      RPO_CHECK_CUDA(cudaStreamWaitEvent(hd->side, hd->ev_fork, 0));
+      ts = hd->side;
+    }
+    RPO_TRY(text_forward_stage<T>(hd, text_prompt, ts));
+    if (hd->overlap) RPO_CHECK_CUDA(cudaEventRecord(hd->ev_join, hd->side));
+  }
+  RPO_TRY(image_forward_stage<T>(hd, image, image_dtype, B, img_prompt, st));
+  if (hd->overlap && run_text) RPO_CHECK_CUDA(cudaStreamWaitEvent(st, hd->ev_join, 0));
+  return logits_forward_stage<T>(hd, label, logits, loss, st);
+}
+
+template <typename T>
+static int backward_impl(RpoHandle *hd, float *grad_flat, cudaStream_t st) {
+  RPO_TRY(logits_backward_stage<T>(hd, st));
+  cudaStream_t ts = st;
+  if (hd->overlap) {
+    RPO_CHECK_CUDA(cudaEventRecord(hd->ev_fork, st));
+    RPO_CHECK_CUDA(cudaStreamWaitEvent(hd->side, hd->ev_fork, 0));
+    ts = hd->side;
+  }
+  RPO_TRY(text_backward_stage<T>(hd, grad_flat, ts));
+  if (hd->overlap) RPO_CHECK_CUDA(cudaEventRecord(hd->ev_join, hd->side));
+  RPO_TRY(image_backward_stage<T>(hd, grad_flat, st));
   if (hd->overlap) RPO_CHECK_CUDA(cudaStreamWaitEvent(st, hd->ev_join, 0));
-  hd->launches_bwd = g_launch_count;
   return RPO_OK;
 }
 
@@ -486,8 +549,13 @@ int rpo_create(const RpoConfig *cfg, RpoHandle **out) {
   RPO_REQUIRE(!(c.dtype == RPO_F32 && c.gemm_backend == RPO_GEMM_TCGEN05), "tcgen05 backend needs a 16-bit dtype");
   const int grid = c.v_res / c.v_patch;
   RPO_REQUIRE(grid * grid + 1 <= 320 && c.ctx_len <= 320, "at most 320 context rows per group");
+  const int Cl = c.cls_local > 0 ? c.cls_local : c.n_cls;
+  RPO_REQUIRE(c.cls_local >= 0 && c.cls_first >= 0 && (c.cls_local > 0 || c.cls_first == 0) && c.cls_first + Cl <= c.n_cls,
+              "class shard [cls_first, cls_first + cls_local) must lie inside [0, n_cls)");
   RpoHandle *h = new RpoHandle();
   h->cfg = c;
+  h->c0 = c.cls_first;
+  h->Cl = Cl;
   h->esz = dtype_size(c.dtype);
   h->NP = grid * grid;
   h->S = h->NP + 1;
@@ -499,9 +567,10 @@ int rpo_create(const RpoConfig *cfg, RpoHandle **out) {
   v.Gmax = c.max_batch; v.max_ctx = h->S; v.uniform_n = h->S;
   v.Mc_max = (long long)c.max_batch * h->S; v.Mp_max = (long long)c.max_batch * c.K; v.Mtot_max = v.Mc_max + v.Mp_max;
   t.D = c.t_width; t.H = c.t_heads; t.layers = c.t_layers; t.K = c.K; t.causal = 1;
-  t.Gmax = c.n_cls; t.G = c.n_cls; t.max_ctx = c.ctx_len;
-  t.Mc_max = (long long)c.n_cls * (c.ctx_len - c.K > 0 ? c.ctx_len - c.K : 1);
-  t.Mp_max = (long long)c.n_cls * c.K; t.Mtot_max = t.Mc_max + t.Mp_max;
+  // the text tower covers the handle's class shard only; logits / CE below span all n_cls classes
+  t.Gmax = Cl; t.G = Cl; t.max_ctx = c.ctx_len;
+  t.Mc_max = (long long)Cl * (c.ctx_len - c.K > 0 ? c.ctx_len - c.K : 1);
+  t.Mp_max = (long long)Cl * c.K; t.Mtot_max = t.Mc_max + t.Mp_max;
 
   const size_t e = h->esz;
   const long long Bm = c.max_batch, K = c.K, C = c.n_cls, E = c.embed_dim;
@@ -649,9 +718,10 @@ int rpo_set_classes(RpoHandle *h, const void *text_x, const int32_t *len_prompts
   RPO_REQUIRE(h->bound, "rpo_bind_weights must be called first");
   const RpoConfig &c = h->cfg;
   Tower &t = h->txt;
-  std::vector<int> off(c.n_cls + 1, 0), rc, rp;
+  const int Cl = h->Cl;  // the handle's class shard (all n_cls classes unless RpoConfig.cls_local says otherwise)
+  std::vector<int> off(Cl + 1, 0), rc, rp;
   int mx = 0;
-  for (int i = 0; i < c.n_cls; ++i) {
+  for (int i = 0; i < Cl; ++i) {
     int n = len_prompts[i];
     // the reference indexes position len_prompts+K-1 of a 77-token sequence (trainers/rpo.py:177)
     RPO_REQUIRE(n >= 1 && n + c.K <= c.ctx_len, "len_prompts[c] + K must fit in the context length");
@@ -662,9 +732,9 @@ int rpo_set_classes(RpoHandle *h, const void *text_x, const int32_t *len_prompts
       rp.push_back(j);
     }
   }
-  t.Mc = off[c.n_cls];
+  t.Mc = off[Cl];
   t.max_ctx = mx;
-  t.G = c.n_cls;
+  t.G = Cl;
   RPO_REQUIRE(t.Mc <= t.Mc_max, "internal: context rows exceed the workspace");
   cudaStream_t st = (cudaStream_t)stream;
   RPO_CHECK_CUDA(cudaMemcpyAsync(t.ctx_off, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice, st));
@@ -690,6 +760,8 @@ int rpo_forward(RpoHandle *h, const void *image, int32_t image_dtype, int32_t B,
               "text_prompt may only be NULL for inference after a call that computed the text features");
   RPO_REQUIRE(B >= 1 && B <= h->cfg.max_batch, "batch size exceeds max_batch");
   RPO_REQUIRE(!loss || label, "loss requires labels");
+  RPO_REQUIRE(h->Cl == h->cfg.n_cls || !text_prompt,
+              "a class-sharded handle computes its text features through the stage entry points (rpo_forward_text + all-gather)");
   cudaStream_t st = (cudaStream_t)stream;
   switch (h->cfg.dtype) {
     case RPO_F32: return forward_impl<float>(h, image, image_dtype, B, text_prompt, img_prompt, label, logits, loss, st);
@@ -711,6 +783,8 @@ int rpo_set_image_norm(RpoHandle *h, const float mean[3], const float std[3]) {
 int rpo_backward(RpoHandle *h, float *grad_flat, void *stream) {
   RPO_REQUIRE(h && grad_flat, "null argument");
   RPO_REQUIRE(h->fwd_has_grad, "rpo_backward must follow an rpo_forward that was given labels");
+  RPO_REQUIRE(h->Cl == h->cfg.n_cls,
+              "a class-sharded handle runs its backward through the stage entry points (reduce-scatter in between)");
   cudaStream_t st = (cudaStream_t)stream;
   switch (h->cfg.dtype) {
     case RPO_F32: return backward_impl<float>(h, grad_flat, st);
@@ -719,7 +793,70 @@ int rpo_backward(RpoHandle *h, float *grad_flat, void *stream) {
   }
 }
 
-int64_t rpo_launch_count(const RpoHandle *h) { return h ? h->launches_fwd + h->launches_bwd : 0; }
+// ---- stage entry points ---------------------------------------------------------------------------
+#define STAGE(CALL)                                                          \
+  switch (h->cfg.dtype) {                                                    \
+    case RPO_F32: { using T = float; return CALL; }                          \
+    case RPO_F16: { using T = __half; return CALL; }                         \
+    default: { using T = __nv_bfloat16; return CALL; }                       \
+  }
+
+int rpo_bind_text_exchange(RpoHandle *h, void *text_feat, void *d_text_feat) {
+  RPO_REQUIRE(h && text_feat && d_text_feat, "null argument");
+  h->text_feat = (char *)text_feat;
+  h->d_text_feat = (char *)d_text_feat;
+  h->text_feat_valid = false;
+  h->fwd_has_grad = false;
+  h->have_logits_bwd = false;
+  return RPO_OK;
+}
+
+int rpo_forward_text(RpoHandle *h, const void *text_prompt, void *stream) {
+  RPO_REQUIRE(h && text_prompt, "null argument");
+  RPO_REQUIRE(h->bound && h->classes_set, "rpo_bind_weights and rpo_set_classes must be called first");
+  STAGE(text_forward_stage<T>(h, text_prompt, (cudaStream_t)stream));
+}
+
+int rpo_forward_image(RpoHandle *h, const void *image, int32_t image_dtype, int32_t B, const void *img_prompt,
+                      void *stream) {
+  RPO_REQUIRE(h && image && img_prompt, "null argument");
+  RPO_REQUIRE(h->bound, "rpo_bind_weights must be called first");
+  RPO_REQUIRE(B >= 1 && B <= h->cfg.max_batch, "batch size exceeds max_batch");
+  STAGE(image_forward_stage<T>(h, image, image_dtype, B, img_prompt, (cudaStream_t)stream));
+}
+
+int rpo_forward_logits(RpoHandle *h, const int64_t *label, float *logits, float *loss, void *stream) {
+  RPO_REQUIRE(h, "null argument");
+  RPO_REQUIRE(h->have_image && h->text_feat_valid, "rpo_forward_logits needs image and text features");
+  RPO_REQUIRE(!loss || label, "loss requires labels");
+  STAGE(logits_forward_stage<T>(h, label, logits, loss, (cudaStream_t)stream));
+}
+
+int rpo_backward_logits(RpoHandle *h, void *stream) {
+  RPO_REQUIRE(h, "null argument");
+  RPO_REQUIRE(h->fwd_has_grad, "rpo_backward_logits must follow an rpo_forward_logits that was given labels");
+  STAGE(logits_backward_stage<T>(h, (cudaStream_t)stream));
+}
+
+int rpo_backward_text(RpoHandle *h, float *grad_flat, void *stream) {
+  RPO_REQUIRE(h && grad_flat, "null argument");
+  RPO_REQUIRE(h->have_logits_bwd, "rpo_backward_text must follow rpo_backward_logits");
+  STAGE(text_backward_stage<T>(h, grad_flat, (cudaStream_t)stream));
+}
+
+int rpo_backward_image(RpoHandle *h, float *grad_flat, void *stream) {
+  RPO_REQUIRE(h && grad_flat, "null argument");
+  RPO_REQUIRE(h->have_logits_bwd, "rpo_backward_image must follow rpo_backward_logits");
+  STAGE(image_backward_stage<T>(h, grad_flat, (cudaStream_t)stream));
+}
+#undef STAGE
+
+int64_t rpo_launch_count(const RpoHandle *h) {
+  if (!h) return 0;
+  int64_t n = 0;
+  for (int64_t v : h->launches) n += v;
+  return n;
+}
 
 int rpo_profile_begin(void *stream) {
   for (ProfEntry &e : g_prof) cudaEventDestroy(e.ev);

@@ -20,18 +20,28 @@ class Engine:
     `forward` / `backward` only enqueue kernels on the current stream (graph-capturable)."""
 
     def __init__(self, arch, K, n_cls, dtype, max_batch, w_mm, w_f32, index, text_x, len_prompts,
-                 gemm_backend=_lib.GEMM_AUTO):
+                 gemm_backend=_lib.GEMM_AUTO, shard=None, group=None):
+        """`shard` (text_shard.ClassShard): this handle's text tower covers shard.slice of the classes only;
+        `forward` / `backward` then run the native stages with the all-gather / reduce-scatter of
+        text_shard.TextExchange in between (`group`: the torch.distributed process group)."""
         self.lib = _lib.load()
         self.device = w_mm.device
         if self.device.type != "cuda":
             raise _lib.RpoError("rpo_b200 runs on CUDA devices only (no CPU fallback)")
         self.arch, self.K, self.C, self.dtype, self.max_batch = arch, K, n_cls, dtype, max_batch
+        self.shard, self.exchange = shard, None
+        if shard is not None:
+            if shard.n_cls != n_cls:
+                raise _lib.RpoError(f"{shard} does not partition {n_cls} classes")
+            text_x = text_x[shard.slice].contiguous()
+            len_prompts = len_prompts[shard.slice]
         self.w_mm, self.w_f32, self.text_x = w_mm, w_f32, text_x  # keep alive: the handle holds raw pointers
         cfg = _lib.RpoConfig(
             dtype=_lib.dtype_code(dtype), K=K, n_cls=n_cls, ctx_len=arch.ctx_len, embed_dim=arch.embed_dim,
             v_width=arch.v_width, v_layers=arch.v_layers, v_heads=arch.v_heads, v_patch=arch.v_patch,
             v_res=arch.v_res, t_width=arch.t_width, t_layers=arch.t_layers, t_heads=arch.t_heads,
-            max_batch=max_batch, gemm_backend=gemm_backend)
+            max_batch=max_batch, gemm_backend=gemm_backend,
+            cls_first=shard.first if shard is not None else 0, cls_local=shard.local if shard is not None else 0)
         self.handle = C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.rpo_create(C.byref(cfg), C.byref(self.handle)))
@@ -57,8 +67,13 @@ class Engine:
                 setattr(w, field, addr(key))
             st = _lib.stream_ptr(self.device)
             _lib.check(self.lib.rpo_bind_weights(self.handle, C.byref(w), st))
-            lp = (C.c_int32 * n_cls)(*[int(v) for v in len_prompts])
+            lp = (C.c_int32 * len(len_prompts))(*[int(v) for v in len_prompts])
             _lib.check(self.lib.rpo_set_classes(self.handle, _lib.ptr(text_x), lp, st))
+            if shard is not None:
+                from .text_shard import TextExchange
+                self.exchange = TextExchange(shard, K, arch.embed_dim, dtype, self.device, group)
+                _lib.check(self.lib.rpo_bind_text_exchange(self.handle, _lib.ptr(self.exchange.text_feat),
+                                                           _lib.ptr(self.exchange.d_text_feat)))
         Dt, Dv = arch.t_width, arch.v_width
         self.n_text = K * Dt
         self.grad_flat = torch.zeros(K * Dt + K * Dv, dtype=torch.float32, device=self.device)
@@ -110,6 +125,14 @@ class Engine:
             raise _lib.RpoError("label must be int64 [B] on the engine device")
         image = image.contiguous()
         logits = self.logits[:B] if (want_logits or label is None) else None
+        if self.exchange is not None:
+            # class-sharded text tower: native stages with the text-feature all-gather in between
+            if text_prompt is not None:
+                self.text_forward(text_prompt)
+                self.exchange.gather_text_features()
+            self.image_forward(image, idt, img_prompt)
+            self.logits_forward(label, logits)
+            return (self.loss if label is not None else None), logits
         with torch.cuda.device(self.device):
             _lib.check(self.lib.rpo_forward(
                 self.handle, _lib.ptr(image), idt, B,
@@ -125,8 +148,41 @@ class Engine:
         sd = (ctypes.c_float * 3)(*[float(x) for x in std])
         _lib.check(self.lib.rpo_set_image_norm(self.handle, m, sd))
 
+    # -- native stages (include/rpo_b200.h "stage entry points"); arguments are validated by `forward` -----
+    def _stage(self, fn, *args):
+        with torch.cuda.device(self.device):
+            _lib.check(fn(self.handle, *args, _lib.stream_ptr(self.device)))
+
+    def text_forward(self, text_prompt):
+        self._stage(self.lib.rpo_forward_text, _lib.ptr(text_prompt.detach().contiguous()))
+
+    def image_forward(self, image, image_dtype_code, img_prompt):
+        self._stage(self.lib.rpo_forward_image, _lib.ptr(image), image_dtype_code, image.shape[0],
+                    _lib.ptr(img_prompt.detach().contiguous()))
+
+    def logits_forward(self, label, logits):
+        self._stage(self.lib.rpo_forward_logits, _lib.ptr(label), _lib.ptr(logits),
+                    _lib.ptr(self.loss) if label is not None else None)
+
+    def logits_backward(self):
+        self._stage(self.lib.rpo_backward_logits)
+
+    def text_backward(self):
+        self._stage(self.lib.rpo_backward_text, _lib.ptr(self.grad_flat))
+
+    def image_backward(self):
+        self._stage(self.lib.rpo_backward_image, _lib.ptr(self.grad_flat))
+
     def backward(self):
-        """Enqueues the prompt-gradient pass; returns the flat f32 gradient [K*Dt + K*Dv]."""
+        """Enqueues the prompt-gradient pass; returns the flat f32 gradient [K*Dt + K*Dv].
+        With a class shard the text half is the sum over this rank's classes of the gradient of the
+        ranks' SUMMED losses, the image half this rank's images: all-reduce (sum), then scale by 1/world."""
+        if self.exchange is not None:
+            self.logits_backward()
+            self.exchange.scatter_text_grads()
+            self.text_backward()
+            self.image_backward()
+            return self.grad_flat
         with torch.cuda.device(self.device):
             _lib.check(self.lib.rpo_backward(self.handle, _lib.ptr(self.grad_flat), _lib.stream_ptr(self.device)))
         return self.grad_flat
@@ -239,8 +295,25 @@ class CustomCLIP(nn.Module):
         self.register_buffer("w_mm", w_mm, persistent=False)
         self.register_buffer("w_f32", w_f32, persistent=False)
         self._engine = None
+        self._shard, self._group = None, None
         self._text_key = None     # (engine, prompt storage, prompt version, epoch) of the cached text features
         self._prompt_epoch = 0    # bumped by whatever changes the prompts behind autograd's back (fused SGD step)
+
+    def shard_text(self, rank=None, world=None, group=None):
+        """Class-sharded text tower for data-parallel training: this rank runs the text
+        tower for its ceil(n_cls / world) classes only; text features are all-gathered, their gradient
+        reduce-scattered (rpo_b200/text_shard.py).  rank / world default to the torch.distributed group.
+        The prompt gradients the backward leaves behind are per-rank partial sums: average them over the
+        group as for plain data parallelism (trainer.allreduce_mean_ / StepRunner do)."""
+        from .text_shard import ClassShard
+        if rank is None or world is None:
+            import torch.distributed as dist
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
+        self._shard = ClassShard(self.text_x.shape[0], rank, world)
+        self._group = group
+        self._engine = None
+        self._text_key = None
+        return self._shard
 
     def invalidate_text_features(self):
         self._prompt_epoch += 1
@@ -273,7 +346,7 @@ class CustomCLIP(nn.Module):
         if eng is None or eng.device != self.w_mm.device or eng.max_batch < need:
             self._engine = None
             eng = Engine(self.arch, self.K, self.text_x.shape[0], self.dtype, need, self.w_mm, self.w_f32,
-                         self._index, self.text_x, self.len_prompts, self.gemm_backend)
+                         self._index, self.text_x, self.len_prompts, self.gemm_backend, self._shard, self._group)
             self._engine = eng
         return eng
 

@@ -3,6 +3,11 @@
 graph: forward + CE + prompt-gradient backward (librpo_b200), an NCCL all-reduce of the flat
 [K*Dt + K*Dv] f32 gradient when data-parallel, and the fused SGD update of the two prompt tensors.
 
+With a class-sharded text tower (`model.shard_text(...)`) the step is five graph
+segments -- text forward | image forward | logits forward+backward | text backward | image backward --
+with the text segments and their two collectives (all-gather of the text features, reduce-scatter of
+their gradient) on a side stream next to the vision tower.
+
 Used by bench.py and by rpo_b200.trainer.RPO.forward_backward.  Host code is plumbing only.
 """
 import torch
@@ -32,6 +37,9 @@ class StepRunner:
         self.graph = None
         self.use_graph = use_graph
         self.launches_per_step = 0
+        self.sharded = self.eng.exchange is not None
+        self.side = torch.cuda.Stream(self.device) if self.sharded else None
+        self.segments = None
 
     # -- enqueue helpers (no host sync) ----------------------------------------------------------
     def _fwd_bwd(self):
@@ -59,6 +67,40 @@ class StepRunner:
         self._fwd_bwd()
         self._update()
 
+    # -- class-sharded text tower: stage segments -------------------------------------------------
+    def _segment_fns(self):
+        eng, pl = self.eng, self.model.prompt_learner
+        idt = _lib.RPO_U8 if self.image.dtype == torch.uint8 else _lib.dtype_code(self.image.dtype)
+
+        def logits():
+            eng.logits_forward(self.label, None)
+            eng.logits_backward()
+
+        return {"text_fwd": lambda: eng.text_forward(pl.text_prompt.data),
+                "image_fwd": lambda: eng.image_forward(self.image, idt, pl.img_prompt.data),
+                "logits": logits, "text_bwd": eng.text_backward, "image_bwd": eng.image_backward}
+
+    def _run(self, name):
+        seg = self.segments[name]
+        seg.replay() if isinstance(seg, torch.cuda.CUDAGraph) else seg()
+
+    def _sharded_fwd_bwd(self):
+        """text stages + collectives on the side stream, vision stages on the current stream"""
+        ex, main, side = self.eng.exchange, torch.cuda.current_stream(self.device), self.side
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            self._run("text_fwd")
+            ex.gather_text_features()
+        self._run("image_fwd")
+        main.wait_stream(side)
+        self._run("logits")
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            ex.scatter_text_grads()
+            self._run("text_bwd")
+        self._run("image_bwd")
+        main.wait_stream(side)
+
     def prepare(self, warmup=3):
         """Warm-up (sets kernel attributes, loads modules) and CUDA-graph capture of the step."""
         with torch.cuda.device(self.device):
@@ -70,7 +112,16 @@ class StepRunner:
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
             self.launches_per_step = self.eng.launch_count() + 2  # + two SGD kernels
-            if self.use_graph:
+            if self.sharded:
+                self.segments = self._segment_fns()
+                if self.use_graph:
+                    for name, fn in list(self.segments.items()):
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            fn()
+                        self.segments[name] = g
+                torch.cuda.synchronize()
+            elif self.use_graph:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     if self.world > 1:
@@ -83,7 +134,10 @@ class StepRunner:
     def step(self):
         """Enqueues one step on the current stream.  Inputs are whatever self.image / self.label hold."""
         self.model.invalidate_text_features()  # the fused SGD kernel rewrites the prompts in place
-        if self.graph is not None:
+        if self.sharded:
+            self._sharded_fwd_bwd()
+            self._update()
+        elif self.graph is not None:
             self.graph.replay()
             if self.world > 1:
                 self._update()
