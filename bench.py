@@ -325,11 +325,12 @@ def main_own(args):
                        tokens=synthetic_tokens(C), max_batch=B).to(dev)
     model.prompt_learner.train()
     pg = dist.group.WORLD if world > 1 else None
-    shard_text = world > 1 and args.shard_text
+    shard_text = world > 1 and not args.no_shard_text
+    pipeline = not args.no_pipeline
     if shard_text:
         model.shard_text(rank, world, pg)  # each rank runs ceil(C / world) class prompts
     runner = StepRunner(model, B, lr=0.01, momentum=0.9, weight_decay=5e-4, use_graph=not args.no_graph,
-                        process_group=pg, world_size=world)
+                        process_group=pg, world_size=world, pipeline=pipeline)
 
     # inputs: a pool of distinct batches larger than L2 (8 x 19.3 MB), different per rank
     pool_n = 8
@@ -433,7 +434,11 @@ def main_own(args):
                 **WORKLOAD, "global_batch": B * world, "parallelism": f"dp{world}",
                 "l2_policy": "inputs rotate through 8 distinct batches (154 MB > 126 MB L2); a step touches ~1.5 GB "
                              "of activations",
-                "cuda_graph": runner.graph is not None or (runner.segments is not None and not args.no_graph),
+                "cuda_graph": not args.no_graph,
+                "pipeline": ("context rows (cls + patches: independent of the prompts) of batch i+1 run on a second "
+                             "stream beside the prompt-row chain / backward / SGD of batch i; one batch in flight, every "
+                             "timed step completes one batch; same trajectory as the sequential step") if pipeline
+                else "none: each step runs one batch start to end",
                 "text_tower": (f"class-sharded over {world} ranks (all-gather of text features + reduce-scatter of "
                                f"their gradient)") if shard_text else "replicated on every rank (as the reference)",
             },
@@ -473,8 +478,11 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--shard-text", action="store_true",
-                    help="N > 1: class-shard the text tower over the ranks (default: replicated, as the reference)")
+    ap.add_argument("--no-shard-text", action="store_true",
+                    help="N > 1: run every class prompt on every rank (as the reference) instead of class-sharding "
+                         "the text tower over the ranks")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="do not overlap the context rows of the next batch with the prompt-row chain of the current one")
     a = ap.parse_args()
     if a.impl == "reference":
         main_reference(a)

@@ -61,7 +61,10 @@ typedef struct {
    * with an all-gather of the text features and a reduce-scatter of their gradient in between.  Logits, loss and
    * the image side always span all n_cls classes. */
   int32_t cls_first, cls_local;
-  int32_t reserved[1];
+  /* 2: the handle keeps two sets of vision-tower activations so that the context rows of the NEXT batch
+   * (rpo_forward_image_context, slot s) can be computed while the prompt rows and the backward of the current batch
+   * (rpo_forward_image_prompts, other slot) are still in flight.  0 / 1: one set. */
+  int32_t image_slots;
 } RpoConfig;
 
 /* One ResidualAttentionBlock (clip/model.py:167-191).  ln_* are f32 [D]; the rest are `dtype`:
@@ -149,6 +152,17 @@ int rpo_forward_text(RpoHandle *h, const void *text_prompt, void *stream);
 /* trainers/rpo.py:198-211: patch embedding, prompt concat, ln_pre, vision tower, ln_post, projection */
 int rpo_forward_image(RpoHandle *h, const void *image, int32_t image_dtype, int32_t B, const void *img_prompt,
                       void *stream);
+/* rpo_forward_image in two passes.  The context rows (cls + patch tokens) of the vision tower depend on the image
+ * and the frozen weights only -- visual_mask (trainers/rpo.py:155-156) hides the prompt columns from every row --
+ * so they can be computed before this step's prompts exist, e.g. while the previous batch's prompt rows, backward
+ * and SGD update are still running on another stream.  _context: patch embedding, ln_pre and all blocks over the
+ * B*S context rows of `slot` (their per-layer q|k|v stay in the slot).  _prompts: the B*K prompt rows of the slot
+ * (queries only), ln_post, projection; makes `slot` the one rpo_forward_logits / rpo_backward_image refer to.
+ * slot < RpoConfig.image_slots.  Results equal rpo_forward_image's up to the rounding of the attention kernels
+ * (prompt rows go through the mma.sync kernel here, the tcgen05 one there). */
+int rpo_forward_image_context(RpoHandle *h, const void *image, int32_t image_dtype, int32_t B, int32_t slot,
+                              void *stream);
+int rpo_forward_image_prompts(RpoHandle *h, const void *img_prompt, int32_t slot, void *stream);
 /* trainers/rpo.py:215-230: normalise, K-pair logits, cross-entropy (same argument rules as rpo_forward) */
 int rpo_forward_logits(RpoHandle *h, const int64_t *label, float *logits, float *loss, void *stream);
 /* d loss / d img_feat and d loss / d text_feat (all n_cls classes, this rank's images) */

@@ -22,15 +22,14 @@ SYMBOLS = [
     "rpo_gemm_bias_act", "rpo_gemm_bias_act_ws", "rpo_gemm_workspace_bytes", "rpo_ro_attention_fwd", "rpo_ro_attention_fwd_dense", "rpo_ro_attention_bwd", "rpo_logits_ce_fwd", "rpo_logits_ce_bwd",
     "rpo_debug_fetch", "rpo_launch_count", "rpo_profile_begin", "rpo_profile_end",
     "rpo_bind_text_exchange", "rpo_forward_text", "rpo_forward_image", "rpo_forward_logits", "rpo_backward_logits",
-    "rpo_backward_text", "rpo_backward_image",
+    "rpo_backward_text", "rpo_backward_image", "rpo_forward_image_context", "rpo_forward_image_prompts",
 ]
 
 
 class RpoConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "dtype", "K", "n_cls", "ctx_len", "embed_dim", "v_width", "v_layers", "v_heads", "v_patch", "v_res",
-        "t_width", "t_layers", "t_heads", "max_batch", "gemm_backend", "cls_first", "cls_local")] + \
-        [("reserved", C.c_int32 * 1)]
+        "t_width", "t_layers", "t_heads", "max_batch", "gemm_backend", "cls_first", "cls_local", "image_slots")]
 
 
 class RpoBlockWeights(C.Structure):
@@ -78,6 +77,8 @@ def load():
     lib.rpo_forward_text.argtypes = [vp, vp, vp]
     lib.rpo_forward_image.argtypes = [vp, vp, i32, i32, vp, vp]
     lib.rpo_forward_logits.argtypes = [vp, vp, vp, vp, vp]
+    lib.rpo_forward_image_context.argtypes = [vp, vp, i32, i32, i32, vp]
+    lib.rpo_forward_image_prompts.argtypes = [vp, vp, i32, vp]
     lib.rpo_backward_logits.argtypes = [vp, vp]
     lib.rpo_backward_text.argtypes = [vp, vp, vp]
     lib.rpo_backward_image.argtypes = [vp, vp, vp]

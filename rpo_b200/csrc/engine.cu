@@ -101,6 +101,12 @@ struct RpoHandle {
   int pk = 0, pk_pad = 0;  // 3*p*p and its zero-padded extent
   const void *conv_w_eff = nullptr;  // conv weight as [Dv, pk_pad]
   Tower vis, txt;
+  // Second set of vision-tower activations (RpoConfig.image_slots == 2): the context rows of the NEXT batch are
+  // computed into one slot (rpo_forward_image_context) while the prompt rows / backward of the current batch use the
+  // other -- context rows never depend on the prompts (trainers/rpo.py:155-156 masks the prompt columns).
+  Tower vis2;
+  Tower *vcur = &vis;  // the slot the last image forward used: what the logits / backward stages refer to
+  int slots = 1;
   Arena arena;
   size_t device_bytes = 0;
   std::vector<void *> owned;  // separately cudaMalloc'ed blocks
@@ -113,6 +119,7 @@ struct RpoHandle {
   bool have_image = false, have_logits_bwd = false;
   // vision front end
   char *patches = nullptr, *patch_emb = nullptr, *x_raw = nullptr;
+  char *x_raw_p = nullptr;  // prompt rows before ln_pre (split image forward)
   // heads
   char *hp_v = nullptr, *hp_t = nullptr, *img_feat = nullptr, *text_feat = nullptr;
   char *v_projT = nullptr, *t_projT = nullptr;
@@ -124,7 +131,9 @@ struct RpoHandle {
   // text context gather maps
   int *row_cls = nullptr, *row_pos = nullptr;
   const void *img_prompt = nullptr;  // from the last forward (needed by the ln_pre backward)
-  int64_t launches[6] = {0, 0, 0, 0, 0, 0};  // per stage: text / image / logits forward, logits / text / image backward
+  // per stage: text / image (prompt rows or the whole tower) / logits forward, logits / text / image backward,
+  // image context rows
+  int64_t launches[7] = {0, 0, 0, 0, 0, 0, 0};
   // The text tower (C*K prompt rows: many short, latency-bound kernels) runs on a side stream next to
   // the vision tower, fork/joined with events so that the pair stays capturable into one CUDA graph.
   cudaStream_t side = nullptr;
@@ -196,9 +205,10 @@ static int tower_forward(RpoHandle *hd, Tower &tw, bool do_ctx, bool do_prompt, 
       ep.bias = (const T *)bw.in_b;
       RPO_TRY(gemm_dispatch<T>(backend, h + Mc * D, D, (const T *)bw.in_w, D, qp, D, Mp, D, D, ep, st));
     }
-    if (do_ctx && do_prompt && tw.uniform_n > 0 && !tw.causal &&
-        ro_attention_fwd_dense_supported(Num<T>::dtype, tw.uniform_n, tw.K, tw.H))
-      RPO_TRY(ro_attention_fwd_dense<T>(qkv, qp, o, o + Mc * D, tw.G, tw.uniform_n, tw.K, tw.H, st));
+    const int Kq = do_prompt ? tw.K : 0;  // prompt queries in this pass
+    if (do_ctx && tw.uniform_n > 0 && !tw.causal &&
+        ro_attention_fwd_dense_supported(Num<T>::dtype, tw.uniform_n, Kq, tw.H))
+      RPO_TRY(ro_attention_fwd_dense<T>(qkv, qp, o, o + Mc * D, tw.G, tw.uniform_n, Kq, tw.H, st));
     else
       RPO_TRY(ro_attention_fwd<T>(qkv, qp, o, o + Mc * D, tw.ctx_off, tw.G, do_prompt ? tw.K : 0, tw.H, tw.max_ctx,
                                   tw.causal, do_ctx ? 1 : 0, st));
@@ -282,7 +292,7 @@ static int text_forward_stage(RpoHandle *hd, const void *text_prompt, cudaStream
   return RPO_OK;
 }
 
-// vision front end and tower (trainers/rpo.py:198-211)
+// vision front end and tower (trainers/rpo.py:198-211), context and prompt rows in one pass
 template <typename T>
 static int image_forward_stage(RpoHandle *hd, const void *image, int image_dtype, int B, const void *img_prompt,
                                cudaStream_t st) {
@@ -309,6 +319,58 @@ static int image_forward_stage(RpoHandle *hd, const void *image, int image_dtype
   RPO_TRY(layernorm_fwd<T>(xv_out, hd->w.ln_post_w, hd->w.ln_post_b, (T *)hd->hp_v, Mp_v, Dv, st));
   RPO_TRY(gemm_dispatch<T>(backend, (const T *)hd->hp_v, Dv, (const T *)hd->v_projT, Dv, (T *)hd->img_feat, E, Mp_v, E,
                            Dv, ep, st));
+  hd->vcur = &v;
+  hd->B = B;
+  hd->img_prompt = img_prompt;
+  hd->have_image = true;
+  hd->fwd_has_grad = false;
+  hd->have_logits_bwd = false;
+  hd->launches[1] = g_launch_count;
+  hd->launches[6] = 0;
+  return RPO_OK;
+}
+
+// The same tower in two passes.  Context rows (cls + patches) depend on the image and the frozen weights only:
+// patch embedding, ln_pre and all blocks over the B*S context rows, leaving their per-layer q|k|v in the slot.
+template <typename T>
+static int image_context_stage(RpoHandle *hd, Tower &v, const void *image, int image_dtype, int B, cudaStream_t st) {
+  const RpoConfig &c = hd->cfg;
+  const int Dv = c.v_width, S = hd->S;
+  g_launch_count = 0;
+  v.G = B;
+  v.Mc = (long long)B * S;
+  RPO_TRY(im2col_patches<T>(image, image_dtype, (T *)hd->patches, B, c.v_res, c.v_patch, hd->pk_pad, hd->norm, st));
+  Epilogue<T> ep = frozen_ep<T>(v.sk_ws);
+  const int pk = hd->pk_pad;
+  RPO_TRY(gemm_dispatch<T>(c.gemm_backend, (const T *)hd->patches, pk, (const T *)hd->conv_w_eff, pk,
+                           (T *)hd->patch_emb, Dv, (long long)B * hd->NP, Dv, pk, ep, st));
+  T *x_raw = (T *)hd->x_raw;
+  RPO_TRY(vision_assemble_lnpre<T>((const T *)hd->patch_emb, hd->w.cls_emb, hd->w.v_pos, nullptr, nullptr,
+                                   (const T *)nullptr, x_raw, (T *)nullptr, B, S, 0, Dv, st));
+  RPO_TRY(layernorm_fwd<T>(x_raw, hd->w.ln_pre_w, hd->w.ln_pre_b, (T *)v.x_in, v.Mc, Dv, st));
+  if (hd->skip != 2) RPO_TRY(tower_forward<T>(hd, v, true, false, st));
+  hd->launches[6] = g_launch_count;
+  return RPO_OK;
+}
+
+// ... and the K prompt rows of every image of the slot (queries only; they read the slot's context keys / values):
+// prompt concat (no positional embedding, trainers/rpo.py:204), ln_pre, all blocks, ln_post, projection.
+template <typename T>
+static int image_prompt_stage(RpoHandle *hd, Tower &v, const void *img_prompt, cudaStream_t st) {
+  const RpoConfig &c = hd->cfg;
+  const int K = c.K, E = c.embed_dim, Dv = c.v_width, B = v.G;
+  const long long Mp_v = (long long)B * K;
+  g_launch_count = 0;
+  RPO_TRY(broadcast_rows<T>((const T *)img_prompt, (T *)hd->x_raw_p, B, K, Dv, st));
+  RPO_TRY(layernorm_fwd<T>((const T *)hd->x_raw_p, hd->w.ln_pre_w, hd->w.ln_pre_b, (T *)v.x_in + v.Mc * Dv, Mp_v, Dv,
+                           st));
+  if (hd->skip != 2) RPO_TRY(tower_forward<T>(hd, v, false, true, st));
+  T *xv_out = at<T>(v.x_in, (long long)v.layers * v.Mtot_max * Dv) + v.Mc * Dv;
+  RPO_TRY(layernorm_fwd<T>(xv_out, hd->w.ln_post_w, hd->w.ln_post_b, (T *)hd->hp_v, Mp_v, Dv, st));
+  Epilogue<T> ep = frozen_ep<T>();
+  RPO_TRY(gemm_dispatch<T>(c.gemm_backend, (const T *)hd->hp_v, Dv, (const T *)hd->v_projT, Dv, (T *)hd->img_feat, E,
+                           Mp_v, E, Dv, ep, st));
+  hd->vcur = &v;
   hd->B = B;
   hd->img_prompt = img_prompt;
   hd->have_image = true;
@@ -374,7 +436,7 @@ static int text_backward_stage(RpoHandle *hd, float *grad_flat, cudaStream_t st)
 template <typename T>
 static int image_backward_stage(RpoHandle *hd, float *grad_flat, cudaStream_t st) {
   const RpoConfig &c = hd->cfg;
-  Tower &v = hd->vis;
+  Tower &v = *hd->vcur;
   const int K = c.K, E = c.embed_dim, Dv = c.v_width, Dt = c.t_width, B = hd->B;
   const long long Mp_v = (long long)B * K;
   g_launch_count = 0;
@@ -552,10 +614,12 @@ int rpo_create(const RpoConfig *cfg, RpoHandle **out) {
   const int Cl = c.cls_local > 0 ? c.cls_local : c.n_cls;
   RPO_REQUIRE(c.cls_local >= 0 && c.cls_first >= 0 && (c.cls_local > 0 || c.cls_first == 0) && c.cls_first + Cl <= c.n_cls,
               "class shard [cls_first, cls_first + cls_local) must lie inside [0, n_cls)");
+  RPO_REQUIRE(c.image_slots >= 0 && c.image_slots <= 2, "image_slots must be 0, 1 or 2");
   RpoHandle *h = new RpoHandle();
   h->cfg = c;
   h->c0 = c.cls_first;
   h->Cl = Cl;
+  h->slots = c.image_slots == 2 ? 2 : 1;
   h->esz = dtype_size(c.dtype);
   h->NP = grid * grid;
   h->S = h->NP + 1;
@@ -575,8 +639,8 @@ int rpo_create(const RpoConfig *cfg, RpoHandle **out) {
   const size_t e = h->esz;
   const long long Bm = c.max_batch, K = c.K, C = c.n_cls, E = c.embed_dim;
   const long long pk = h->pk_pad;
-  size_t total = tower_bytes(v, e) + tower_bytes(t, e);
-  total += e * (Bm * h->NP * pk + Bm * h->NP * v.D + v.Mtot_max * v.D);                 // patches, patch_emb, x_raw
+  size_t total = tower_bytes(v, e) * h->slots + tower_bytes(t, e);
+  total += e * (Bm * h->NP * pk + Bm * h->NP * v.D + v.Mtot_max * v.D + v.Mp_max * v.D);  // patches, patch_emb, x_raw(_p)
   total += e * (v.Mp_max * v.D + t.Mp_max * t.D + Bm * K * E + C * K * E);              // hp_v, hp_t, feats
   total += e * (2 * Bm * K * E + C * K * E + K * Bm * C + Bm * C);                      // img_n, img_s, text_n, pair, dl_t
   total += e * (2 * Bm * K * E + 2 * C * K * E);                                        // d_img_s, d_img_feat, d_text_n, d_text_feat
@@ -595,6 +659,10 @@ int rpo_create(const RpoConfig *cfg, RpoHandle **out) {
   h->device_bytes = total;
   int s = alloc_tower(h, v, true);
   if (s == RPO_OK) s = alloc_tower(h, t, true);
+  if (s == RPO_OK && h->slots == 2) {
+    h->vis2 = v;  // same geometry, own buffers
+    s = alloc_tower(h, h->vis2, true);
+  }
   Arena &a = h->arena;
   bool ok = s == RPO_OK;
 #define TAKE(field, bytes)                                   \
@@ -605,6 +673,7 @@ int rpo_create(const RpoConfig *cfg, RpoHandle **out) {
   TAKE(patches, e * Bm * h->NP * pk);
   TAKE(patch_emb, e * Bm * h->NP * v.D);
   TAKE(x_raw, e * v.Mtot_max * v.D);
+  TAKE(x_raw_p, e * v.Mp_max * v.D);
   TAKE(hp_v, e * v.Mp_max * v.D);
   TAKE(hp_t, e * t.Mp_max * t.D);
   TAKE(img_feat, e * Bm * K * E);
@@ -637,6 +706,8 @@ int rpo_create(const RpoConfig *cfg, RpoHandle **out) {
   std::vector<int> off(c.max_batch + 1);
   for (int b = 0; b <= c.max_batch; ++b) off[b] = b * h->S;
   err = cudaMemcpy(v.ctx_off, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice);
+  if (err == cudaSuccess && h->slots == 2)
+    err = cudaMemcpy(h->vis2.ctx_off, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice);
   if (err != cudaSuccess) {
     set_error(std::string("cudaMemcpy failed: ") + cudaGetErrorString(err));
     cudaFree(base);
@@ -667,7 +738,8 @@ int rpo_create(const RpoConfig *cfg, RpoHandle **out) {
     }
     h->owned.push_back(ws);
     h->device_bytes += wsb;
-    h->vis.sk_ws = ws;
+    // with two image slots the context pass and the prompt chain run on different streams: no stream-K at all
+    if (h->slots == 1) h->vis.sk_ws = ws;
   }
   *out = h;
   return RPO_OK;
@@ -708,6 +780,11 @@ int rpo_bind_weights(RpoHandle *h, const RpoWeights *w, void *stream) {
     case RPO_F32: s = bind_impl<float>(h, st); break;
     case RPO_F16: s = bind_impl<__half>(h, st); break;
     default: s = bind_impl<__nv_bfloat16>(h, st); break;
+  }
+  if (s == RPO_OK && h->slots == 2) {
+    Tower &a = h->vis, &b = h->vis2;
+    b.blocks = a.blocks;
+    b.proj_wT = a.proj_wT; b.fc_wT = a.fc_wT; b.out_wT = a.out_wT; b.q_wT = a.q_wT;
   }
   if (s == RPO_OK) h->bound = true;
   return s;
@@ -825,6 +902,24 @@ int rpo_forward_image(RpoHandle *h, const void *image, int32_t image_dtype, int3
   STAGE(image_forward_stage<T>(h, image, image_dtype, B, img_prompt, (cudaStream_t)stream));
 }
 
+int rpo_forward_image_context(RpoHandle *h, const void *image, int32_t image_dtype, int32_t B, int32_t slot,
+                              void *stream) {
+  RPO_REQUIRE(h && image, "null argument");
+  RPO_REQUIRE(h->bound, "rpo_bind_weights must be called first");
+  RPO_REQUIRE(B >= 1 && B <= h->cfg.max_batch, "batch size exceeds max_batch");
+  RPO_REQUIRE(slot >= 0 && slot < h->slots, "image slot (RpoConfig.image_slots)");
+  Tower &v = slot ? h->vis2 : h->vis;
+  STAGE(image_context_stage<T>(h, v, image, image_dtype, B, (cudaStream_t)stream));
+}
+
+int rpo_forward_image_prompts(RpoHandle *h, const void *img_prompt, int32_t slot, void *stream) {
+  RPO_REQUIRE(h && img_prompt, "null argument");
+  RPO_REQUIRE(slot >= 0 && slot < h->slots, "image slot (RpoConfig.image_slots)");
+  Tower &v = slot ? h->vis2 : h->vis;
+  RPO_REQUIRE(h->bound && v.G >= 1 && v.Mc > 0, "rpo_forward_image_context must fill the slot first");
+  STAGE(image_prompt_stage<T>(h, v, img_prompt, (cudaStream_t)stream));
+}
+
 int rpo_forward_logits(RpoHandle *h, const int64_t *label, float *logits, float *loss, void *stream) {
   RPO_REQUIRE(h, "null argument");
   RPO_REQUIRE(h->have_image && h->text_feat_valid, "rpo_forward_logits needs image and text features");
@@ -912,7 +1007,7 @@ int64_t rpo_debug_fetch(RpoHandle *h, int32_t which, int32_t layer, void *dst, i
   const char *src = nullptr;
   int64_t n = 0;
   if (which == 0 || which == 1) {
-    Tower &tw = which == 0 ? h->vis : h->txt;
+    Tower &tw = which == 0 ? *h->vcur : h->txt;
     if (layer < -1 || layer >= tw.layers) return -1;
     src = tw.x_in + (size_t)(layer + 1) * tw.Mtot_max * tw.D * h->esz;
     n = (tw.Mc + (int64_t)tw.G * tw.K) * tw.D;

@@ -20,7 +20,7 @@ class Engine:
     `forward` / `backward` only enqueue kernels on the current stream (graph-capturable)."""
 
     def __init__(self, arch, K, n_cls, dtype, max_batch, w_mm, w_f32, index, text_x, len_prompts,
-                 gemm_backend=_lib.GEMM_AUTO, shard=None, group=None):
+                 gemm_backend=_lib.GEMM_AUTO, shard=None, group=None, image_slots=1):
         """`shard` (text_shard.ClassShard): this handle's text tower covers shard.slice of the classes only;
         `forward` / `backward` then run the native stages with the all-gather / reduce-scatter of
         text_shard.TextExchange in between (`group`: the torch.distributed process group)."""
@@ -41,7 +41,9 @@ class Engine:
             v_width=arch.v_width, v_layers=arch.v_layers, v_heads=arch.v_heads, v_patch=arch.v_patch,
             v_res=arch.v_res, t_width=arch.t_width, t_layers=arch.t_layers, t_heads=arch.t_heads,
             max_batch=max_batch, gemm_backend=gemm_backend,
-            cls_first=shard.first if shard is not None else 0, cls_local=shard.local if shard is not None else 0)
+            cls_first=shard.first if shard is not None else 0, cls_local=shard.local if shard is not None else 0,
+            image_slots=int(image_slots))
+        self.image_slots = int(image_slots)
         self.handle = C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.rpo_create(C.byref(cfg), C.byref(self.handle)))
@@ -159,6 +161,14 @@ class Engine:
     def image_forward(self, image, image_dtype_code, img_prompt):
         self._stage(self.lib.rpo_forward_image, _lib.ptr(image), image_dtype_code, image.shape[0],
                     _lib.ptr(img_prompt.detach().contiguous()))
+
+    def image_context(self, image, image_dtype_code, slot):
+        """context rows (cls + patches) of the vision tower for `image` into activation slot `slot`"""
+        self._stage(self.lib.rpo_forward_image_context, _lib.ptr(image), image_dtype_code, image.shape[0], int(slot))
+
+    def image_prompts(self, img_prompt, slot):
+        """prompt rows of the vision tower over the context already in `slot`; selects the slot for logits / backward"""
+        self._stage(self.lib.rpo_forward_image_prompts, _lib.ptr(img_prompt.detach().contiguous()), int(slot))
 
     def logits_forward(self, label, logits):
         self._stage(self.lib.rpo_forward_logits, _lib.ptr(label), _lib.ptr(logits),
@@ -296,6 +306,7 @@ class CustomCLIP(nn.Module):
         self.register_buffer("w_f32", w_f32, persistent=False)
         self._engine = None
         self._shard, self._group = None, None
+        self._image_slots = 1
         self._text_key = None     # (engine, prompt storage, prompt version, epoch) of the cached text features
         self._prompt_epoch = 0    # bumped by whatever changes the prompts behind autograd's back (fused SGD step)
 
@@ -314,6 +325,15 @@ class CustomCLIP(nn.Module):
         self._engine = None
         self._text_key = None
         return self._shard
+
+    def pipeline_images(self, slots=2):
+        """Two sets of vision-tower activations in the native handle (RpoConfig.image_slots) so that
+        runner.StepRunner(pipeline=True) can run the context rows of the next batch beside the prompt-row chain of
+        the current one.  Costs one more copy of the vision activations (~1.5 GB at ViT-B/16, batch 32)."""
+        if int(slots) != self._image_slots:
+            self._image_slots = int(slots)
+            self._engine = None
+            self._text_key = None
 
     def invalidate_text_features(self):
         self._prompt_epoch += 1
@@ -346,7 +366,8 @@ class CustomCLIP(nn.Module):
         if eng is None or eng.device != self.w_mm.device or eng.max_batch < need:
             self._engine = None
             eng = Engine(self.arch, self.K, self.text_x.shape[0], self.dtype, need, self.w_mm, self.w_f32,
-                         self._index, self.text_x, self.len_prompts, self.gemm_backend, self._shard, self._group)
+                         self._index, self.text_x, self.len_prompts, self.gemm_backend, self._shard, self._group,
+                         self._image_slots)
             self._engine = eng
         return eng
 

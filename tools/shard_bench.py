@@ -4,7 +4,7 @@
         tools/shard_bench.py [--steps 30] [--cls 100 1000]
 
 For every class count: ViT-B/16, K=24, batch 32 per GPU, fp16 (BASELINE.json configs[1] / configs[3] geometry), one
-StepRunner without and one with `model.shard_text()`; CUDA-event time of `steps` steps after warm-up, max over ranks.
+StepRunner per mode (plain data parallelism, `model.shard_text()`, pipelined context rows, both); CUDA-event time of `steps` steps after warm-up, max over ranks.
 Rank 0 prints one JSON line per run."""
 import argparse
 import json
@@ -24,7 +24,7 @@ from rpo_b200.model import CustomCLIP
 from rpo_b200.runner import StepRunner
 
 
-def run(C, shard, steps, warmup, B=32, K=24, arch_name="ViT-B/16", prec="fp16"):
+def run(C, shard, pipeline, steps, warmup, B=32, K=24, arch_name="ViT-B/16", prec="fp16"):
     world, rank = dist.get_world_size(), dist.get_rank()
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     arch = synth.ARCHS[arch_name]
@@ -37,7 +37,7 @@ def run(C, shard, steps, warmup, B=32, K=24, arch_name="ViT-B/16", prec="fp16"):
     model.prompt_learner.train()
     if shard:
         model.shard_text()
-    r = StepRunner(model, B, use_graph=True, process_group=dist.group.WORLD, world_size=world)
+    r = StepRunner(model, B, use_graph=True, process_group=dist.group.WORLD, world_size=world, pipeline=pipeline)
     pool = [synth.make_images(B, arch.image_resolution, seed=1234 + 97 * rank + i).to(dev) for i in range(8)]
     labels = [((torch.arange(B) + i + rank) % C).to(torch.int64).to(dev) for i in range(8)]
     r.image.copy_(pool[0])
@@ -66,7 +66,7 @@ def run(C, shard, steps, warmup, B=32, K=24, arch_name="ViT-B/16", prec="fp16"):
     dist.all_reduce(losses)
     if rank == 0:
         ms = float(t[0])
-        print(json.dumps({"n_gpus": world, "n_cls": C, "K": K, "batch_per_gpu": B, "shard_text": bool(shard),
+        print(json.dumps({"n_gpus": world, "n_cls": C, "K": K, "batch_per_gpu": B, "shard_text": bool(shard), "pipeline": bool(pipeline),
                           "ms_per_step": ms, "images_per_s": B * world / ms * 1e3,
                           "mean_loss_after": float(losses[0]) / world, "launches_per_step": r.launches_per_step,
                           "device_bytes": r.eng.device_bytes(),
@@ -81,12 +81,13 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--cls", type=int, nargs="+", default=[100, 1000])
+    ap.add_argument("--modes", nargs="+", default=["plain", "shard", "pipe", "shard+pipe"])
     a = ap.parse_args()
     lr = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
     for C in a.cls:
-        for shard in (False, True):
-            run(C, shard, a.steps, a.warmup)
+        for mode in a.modes:
+            run(C, "shard" in mode, "pipe" in mode, a.steps, a.warmup)
     dist.barrier()
     dist.destroy_process_group()
