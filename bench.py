@@ -326,7 +326,7 @@ def main_own(args):
     model.prompt_learner.train()
     pg = dist.group.WORLD if world > 1 else None
     shard_text = world > 1 and not args.no_shard_text
-    pipeline = not args.no_pipeline
+    pipeline = args.pipeline
     if shard_text:
         model.shard_text(rank, world, pg)  # each rank runs ceil(C / world) class prompts
     runner = StepRunner(model, B, lr=0.01, momentum=0.9, weight_decay=5e-4, use_graph=not args.no_graph,
@@ -481,8 +481,9 @@ if __name__ == "__main__":
     ap.add_argument("--no-shard-text", action="store_true",
                     help="N > 1: run every class prompt on every rank (as the reference) instead of class-sharding "
                          "the text tower over the ranks")
-    ap.add_argument("--no-pipeline", action="store_true",
-                    help="do not overlap the context rows of the next batch with the prompt-row chain of the current one")
+    ap.add_argument("--pipeline", action="store_true",
+                    help="overlap the context rows of the next batch with the prompt-row chain of the current one "
+                         "(StepRunner(pipeline=True); measured slower on B200, see DESIGN.md)")
     a = ap.parse_args()
     if a.impl == "reference":
         main_reference(a)

@@ -163,6 +163,10 @@ int rpo_forward_image(RpoHandle *h, const void *image, int32_t image_dtype, int3
 int rpo_forward_image_context(RpoHandle *h, const void *image, int32_t image_dtype, int32_t B, int32_t slot,
                               void *stream);
 int rpo_forward_image_prompts(RpoHandle *h, const void *img_prompt, int32_t slot, void *stream);
+/* SM budget of rpo_forward_image_context: its persistent kernels (GEMMs, attention) size their grids for n_sms SMs
+ * instead of the whole device, so that the prompt-row chain running beside it on another stream finds free SMs.
+ * 0 = whole device.  Takes effect at the next call (a captured graph keeps the budget it was captured with). */
+int rpo_set_context_sms(RpoHandle *h, int32_t n_sms);
 /* trainers/rpo.py:215-230: normalise, K-pair logits, cross-entropy (same argument rules as rpo_forward) */
 int rpo_forward_logits(RpoHandle *h, const int64_t *label, float *logits, float *loss, void *stream);
 /* d loss / d img_feat and d loss / d text_feat (all n_cls classes, this rank's images) */

@@ -23,6 +23,7 @@ SYMBOLS = [
     "rpo_debug_fetch", "rpo_launch_count", "rpo_profile_begin", "rpo_profile_end",
     "rpo_bind_text_exchange", "rpo_forward_text", "rpo_forward_image", "rpo_forward_logits", "rpo_backward_logits",
     "rpo_backward_text", "rpo_backward_image", "rpo_forward_image_context", "rpo_forward_image_prompts",
+    "rpo_set_context_sms",
 ]
 
 
@@ -79,6 +80,7 @@ def load():
     lib.rpo_forward_logits.argtypes = [vp, vp, vp, vp, vp]
     lib.rpo_forward_image_context.argtypes = [vp, vp, i32, i32, i32, vp]
     lib.rpo_forward_image_prompts.argtypes = [vp, vp, i32, vp]
+    lib.rpo_set_context_sms.argtypes = [vp, i32]
     lib.rpo_backward_logits.argtypes = [vp, vp]
     lib.rpo_backward_text.argtypes = [vp, vp, vp]
     lib.rpo_backward_image.argtypes = [vp, vp, vp]

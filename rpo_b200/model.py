@@ -166,6 +166,10 @@ class Engine:
         """context rows (cls + patches) of the vision tower for `image` into activation slot `slot`"""
         self._stage(self.lib.rpo_forward_image_context, _lib.ptr(image), image_dtype_code, image.shape[0], int(slot))
 
+    def set_context_sms(self, n_sms):
+        """SM budget of `image_context` (0 = whole device): leaves SMs to the prompt-row chain on the other stream"""
+        _lib.check(self.lib.rpo_set_context_sms(self.handle, int(n_sms)))
+
     def image_prompts(self, img_prompt, slot):
         """prompt rows of the vision tower over the context already in `slot`; selects the slot for logits / backward"""
         self._stage(self.lib.rpo_forward_image_prompts, _lib.ptr(img_prompt.detach().contiguous()), int(slot))

@@ -31,7 +31,7 @@ from . import _lib
 
 class StepRunner:
     def __init__(self, model, batch, lr=0.01, momentum=0.9, weight_decay=5e-4, use_graph=True, process_group=None,
-                 world_size=1, image_dtype=torch.float32, pipeline=False):
+                 world_size=1, image_dtype=torch.float32, pipeline=False, context_sms=None):
         self.model = model
         self.B = int(batch)
         self.device = model.w_mm.device
@@ -42,6 +42,11 @@ class StepRunner:
         if self.pipeline:
             model.pipeline_images(2)
         self.eng = model.engine(self.B)
+        if self.pipeline:
+            # SMs the context pass may occupy (the rest stay free for the prompt-row chain); 0 = all of them
+            if context_sms is None:
+                context_sms = int(os.environ.get("RPO_CTX_SMS", "0"))
+            self.eng.set_context_sms(context_sms)
         res = model.arch.v_res
         # float32 = what the reference's DataLoader hands over (trainers/rpo.py:318-323); torch.uint8 = raw pixels,
         # normalised inside the patch extraction (a quarter of the host-to-device bytes)
