@@ -16,6 +16,10 @@ Deliberate differences from trainers/rpo.py (none changes a result):
     one all-reduce of a flat f32 buffer before `optim.step()`.
   * `torch.autograd.set_detect_anomaly(True)` (:288) is not switched on (a debugging aid that halves
     throughput); set RPO_B200_DETECT_ANOMALY=1 to get it back.
+  * RPO_B200_SHARD_TEXT=1 with torch.distributed initialised: each rank runs the text tower for its
+    ceil(n_cls / world) class prompts only (`CustomCLIP.shard_text`, rpo_b200/text_shard.py); text features
+    are all-gathered, their gradient reduce-scattered, results unchanged.  Every rank must then call the
+    model the same number of times (training steps and evaluation batches alike).
   * PREC="amp": the reference keeps fp32 weights and autocasts the matmuls; here the fp32 engine runs
     (at least as precise as autocast) and the GradScaler is kept so the control flow is identical.
 
@@ -79,6 +83,21 @@ def allreduce_mean_(params, group=None):
     return world
 
 
+def maybe_shard_text(model, group=None):
+    """Class-shards the text tower over the process group when RPO_B200_SHARD_TEXT=1 and there is more than one
+    rank (and at least one class per rank).  Returns the shard or None."""
+    import torch.distributed as dist
+    if os.environ.get("RPO_B200_SHARD_TEXT") != "1" or not (dist.is_available() and dist.is_initialized()):
+        return None
+    if dist.get_world_size(group) == 1:
+        return None
+    try:
+        return model.shard_text(group=group)
+    except ValueError as e:  # fewer classes than ranks
+        print(f"text tower stays replicated: {e}")
+        return None
+
+
 class RPO(TrainerX):
     def check_cfg(self, cfg):
         assert cfg.TRAINER.RPO.PREC in ["fp16", "fp32", "amp"]  # trainers/rpo.py:238
@@ -100,6 +119,7 @@ class RPO(TrainerX):
         if cfg.MODEL.INIT_WEIGHTS:
             load_pretrained_weights(self.model.prompt_learner, cfg.MODEL.INIT_WEIGHTS)
         self.model.to(self.device)
+        maybe_shard_text(self.model)
         # only the prompt learner goes to the optimizer (:274-276)
         self.optim = build_optimizer(self.model.prompt_learner, cfg.OPTIM)
         self.sched = build_lr_scheduler(self.optim, cfg.OPTIM)

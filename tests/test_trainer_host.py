@@ -97,3 +97,13 @@ def test_allreduce_mean_is_noop_without_process_group():
     m.text_prompt.grad = torch.ones_like(m.text_prompt)
     assert trainer.allreduce_mean_(list(m.parameters())) == 1
     assert torch.all(m.text_prompt.grad == 1)
+
+
+def test_maybe_shard_text_needs_opt_in_and_a_process_group(monkeypatch):
+    class M:
+        def shard_text(self, group=None):
+            raise AssertionError("must not be called")
+    monkeypatch.delenv("RPO_B200_SHARD_TEXT", raising=False)
+    assert trainer.maybe_shard_text(M()) is None
+    monkeypatch.setenv("RPO_B200_SHARD_TEXT", "1")
+    assert trainer.maybe_shard_text(M()) is None  # torch.distributed is not initialised here
