@@ -300,3 +300,57 @@ def test_eval_reuses_text_features():
     with pytest.raises(_lib.RpoError):
         eng.forward(img1, None, model.prompt_learner.img_prompt.data, torch.tensor([0, 1], device="cuda:0"))
     assert first.shape == (2, 4)
+
+
+def _long_tokens(n_words, width=77):
+    """A prompt of `n_words` tokens between SOT (49406) and EOT (49407): len_prompts = n_words + 2."""
+    t = torch.zeros(1, width, dtype=torch.int64)
+    t[0, 0] = 49406
+    t[0, 1:1 + n_words] = torch.arange(n_words) % 1000 + 320
+    t[0, 1 + n_words] = 49407
+    return t
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp16"])
+@pytest.mark.parametrize("case", ["k1", "one_class_one_image", "max_length", "ragged_with_max"])
+def test_edge_shapes_match_oracle(prec, case):
+    """Edges of the reference's index arithmetic (trainers/rpo.py:137,149,177): a single prompt pair, a single
+    class / image, a class prompt whose K prompt slots end exactly at position 76 (len_prompts + K == 77), and a
+    class list mixing the shortest and the longest admissible prompts."""
+    K, B = {"k1": (1, 3), "one_class_one_image": (3, 1), "max_length": (4, 2), "ragged_with_max": (4, 3)}[case]
+    if case == "k1":
+        tokens = class_tokens([5, 600])
+    elif case == "one_class_one_image":
+        tokens = class_tokens([42])
+    elif case == "max_length":
+        tokens = _long_tokens(77 - K - 2)  # len_prompts = 77 - K
+    else:
+        tokens = torch.cat([class_tokens([7]), _long_tokens(77 - K - 2), _long_tokens(1), class_tokens([999])])
+    model, arch, sd = build_model("tiny", prec, K, tokens)
+    assert int(model.len_prompts.max()) + K <= 77
+    tp, ip = synth.make_prompt_init(sd, K)
+    set_prompts(model, tp, ip)
+    Cn = tokens.shape[0]
+    image = synth.make_images(B, arch.image_resolution)
+    label = synth.make_labels(B, Cn)
+    loss, gt, gi = step(model, image.cuda(), label.cuda())
+    logits = eval_logits(model, image.cuda())
+    om = OracleModel(convert_state_dict(sd, prec), tokens, K, prec, device="cuda:0")
+    tpd, ipd = model.prompt_learner.text_prompt.detach(), model.prompt_learner.img_prompt.detach()
+    oloss, ogt, ogi = om.step(image, tpd, ipd, label)
+    ologits = om.logits(image, tpd, ipd).cpu()
+    tol = TOL[prec]
+    assert logits.shape == (B, Cn)
+    assert abs(loss.item() - oloss.item()) <= tol * max(1.0, abs(oloss.item()))
+    assert (logits - ologits).abs().max().item() <= tol * float(np.exp(2.6592600369327783))
+    if Cn == 1:
+        # one class: softmax over a single logit, the loss is exactly 0 and so are both gradients
+        assert loss.item() == 0.0 and float(gt.abs().max()) == 0.0 and float(gi.abs().max()) == 0.0
+        assert float(ogt.abs().max()) == 0.0
+        return
+    ogt32, ogi32 = ogt, ogi
+    if prec != "fp32":
+        om32 = OracleModel(convert_state_dict(sd, "fp32"), tokens, K, "fp32", device="cuda:0")
+        _, ogt32, ogi32 = om32.step(image, tpd.float(), ipd.float(), label)
+    check_grads(prec, gt, ogt, ogt32, "text")
+    check_grads(prec, gi, ogi, ogi32, "image")
