@@ -721,7 +721,11 @@ int rpo_create(const RpoConfig *cfg, RpoHandle **out) {
     h->overlap = !(e && e[0] == '1');
     if (const char *sk = getenv("RPO_DEBUG_SKIP")) h->skip = atoi(sk);
   }
-  if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+  // RPO_SIDE_PRIO=<n>: stream priority of the text tower's side stream relative to the caller's stream (0 = same
+  // as a default stream, negative = higher); kernel nodes of a captured graph keep it
+  int side_prio = 0;
+  if (const char *e = getenv("RPO_SIDE_PRIO")) side_prio = atoi(e);
+  if (cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, side_prio) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
     set_error("could not create the side stream / events");

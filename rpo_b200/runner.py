@@ -65,8 +65,9 @@ class StepRunner:
         self.side = None
         if self.staged:
             # RPO_PIPE_PRIO=1: the prompt-row chain (many short dependent kernels) gets a higher stream priority than
-            # the context pass (few long kernels), so that its CTAs are placed first whenever an SM frees up
-            self.prio = self.pipeline and os.environ.get("RPO_PIPE_PRIO", "1") == "1"
+            # the context pass (few long kernels), so that its CTAs are placed first whenever an SM frees up.
+            # Measured slower (profiles/r01_pipeline_sweep.txt): off by default
+            self.prio = self.pipeline and os.environ.get("RPO_PIPE_PRIO", "0") == "1"
             hp = -1 if self.prio else 0
             self.side = torch.cuda.Stream(self.device, priority=hp)
             self.chain_stream = torch.cuda.Stream(self.device, priority=hp) if self.prio else None
@@ -237,7 +238,12 @@ class StepRunner:
                 self._capture_staged()
             elif self.use_graph:
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                # RPO_MAIN_PRIO=<n>: capture on a stream of that priority (negative = higher than the text tower's
+                # side stream, whose kernels then only fill the gaps the vision tower leaves).  Measured on B200: any
+                # priority difference inside the graph costs 15 % (3.27 -> 3.77 ms, profiles/r01_stream_priority.txt)
+                mp = int(os.environ.get("RPO_MAIN_PRIO", "0"))
+                cap = torch.cuda.Stream(self.device, priority=mp) if mp else None
+                with torch.cuda.graph(g, stream=cap):
                     if self.world > 1:
                         self._fwd_bwd()
                     else:
