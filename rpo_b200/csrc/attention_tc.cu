@@ -87,6 +87,18 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
                :
                : "memory");
 }
+// packed f32x2 arithmetic (sm_100: FFMA2 / FADD2, two lanes per issue slot): (a, b) = (a, b) * s + o ; (a, b) += (c, d)
+__device__ __forceinline__ void ffma2(float &a, float &b, float s, float o) {
+  asm("{ .reg .b64 x, y, z; mov.b64 x, {%0, %1}; mov.b64 y, {%2, %2}; mov.b64 z, {%3, %3}; fma.rn.f32x2 x, x, y, z; "
+      "mov.b64 {%0, %1}, x; }"
+      : "+f"(a), "+f"(b)
+      : "f"(s), "f"(o));
+}
+__device__ __forceinline__ void fadd2(float &a, float &b, float c, float d) {
+  asm("{ .reg .b64 x, y; mov.b64 x, {%0, %1}; mov.b64 y, {%2, %3}; add.rn.f32x2 x, x, y; mov.b64 {%0, %1}, x; }"
+      : "+f"(a), "+f"(b)
+      : "f"(c), "f"(d));
+}
 __device__ __forceinline__ void pair_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
 struct Geo {
@@ -97,6 +109,8 @@ struct Geo {
   int prompt_row;   // ... starting at this row of the tile (== context rows in that tile)
   int H;
   int tiles;        // query tiles per (group, head)
+  int phase_delay;  // SM clocks the second CTA of an SM holds back its first loads (0: none), see the kernel
+  int flags;        // bit 0: packed f32x2 arithmetic in the probability pass
 };
 
 template <typename T>
@@ -192,6 +206,14 @@ __global__ void __launch_bounds__(THREADS, 2)
       const uint32_t idesc_o = make_idesc((int)fmt, QT, HD) | (1u << 16);  // B (= V) is MN-major
       const int nsteps = n16 >> 4;
       pdl_wait();
+      // Two CTAs share an SM and would otherwise run in lockstep -- both in the MUFU-bound probability pass at the
+      // same time, both waiting on the tensor core at the same time.  The CTA that got the upper half of the SM's
+      // tensor memory starts late by a fraction of an item so that one CTA's exponentials run beside the other's
+      // MMA / row-maximum / epilogue phases.
+      if (geo.phase_delay > 0 && (tmem_base & 0xFFFFu) >= (uint32_t)TMEM_COLS) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < (long long)geo.phase_delay) __nanosleep(100);
+      }
       int id = blockIdx.x;
       if (id < num_items) {
         const Item first = item_of(id);
@@ -288,7 +310,7 @@ __global__ void __launch_bounds__(THREADS, 2)
         mx = fmaxf(red_max[row], red_max[QT + row]);  // every row sees key 0, so the maximum is finite
         const float off = mx * sl2;
         // ---- pass 2: probabilities -> P blocks, row sum ----
-        float l = 0.f;
+        float l = 0.f, l_odd = 0.f;
         {
           uint32_t cur[16], nxt[16];
           tmem_ld16_nowait(taddr + (uint32_t)(b0 * 16), cur);
@@ -296,7 +318,16 @@ __global__ void __launch_bounds__(THREADS, 2)
           for (int b = b0; b < b1; ++b) {
             if (b + 1 < b1) tmem_ld16_nowait(taddr + (uint32_t)((b + 1) * 16), nxt);
             uint32_t pk[8];
-            if (b * 16 + 16 <= n) {
+            if (b * 16 + 16 <= n && (geo.flags & 1)) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float x0 = __uint_as_float(cur[2 * e]), x1 = __uint_as_float(cur[2 * e + 1]);
+                ffma2(x0, x1, sl2, -off);
+                const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+                fadd2(l, l_odd, p0, p1);
+                pk[e] = pack2<T>(p0, p1);
+              }
+            } else if (b * 16 + 16 <= n) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
                 const float p0 = ex2_approx(fmaf(__uint_as_float(cur[2 * e]), sl2, -off));
@@ -324,7 +355,7 @@ __global__ void __launch_bounds__(THREADS, 2)
             }
           }
         }
-        red_sum[hf * QT + row] = l;
+        red_sum[hf * QT + row] = l + l_odd;
         // make the generic-proxy stores of P visible to the tensor core (async proxy), release S
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         tc_fence_before();
@@ -405,6 +436,10 @@ int ro_attention_fwd_dense(const T *qkv_ctx, const T *q_prompt, T *out_ctx, T *o
     geo.prompt_tile = n / 128;
     geo.prompt_row = n % 128;
     geo.H = H;
+    geo.phase_delay = 0;
+    geo.flags = 0;
+    if (const char *e = getenv("RPO_ATTN_PHASE_DELAY")) geo.phase_delay = atoi(e);
+    if (const char *e = getenv("RPO_ATTN_F32X2")) geo.flags |= (e[0] == '1') ? 1 : 0;
     const int tiles = K > 0 ? geo.prompt_tile + 1 : (n + 127) / 128;
     CUtensorMap map_full, map_kvt, map_qt, map_prompt;
     const long long Mc = (long long)G * n;
