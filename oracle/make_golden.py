@@ -30,6 +30,12 @@ CASES = {
     # K=24 with ragged prompt lengths (1/2/3-digit class ids tokenise to 9/10/11 tokens)
     "k24_ragged_fp32": dict(arch="ViT-B/16", K=24, class_ids=[0, 5, 17, 123, 999, 42, 7, 256, 1, 64], B=3, prec="fp32"),
     "k24_ragged_fp16": dict(arch="ViT-B/16", K=24, class_ids=[0, 5, 17, 123, 999, 42, 7, 256, 1, 64], B=3, prec="fp16"),
+    # edges of the index arithmetic (trainers/rpo.py:137,149,177): a class prompt whose K prompt slots end exactly
+    # at position 76 (len_prompts + K == 77) next to a 9- and an 8-token prompt, one image; and a single prompt pair
+    "edge_maxlen_fp32": dict(arch="ViT-B/16", K=4, names=["class 7", " ".join(["dog"] * 66), "x"], B=1, prec="fp32"),
+    "edge_maxlen_fp16": dict(arch="ViT-B/16", K=4, names=["class 7", " ".join(["dog"] * 66), "x"], B=1, prec="fp16"),
+    "edge_k1_fp32": dict(arch="ViT-B/16", K=1, class_ids=[0, 10, 100], B=2, prec="fp32"),
+    "edge_k1_fp16": dict(arch="ViT-B/16", K=1, class_ids=[0, 10, 100], B=2, prec="fp16"),
 }
 TAP_ROWS_V = [0, 100]  # cls row and one patch row; the first and last prompt rows are appended
 TAP_ROWS_T = [0, 4]
@@ -38,7 +44,7 @@ TAP_ROWS_T = [0, 4]
 def run_case(name, spec):
     arch = synth.ARCHS[spec["arch"]]
     sd = synth.make_state_dict(arch, seed=0)
-    names = [f"class {i}" for i in spec["class_ids"]]
+    names = spec.get("names") or [f"class {i}" for i in spec["class_ids"]]
     K, B, prec = spec["K"], spec["B"], spec["prec"]
     C = len(names)
     model = rh.build_reference_customclip(sd, names, K, prec, seed_prompts=0)
@@ -66,7 +72,7 @@ def run_case(name, spec):
     taps_t = torch.stack([o[rows_t, 0, :] for o in tt])
     out = dict(
         tokens=model.text_tokenized.numpy().astype(np.int32),
-        class_ids=np.asarray(spec["class_ids"], np.int32),
+        class_ids=np.asarray(spec.get("class_ids", []), np.int32),  # empty: free-form class names
         K=np.int32(K), B=np.int32(B),
         text_prompt=model.prompt_learner.text_prompt.detach().float().numpy(),
         img_prompt=model.prompt_learner.img_prompt.detach().float().numpy(),
@@ -79,7 +85,7 @@ def run_case(name, spec):
     )
     path = os.path.join(GOLDEN_DIR, f"{name}.npz")
     np.savez_compressed(path, **out)
-    print(f"{name}: loss={loss.item():.6f} |g_text|max={g_text.abs().max():.3e} "
+    print(f"{name}: len_prompts={lp.tolist()} loss={loss.item():.6f} |g_text|max={g_text.abs().max():.3e} "
           f"|g_img|max={g_img.abs().max():.3e} -> {path} ({os.path.getsize(path)/1024:.0f} KiB)")
 
 
@@ -97,8 +103,9 @@ def tokens_table():
 if __name__ == "__main__":
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    tokens_table()
     only = sys.argv[1:]
+    if not only:
+        tokens_table()
     for name, spec in CASES.items():
         if only and name not in only:
             continue

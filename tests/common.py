@@ -9,7 +9,9 @@ from rpo_b200 import synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-GOLDEN_CASES = ["cfg1_fp32", "cfg1_fp16", "k24_ragged_fp32", "k24_ragged_fp16"]
+GOLDEN_CASES = ["cfg1_fp32", "cfg1_fp16", "k24_ragged_fp32", "k24_ragged_fp16",
+                # edges: len_prompts + K == 77 next to short prompts with one image; a single prompt pair
+                "edge_maxlen_fp32", "edge_maxlen_fp16", "edge_k1_fp32", "edge_k1_fp16"]
 
 
 def load_golden(name):

@@ -17,7 +17,8 @@ def test_oracle_matches_reference_golden(name):
     K, B = int(g["K"]), int(g["B"])
     tokens = torch.from_numpy(g["tokens"].astype(np.int64))
     # the committed token table agrees with what the reference tokenizer produced for this case
-    assert torch.equal(class_tokens(g["class_ids"].tolist()), tokens)
+    if g["class_ids"].size:  # (free-form class names carry no ids)
+        assert torch.equal(class_tokens(g["class_ids"].tolist()), tokens)
     om = OracleModel(convert_state_dict(state_dict("ViT-B/16"), prec), tokens, K, prec)
     image = synth.make_images(B, arch.image_resolution)
     label = synth.make_labels(B, tokens.shape[0])
