@@ -176,7 +176,6 @@ class StepRunner:
             self._ctx_ready[slot].record(self.ctx_stream)
 
     def _staged_step(self):
-        main = torch.cuda.current_stream(self.device)
         if not self.pipeline:
             self._run_chain(0)
             return
