@@ -57,3 +57,23 @@ def test_no_cpu_fallback():
     assert model.prompt_learner.text_prompt.shape == (2, 128) and model.prompt_learner.text_prompt.dtype == torch.float16
     with pytest.raises(_lib.RpoError):
         model(torch.zeros(1, 3, 64, 64), torch.zeros(1, dtype=torch.int64))
+
+
+def test_header_is_plain_c_and_a_c_client_links(lib, tmp_path):
+    """The boundary is a C ABI: the header compiles as C99 and a torch-free C program links against the shared
+    library and gets the documented status codes (integration/c_client.c)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    inc = os.path.join(ROOT, "include")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c",
+                    os.path.join(inc, "rpo_b200.h")], check=True)
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    exe = str(tmp_path / "c_client")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", inc, os.path.join(ROOT, "integration", "c_client.c"),
+                    "-L", libdir, "-lrpo_b200", f"-Wl,-rpath,{libdir}", "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "argument validation ok" in r.stdout
