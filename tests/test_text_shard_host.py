@@ -119,3 +119,27 @@ def test_exchange_is_a_noop_at_world_1():
     ex.gather_text_features()
     ex.scatter_text_grads()
     assert torch.all(ex.text_feat == 1.0) and torch.all(ex.d_text_feat == 2.0)
+
+
+def test_class_shard_partition_properties():
+    """every admissible (n_cls, world): contiguous, disjoint, covering, equal padded parts; otherwise a loud error"""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.integers(1, 2000), st.integers(1, 16))
+    def check(n_cls, world):
+        per = -(-n_cls // world)
+        empty_ranks = [r for r in range(world) if r * per >= n_cls]
+        nxt = 0
+        for r in range(world):
+            if r in empty_ranks:
+                with pytest.raises(ValueError):
+                    ClassShard(n_cls, r, world)
+                continue
+            s = ClassShard(n_cls, r, world)
+            assert s.first == nxt and s.per == per and s.n_pad == per * world and 1 <= s.local <= per
+            assert s.slice == slice(s.first, s.first + s.local)
+            nxt = s.first + s.local
+        assert nxt == n_cls
+
+    check()
