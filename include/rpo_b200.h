@@ -163,10 +163,6 @@ int rpo_forward_image(RpoHandle *h, const void *image, int32_t image_dtype, int3
 int rpo_forward_image_context(RpoHandle *h, const void *image, int32_t image_dtype, int32_t B, int32_t slot,
                               void *stream);
 int rpo_forward_image_prompts(RpoHandle *h, const void *img_prompt, int32_t slot, void *stream);
-/* SM budget of rpo_forward_image_context: its persistent kernels (GEMMs, attention) size their grids for n_sms SMs
- * instead of the whole device, so that the prompt-row chain running beside it on another stream finds free SMs.
- * 0 = whole device.  Takes effect at the next call (a captured graph keeps the budget it was captured with). */
-int rpo_set_context_sms(RpoHandle *h, int32_t n_sms);
 /* trainers/rpo.py:215-230: normalise, K-pair logits, cross-entropy (same argument rules as rpo_forward) */
 int rpo_forward_logits(RpoHandle *h, const int64_t *label, float *logits, float *loss, void *stream);
 /* d loss / d img_feat and d loss / d text_feat (all n_cls classes, this rank's images) */
@@ -181,6 +177,42 @@ int rpo_backward_image(RpoHandle *h, float *grad_flat, void *stream);
  * graph-capturable; lr is a device f32 scalar for the same reason. */
 int rpo_sgd_step(void *param, int32_t dtype, const float *grad, float *momentum_buf, int64_t n, const float *lr,
                  float momentum, float weight_decay, float grad_scale, const int32_t *first_step, void *stream);
+
+/* ---- exchanges between the data-parallel ranks of one node through peer-mapped memory (NVLink / NVSwitch) ------
+ * "one ncclAllReduce over the flat [K*Dt + K*Dv] buffer, then the identical SGD step on every
+ * rank" (the reference's own multi-GPU is nn.DataParallel, trainers/rpo.py:282-285, which cannot train RPO).
+ * Here the exchange is done by this library's own kernels over buffers every rank has mapped from every peer
+ * (CUDA IPC / symmetric memory: the CALLER allocates and maps them, e.g. torch.distributed._symmetric_memory), so
+ * the calls are plain kernel launches -- capturable into the step's CUDA graph, no host-issued collective between
+ * graph segments.  Every rank must make the same calls in the same order.
+ *
+ * RpoPeerComm: signals[r] = rank r's signal words (rpo_peer_signal_bytes() bytes, zeroed once before the first
+ * call) as mapped into THIS process; epoch = rpo_peer_epoch_bytes() bytes of local device memory, zeroed once. */
+#define RPO_PEER_MAX_WORLD 8
+#define RPO_PEER_MAX_BLOCKS 128
+typedef struct {
+  void *signals[RPO_PEER_MAX_WORLD];
+  void *epoch;
+  int32_t rank, world;
+} RpoPeerComm;
+size_t rpo_peer_signal_bytes(void);
+size_t rpo_peer_epoch_bytes(void);
+/* optim.step() (trainers/rpo.py:309) fused with the gradient all-reduce: grad_flat[r] = rank r's flat f32 gradient
+ * [n_total] (text part first, n_text elements) as mapped here; the kernel sums them in rank order (bit-identical on
+ * every replica), then updates both prompt tensors exactly as rpo_sgd_step does with grad = the sum. */
+int rpo_peer_allreduce_sgd(const RpoPeerComm *comm, void *const *grad_flat, void *text_prompt, void *img_prompt,
+                           int32_t dtype, int64_t n_text, int64_t n_total, float *momentum_buf, const float *lr,
+                           float momentum, float weight_decay, float grad_scale, const int32_t *first_step,
+                           void *stream);
+/* class-sharded text tower: bufs[r] = rank r's exchange buffer (rpo_bind_text_exchange's text_feat /
+ * d_text_feat).  all_gather pushes bytes [offset, offset + nbytes) of this rank's buffer to the same offset of every
+ * peer's; reduce_scatter replaces elements [offset, offset + n) of this rank's buffer by the sum over all ranks'
+ * buffers (f32 accumulation in rank order, one rounding).  *_max = the largest part of any rank (sizes the grid:
+ * every rank must launch the same number of blocks). */
+int rpo_peer_all_gather(const RpoPeerComm *comm, void *const *bufs, int64_t offset_bytes, int64_t nbytes,
+                        int64_t nbytes_max, void *stream);
+int rpo_peer_reduce_scatter(const RpoPeerComm *comm, void *const *bufs, int32_t dtype, int64_t offset_elems,
+                            int64_t n_elems, int64_t n_elems_max, void *stream);
 
 /* unit kernels (one per hot-path op; used by the parity tests) -------------------------------- */
 
@@ -227,6 +259,9 @@ int rpo_ro_attention_fwd(const void *qkv_ctx, const void *q_prompt, void *out_ct
  * RPO_ERR_INVALID otherwise: use rpo_ro_attention_fwd).  qkv_ctx [G*n_ctx, 3D], q_prompt [G*K, D]. */
 int rpo_ro_attention_fwd_dense(const void *qkv_ctx, const void *q_prompt, void *out_ctx, void *out_prompt, int32_t G,
                                int32_t n_ctx, int32_t K, int32_t H, int32_t dtype, void *stream);
+/* 1 if rpo_ro_attention_fwd_dense takes this shape (dtype RPO_F16 / RPO_BF16, n_ctx context keys, K prompt queries,
+ * H heads of 64), else 0 -- callers then use rpo_ro_attention_fwd */
+int rpo_ro_attention_fwd_dense_supported(int32_t dtype, int32_t n_ctx, int32_t K, int32_t H);
 /* gradient w.r.t. the prompt queries only (keys/values come from rows that carry no gradient):
  * dq_prompt [G*K, D] from d_out_prompt [G*K, D]; out_prompt is the forward output of the same rows
  * (used for the softmax-gradient row term sum_d dO*O). */

@@ -38,13 +38,20 @@ _HALF_KEYS_SUFFIX = (
 )
 _HALF_KEYS_EXACT = ("visual.conv1.weight", "text_projection", "visual.proj")
 
-PREC_DTYPE = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}
+PREC_DTYPE = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16, "fp64": torch.float64}
 
 
-def convert_state_dict(sd, prec: str):
+def convert_state_dict(sd, prec: str, values_of: str = None):
     """clip/model.py:379-400: Linear/Conv/MHA weights+biases and the two projections become 16-bit;
     LayerNorm params, embeddings, class_embedding, logit_scale stay fp32.  bf16 is an
-    extension with the same key set (H9)."""
+    extension with the same key set (H9).
+
+    prec="fp64" is the TRUTH model of the parity tests (no reference counterpart): the weight VALUES of
+    the `values_of` precision (what a fp16 / bf16 / fp32 model holds) carried in double, so that the same
+    function is evaluated with (nearly) exact arithmetic."""
+    if prec == "fp64":
+        src = convert_state_dict(sd, values_of or "fp32")
+        return OrderedDict((k, v.double() if v.is_floating_point() else v) for k, v in src.items())
     dt = PREC_DTYPE[prec]
     out = OrderedDict()
     for k, v in sd.items():
@@ -60,6 +67,8 @@ def convert_state_dict(sd, prec: str):
 def layer_norm(x, w, b):
     # clip/model.py:156-159
     orig = x.dtype
+    if orig == torch.float64:  # truth model: no fp32 detour
+        return F.layer_norm(x, (x.shape[-1],), w, b, 1e-5)
     ret = F.layer_norm(x.type(torch.float32), (x.shape[-1],), w, b, 1e-5)
     return ret.type(orig)
 
@@ -192,7 +201,7 @@ class OracleModel:
         # ---- logits ---- (:215-227)
         text_f = text_f / text_f.norm(dim=-1, keepdim=True)
         img_f = img_f / img_f.norm(dim=-1, keepdim=True)
-        logits = torch.zeros(B, C, device=device)
+        logits = torch.zeros(B, C, device=device, dtype=torch.float64 if dtype == torch.float64 else torch.float32)
         for i in range(K):
             logit = sd["logit_scale"].exp() * img_f[:, i, :] @ text_f[:, i, :].t()
             logits += logit

@@ -19,11 +19,12 @@ ACT_NONE, ACT_QUICKGELU = 0, 1
 SYMBOLS = [
     "rpo_last_error", "rpo_version", "rpo_create", "rpo_destroy", "rpo_device_bytes", "rpo_bind_weights",
     "rpo_set_classes", "rpo_set_image_norm", "rpo_forward", "rpo_backward", "rpo_sgd_step", "rpo_layernorm_fwd", "rpo_layernorm_bwd",
-    "rpo_gemm_bias_act", "rpo_gemm_bias_act_ws", "rpo_gemm_workspace_bytes", "rpo_ro_attention_fwd", "rpo_ro_attention_fwd_dense", "rpo_ro_attention_bwd", "rpo_logits_ce_fwd", "rpo_logits_ce_bwd",
+    "rpo_gemm_bias_act", "rpo_gemm_bias_act_ws", "rpo_gemm_workspace_bytes", "rpo_ro_attention_fwd", "rpo_ro_attention_fwd_dense", "rpo_ro_attention_fwd_dense_supported", "rpo_ro_attention_bwd", "rpo_logits_ce_fwd", "rpo_logits_ce_bwd",
     "rpo_debug_fetch", "rpo_launch_count", "rpo_profile_begin", "rpo_profile_end",
     "rpo_bind_text_exchange", "rpo_forward_text", "rpo_forward_image", "rpo_forward_logits", "rpo_backward_logits",
     "rpo_backward_text", "rpo_backward_image", "rpo_forward_image_context", "rpo_forward_image_prompts",
-    "rpo_set_context_sms",
+    "rpo_peer_signal_bytes", "rpo_peer_epoch_bytes", "rpo_peer_allreduce_sgd", "rpo_peer_all_gather",
+    "rpo_peer_reduce_scatter",
 ]
 
 
@@ -43,6 +44,14 @@ class RpoWeights(C.Structure):
         [(n, C.c_void_p) for n in (
             "conv_w", "cls_emb", "v_pos", "ln_pre_w", "ln_pre_b", "ln_post_w", "ln_post_b", "v_proj",
             "ln_final_w", "ln_final_b", "t_proj", "logit_scale")]
+
+
+PEER_MAX_WORLD = 8
+
+
+class RpoPeerComm(C.Structure):
+    _fields_ = [("signals", C.c_void_p * PEER_MAX_WORLD), ("epoch", C.c_void_p), ("rank", C.c_int32),
+                ("world", C.c_int32)]
 
 
 class RpoError(RuntimeError):
@@ -80,7 +89,12 @@ def load():
     lib.rpo_forward_logits.argtypes = [vp, vp, vp, vp, vp]
     lib.rpo_forward_image_context.argtypes = [vp, vp, i32, i32, i32, vp]
     lib.rpo_forward_image_prompts.argtypes = [vp, vp, i32, vp]
-    lib.rpo_set_context_sms.argtypes = [vp, i32]
+    lib.rpo_peer_signal_bytes.restype = C.c_size_t
+    lib.rpo_peer_epoch_bytes.restype = C.c_size_t
+    lib.rpo_peer_allreduce_sgd.argtypes = [C.POINTER(RpoPeerComm), C.POINTER(vp), vp, vp, i32, i64, i64, vp, vp, f32,
+                                           f32, f32, vp, vp]
+    lib.rpo_peer_all_gather.argtypes = [C.POINTER(RpoPeerComm), C.POINTER(vp), i64, i64, i64, vp]
+    lib.rpo_peer_reduce_scatter.argtypes = [C.POINTER(RpoPeerComm), C.POINTER(vp), i32, i64, i64, i64, vp]
     lib.rpo_backward_logits.argtypes = [vp, vp]
     lib.rpo_backward_text.argtypes = [vp, vp, vp]
     lib.rpo_backward_image.argtypes = [vp, vp, vp]
@@ -94,6 +108,7 @@ def load():
     lib.rpo_gemm_workspace_bytes.restype = C.c_size_t
     lib.rpo_ro_attention_fwd.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
     lib.rpo_ro_attention_fwd_dense.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.rpo_ro_attention_fwd_dense_supported.argtypes = [i32, i32, i32, i32]
     lib.rpo_ro_attention_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.rpo_logits_ce_fwd.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]
     lib.rpo_logits_ce_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp,
@@ -106,9 +121,7 @@ def load():
     lib.rpo_profile_end.argtypes = [C.c_char_p, i64]
     lib.rpo_profile_end.restype = i64
     for name in SYMBOLS:
-        fn = getattr(lib, name)
-        if fn.restype is C.c_int and name not in ("rpo_version",):
-            pass
+        getattr(lib, name)  # raises if the .so lacks a symbol the header declares
     _lib = lib
     return lib
 

@@ -15,10 +15,6 @@ namespace rpo {
 // ---- error plumbing -----------------------------------------------------------------------------
 void set_error(const std::string &msg);
 extern thread_local int64_t g_launch_count;
-// > 0: the persistent kernels launched from this thread size their grids for this many SMs instead of the whole
-// device (tc_common.cuh sm_count()), leaving the rest to kernels of another stream.  Set around the image-context
-// stage (rpo_set_context_sms) so that the prompt-row chain of the previous batch finds free SMs.
-extern thread_local int g_sm_limit;
 
 #define RPO_CHECK_CUDA(expr)                                                                     \
   do {                                                                                           \

@@ -24,7 +24,6 @@ namespace rpo {
 
 thread_local std::string g_last_error;
 thread_local int64_t g_launch_count = 0;
-thread_local int g_sm_limit = 0;
 void set_error(const std::string &msg) { g_last_error = msg; }
 bool pdl_enabled() {
   static const bool on = [] {
@@ -106,7 +105,6 @@ struct RpoHandle {
   // computed into one slot (rpo_forward_image_context) while the prompt rows / backward of the current batch use the
   // other -- context rows never depend on the prompts (trainers/rpo.py:155-156 masks the prompt columns).
   Tower vis2;
-  int ctx_sms = 0;     // SM budget of the image-context stage (0: whole device), see rpo_set_context_sms
   Tower *vcur = &vis;  // the slot the last image forward used: what the logits / backward stages refer to
   int slots = 1;
   Arena arena;
@@ -915,17 +913,7 @@ int rpo_forward_image_context(RpoHandle *h, const void *image, int32_t image_dty
   RPO_REQUIRE(B >= 1 && B <= h->cfg.max_batch, "batch size exceeds max_batch");
   RPO_REQUIRE(slot >= 0 && slot < h->slots, "image slot (RpoConfig.image_slots)");
   Tower &v = slot ? h->vis2 : h->vis;
-  struct Limit {  // the stage's persistent kernels size their grids for ctx_sms SMs
-    explicit Limit(int n) { g_sm_limit = n; }
-    ~Limit() { g_sm_limit = 0; }
-  } limit(h->ctx_sms);
   STAGE(image_context_stage<T>(h, v, image, image_dtype, B, (cudaStream_t)stream));
-}
-
-int rpo_set_context_sms(RpoHandle *h, int32_t n_sms) {
-  RPO_REQUIRE(h && n_sms >= 0, "null handle or negative SM count");
-  h->ctx_sms = n_sms >= 2 ? (n_sms & ~1) : 0;  // CTA pairs: even
-  return RPO_OK;
 }
 
 int rpo_forward_image_prompts(RpoHandle *h, const void *img_prompt, int32_t slot, void *stream) {
@@ -1119,6 +1107,10 @@ int rpo_ro_attention_fwd_dense(const void *qkv_ctx, const void *q_prompt, void *
   return ro_attention_fwd_dense<__nv_bfloat16>((const __nv_bfloat16 *)qkv_ctx, (const __nv_bfloat16 *)q_prompt,
                                                (__nv_bfloat16 *)out_ctx, (__nv_bfloat16 *)out_prompt, G, n_ctx, K, H,
                                                (cudaStream_t)stream);
+}
+
+int rpo_ro_attention_fwd_dense_supported(int32_t dtype, int32_t n_ctx, int32_t K, int32_t H) {
+  return ro_attention_fwd_dense_supported(dtype, n_ctx, K, H) ? 1 : 0;
 }
 
 int rpo_ro_attention_bwd(const void *qkv_ctx, const void *q_prompt, const void *out_prompt, const void *d_out_prompt,

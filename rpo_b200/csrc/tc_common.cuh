@@ -145,7 +145,7 @@ inline int sm_count() {
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
       n = 148;
   }
-  return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
+  return n;
 }
 
 // 2D row-major [rows, cols] 16-bit tensor with row stride ld (elements); box = [box_rows, 64 cols]

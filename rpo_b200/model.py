@@ -166,10 +166,6 @@ class Engine:
         """context rows (cls + patches) of the vision tower for `image` into activation slot `slot`"""
         self._stage(self.lib.rpo_forward_image_context, _lib.ptr(image), image_dtype_code, image.shape[0], int(slot))
 
-    def set_context_sms(self, n_sms):
-        """SM budget of `image_context` (0 = whole device): leaves SMs to the prompt-row chain on the other stream"""
-        _lib.check(self.lib.rpo_set_context_sms(self.handle, int(n_sms)))
-
     def image_prompts(self, img_prompt, slot):
         """prompt rows of the vision tower over the context already in `slot`; selects the slot for logits / backward"""
         self._stage(self.lib.rpo_forward_image_prompts, _lib.ptr(img_prompt.detach().contiguous()), int(slot))
@@ -331,9 +327,9 @@ class CustomCLIP(nn.Module):
         return self._shard
 
     def pipeline_images(self, slots=2):
-        """Two sets of vision-tower activations in the native handle (RpoConfig.image_slots) so that
-        runner.StepRunner(pipeline=True) can run the context rows of the next batch beside the prompt-row chain of
-        the current one.  Costs one more copy of the vision activations (~1.5 GB at ViT-B/16, batch 32)."""
+        """Two sets of vision-tower activations in the native handle (RpoConfig.image_slots) for the two-pass image
+        forward (rpo_forward_image_context / _prompts): the context rows of one batch can be computed into one slot
+        while another slot is in use.  Costs one more copy of the vision activations (~1.5 GB at ViT-B/16, batch 32)."""
         if int(slots) != self._image_slots:
             self._image_slots = int(slots)
             self._engine = None

@@ -27,13 +27,21 @@ class ClassShard:
         if not (world >= 1 and 0 <= rank < world):
             raise ValueError(f"rank {rank} / world {world}")
         self.n_cls, self.rank, self.world = n_cls, rank, world
-        self.per = -(-n_cls // world)  # classes per rank, the last non-empty rank may hold fewer
+        self.per = -(-n_cls // world)  # classes per rank, the last rank may hold fewer
         self.n_pad = self.per * world
         self.first = rank * self.per
         self.local = min(n_cls, self.first + self.per) - self.first
-        if self.local < 1:
-            raise ValueError(f"{n_cls} classes over {world} ranks in parts of {self.per} leave rank {rank} without a "
+        # The decision must be the same on EVERY rank (a rank that stays replicated while the others issue the
+        # collectives deadlocks them), so it depends on (n_cls, world) only, never on `rank`.
+        if not self.feasible(n_cls, world):
+            raise ValueError(f"{n_cls} classes over {world} ranks in parts of {self.per} leave a rank without a "
                              f"class: use fewer ranks for the text tower or do not shard it")
+
+    @staticmethod
+    def feasible(n_cls, world):
+        """True if every one of `world` ranks gets at least one class with parts of ceil(n_cls / world)."""
+        per = -(-int(n_cls) // int(world))
+        return per * (int(world) - 1) < int(n_cls)
 
     def __repr__(self):
         return f"ClassShard(classes [{self.first}, {self.first + self.local}) of {self.n_cls}, rank {self.rank}/{self.world})"

@@ -22,6 +22,15 @@ Deliberate differences from trainers/rpo.py (none changes a result):
     model the same number of times (training steps and evaluation batches alike).
   * PREC="amp": the reference keeps fp32 weights and autocasts the matmuls; here the fp32 engine runs
     (at least as precise as autocast) and the GradScaler is kept so the control flow is identical.
+  * Fast path (default; RPO_B200_FAST=0 switches it off).  With a plain torch SGD over the two prompt tensors and
+    PREC fp16 / fp32, `forward_backward` does not go through autograd and `optim.step()` at all: the batch goes
+    through `input_pipeline.BatchUploader` (pinned, double-buffered, asynchronous upload instead of the blocking
+    `.to(device)` of :318-323) and the whole step -- forward, CE, prompt-gradient backward, gradient exchange
+    between ranks, SGD(momentum, weight decay) -- is ONE CUDA-graph replay (`runner.StepRunner`).  The learning rate
+    is read from `optim.param_groups` every step (Dassl's scheduler keeps driving it) and fed to the graph through
+    a device scalar; the momentum lives in the runner and is exported into `optim.state` before checkpoints are
+    written.  The returned loss is read back asynchronously: step n reports the loss of step n-1 (RPO_B200_SYNC_LOSS=1
+    restores the reference's blocking `loss.item()` of the current step).
 
 Dassl is imported lazily: without it (this repository's test environment) the class is still
 importable over `object` so that its methods can be exercised with a stand-in base.
@@ -91,11 +100,12 @@ def maybe_shard_text(model, group=None):
         return None
     if dist.get_world_size(group) == 1:
         return None
-    try:
-        return model.shard_text(group=group)
-    except ValueError as e:  # fewer classes than ranks
-        print(f"text tower stays replicated: {e}")
+    from .text_shard import ClassShard
+    n_cls, world = model.text_x.shape[0], dist.get_world_size(group)
+    if not ClassShard.feasible(n_cls, world):  # same answer on every rank (depends on n_cls and world only)
+        print(f"text tower stays replicated: {n_cls} classes do not split over {world} ranks without an empty part")
         return None
+    return model.shard_text(group=group)
 
 
 class RPO(TrainerX):
@@ -128,7 +138,102 @@ class RPO(TrainerX):
         if os.environ.get("RPO_B200_DETECT_ANOMALY") == "1":
             torch.autograd.set_detect_anomaly(True)
 
+    # ---- fast path: uploader + one CUDA-graph replay per step (see the module text) -----------------------------
+    def fast_path_available(self):
+        """The fused step implements exactly torch.optim.SGD(momentum, dampening 0, L2 weight decay, no nesterov)
+        over the two prompt tensors; anything else keeps the reference-shaped autograd path."""
+        if os.environ.get("RPO_B200_FAST", "1") == "0" or getattr(self, "scaler", None) is not None:
+            return False
+        optim, model = self.optim, self.model
+        if type(optim) is not torch.optim.SGD or len(optim.param_groups) != 1:
+            return False
+        g = optim.param_groups[0]
+        pl = model.prompt_learner
+        if [id(p) for p in g["params"]] != [id(pl.text_prompt), id(pl.img_prompt)]:
+            return False
+        if g.get("nesterov") or g.get("dampening", 0) != 0 or g.get("maximize") or not pl.text_prompt.is_cuda:
+            return False
+        return os.environ.get("RPO_B200_DETECT_ANOMALY") != "1"
+
+    def _fast_state(self, batch_size, image_dtype):
+        st = getattr(self, "_fast", None)
+        if st is not None and st["B"] == batch_size and st["dtype"] == image_dtype:
+            return st
+        import torch.distributed as dist
+        from .input_pipeline import BatchUploader, LossReader
+        from .runner import StepRunner
+        g = self.optim.param_groups[0]
+        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        model = self.model
+        old = st["runner"] if st is not None else None
+        runner = StepRunner(model, batch_size, lr=g["lr"], momentum=g.get("momentum", 0.0),
+                            weight_decay=g.get("weight_decay", 0.0), world_size=world, image_dtype=image_dtype)
+        runner.prepare(warmup=2)
+        if old is not None:  # a different batch size mid-run: carry the optimiser state over
+            runner.mom_buf.copy_(old.mom_buf)
+            runner.first.copy_(old.first)
+        else:
+            self._import_momentum(runner)
+        st = {"B": batch_size, "dtype": image_dtype, "runner": runner,
+              "uploader": BatchUploader(model.w_mm.device, batch_size, model.arch.v_res, image_dtype),
+              "loss": LossReader(model.w_mm.device)}
+        self._fast = st
+        return st
+
+    def _momentum_views(self, runner):
+        pl = self.model.prompt_learner
+        nt = runner.eng.n_text
+        return [(pl.text_prompt, runner.mom_buf[:nt]), (pl.img_prompt, runner.mom_buf[nt:])]
+
+    def _import_momentum(self, runner):
+        """resuming from a checkpoint whose optimiser state holds momentum buffers"""
+        have = False
+        for p, view in self._momentum_views(runner):
+            buf = self.optim.state.get(p, {}).get("momentum_buffer")
+            if buf is not None:
+                view.copy_(buf.detach().reshape(-1).float())
+                have = True
+        if have:
+            runner.first.zero_()
+
+    def export_optimizer_state(self):
+        """Writes the runner's f32 momentum into `optim.state` (torch's layout), so that Dassl's save_model /
+        a later switch to the autograd path see the optimiser they expect."""
+        st = getattr(self, "_fast", None)
+        if st is None or int(st["runner"].first.item()) == 1:
+            return
+        for p, view in self._momentum_views(st["runner"]):
+            self.optim.state.setdefault(p, {})["momentum_buffer"] = view.view_as(p).to(p.dtype).clone()
+
+    def save_model(self, *args, **kwargs):  # Dassl TrainerBase.save_model: checkpoints carry optim.state_dict()
+        self.export_optimizer_state()
+        return super().save_model(*args, **kwargs)
+
+    def _forward_backward_fast(self, batch):
+        image, label = batch["img"], batch["label"]
+        st = self._fast_state(image.shape[0], image.dtype)
+        runner, up, lr_ = st["runner"], st["uploader"], st["loss"]
+        if image.is_cuda:  # already on the device (a custom loader): no staging
+            runner.image.copy_(image, non_blocking=True)
+            runner.label.copy_(label, non_blocking=True)
+        else:
+            ticket = up.submit(image, label)
+            img_d, lab_d = up.acquire(ticket)
+            runner.image.copy_(img_d, non_blocking=True)
+            runner.label.copy_(lab_d, non_blocking=True)
+            up.release(ticket)
+        runner.set_lr(self.optim.param_groups[0]["lr"])
+        runner.step()
+        lr_.push(runner.loss)
+        lag = 0 if os.environ.get("RPO_B200_SYNC_LOSS") == "1" else 1
+        loss_summary = {"loss": lr_.latest(lag)}
+        if (self.batch_idx + 1) == self.num_batches:
+            self.update_lr()
+        return loss_summary
+
     def forward_backward(self, batch):
+        if self.fast_path_available():
+            return self._forward_backward_fast(batch)
         image, label = self.parse_batch_train(batch)
         model, optim, scaler = self.model, self.optim, self.scaler
         loss = model(image, label)

@@ -24,8 +24,13 @@ def test_class_shard_partition():
         assert covered == list(range(n_cls))
         assert all(s.per == shards[0].per and s.n_pad == s.per * world >= n_cls for s in shards)
         assert all(1 <= s.local <= s.per for s in shards)
-    with pytest.raises(ValueError):  # parts of 2 leave ranks 5..7 empty
-        ClassShard(10, 5, 8)
+    # 10 classes over 8 ranks (e.g. EuroSAT on 8 GPUs): parts of 2 would leave ranks 5..7 empty.  The refusal must
+    # come from EVERY rank -- a rank that stays replicated while others issue the collectives deadlocks them.
+    for r in range(8):
+        with pytest.raises(ValueError):
+            ClassShard(10, r, 8)
+    assert not ClassShard.feasible(10, 8) and not ClassShard.feasible(5, 4) and ClassShard.feasible(8, 8)
+    assert ClassShard.feasible(100, 8) and ClassShard.feasible(13, 2) and not ClassShard.feasible(9, 8)
     with pytest.raises(ValueError):
         ClassShard(10, 2, 2)
 
@@ -130,12 +135,14 @@ def test_class_shard_partition_properties():
     def check(n_cls, world):
         per = -(-n_cls // world)
         empty_ranks = [r for r in range(world) if r * per >= n_cls]
-        nxt = 0
-        for r in range(world):
-            if r in empty_ranks:
+        assert ClassShard.feasible(n_cls, world) == (not empty_ranks)
+        if empty_ranks:  # the same (loud) answer on every rank, empty or not
+            for r in range(world):
                 with pytest.raises(ValueError):
                     ClassShard(n_cls, r, world)
-                continue
+            return
+        nxt = 0
+        for r in range(world):
             s = ClassShard(n_cls, r, world)
             assert s.first == nxt and s.per == per and s.n_pad == per * world and 1 <= s.local <= per
             assert s.slice == slice(s.first, s.first + s.local)

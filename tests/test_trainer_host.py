@@ -107,3 +107,47 @@ def test_maybe_shard_text_needs_opt_in_and_a_process_group(monkeypatch):
     assert trainer.maybe_shard_text(M()) is None
     monkeypatch.setenv("RPO_B200_SHARD_TEXT", "1")
     assert trainer.maybe_shard_text(M()) is None  # torch.distributed is not initialised here
+
+
+def _shard_decision_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["RPO_B200_SHARD_TEXT"] = "1"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class M:
+        def __init__(self, n_cls):
+            self.text_x = torch.zeros(n_cls, 77, 8)
+            self.called = False
+
+        def shard_text(self, group=None):
+            from rpo_b200.text_shard import ClassShard
+            self.called = True
+            return ClassShard(self.text_x.shape[0], dist.get_rank(group), dist.get_world_size(group))
+
+    got = {}
+    for n_cls in (3, 4, 10, 13):   # over 4 ranks: 3 -> infeasible, 4 -> 1 each, 10 -> 3,3,3,1, 13 -> 4,4,4,1
+        m = M(n_cls)
+        sh = trainer.maybe_shard_text(m)
+        got[n_cls] = None if sh is None else sh.local
+    torch.save(got, os.path.join(out, f"d{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_decision_is_the_same_on_every_rank(tmp_path):
+    """with fewer classes than needed to give every rank a part, ALL ranks must stay replicated (a
+    per-rank decision would leave some ranks inside all_gather / reduce_scatter and others outside: deadlock)."""
+    world = 4
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_shard_decision_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    got = [torch.load(tmp_path / f"d{r}.pt") for r in range(world)]
+    for n_cls in (3, 4, 10, 13):
+        sharded = [g[n_cls] is not None for g in got]
+        assert all(sharded) or not any(sharded), (n_cls, sharded)
+    assert all(g[3] is None for g in got)
+    assert [g[10] for g in got] == [3, 3, 3, 1] and [g[4] for g in got] == [1, 1, 1, 1]

@@ -1,9 +1,11 @@
-"""Per-kernel timings of the step's GEMM shapes and the attention kernels through the C ABI (CUDA events on the
-launching stream, buffers rotated so that consecutive launches do not hit L2).  Run on the GPU box:
+"""Per-kernel timings of the step's GEMM shapes, the attention kernels and LayerNorm through the C ABI (CUDA events
+on the launching stream, launches captured into one CUDA graph as the step is, buffers rotated so that consecutive
+launches do not hit L2).  Run on the GPU box:
 
-    python tools/kernel_bench.py [--prec fp16] [--tag note]
+    python tools/kernel_bench.py [--prec fp16] [--cublas] [--arch ViT-B/16] [--batch 32] [--K 24] [--classes 100]
 
-Prints one line per kernel: shape, microseconds, TFLOP/s or GB/s, fraction of the measured peak."""
+Prints one line per kernel: shape, microseconds, TFLOP/s or GB/s, fraction of the measured peak.  bench.py imports
+`bench_kernels` for its `roofline_kernels` list.  Algorithmic bytes / FLOPs per launch follow SURVEY.md 8(d)."""
 import argparse
 import json
 import os
@@ -15,26 +17,28 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from rpo_b200 import _lib  # noqa: E402
 
+ARCH_DIMS = {  # Dv, Hv, S (context rows), patch K extent (padded), Dt, Ht
+    "ViT-B/16": dict(Dv=768, S=197, pk=768, Dt=512),
+    "ViT-L/14": dict(Dv=1024, S=257, pk=640, Dt=768),
+}
+
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d["hbm_gbs"], d["bf16_tflops"]
-    return 6650.0, 1590.0
+        return d["hbm_gbs"], d["bf16_tflops"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
-USE_GRAPH = True
-
-
-def timeit(fn, iters=40, warm=5):
+def timeit(fn, iters=40, warm=5, use_graph=True):
     """Seconds per launch.  The `iters` launches are captured into ONE CUDA graph (as the training step is), so
     host-side costs -- ctypes, tensor-map encoding, launch -- are outside the measurement."""
     for i in range(warm):
         fn(i)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if USE_GRAPH:
+    if use_graph:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             for i in range(iters):
@@ -53,51 +57,48 @@ def timeit(fn, iters=40, warm=5):
     return e0.elapsed_time(e1) / iters * 1e-3
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--prec", default="fp16")
-    ap.add_argument("--tag", default="")
-    ap.add_argument("--cublas", action="store_true", help="also time torch.matmul (cuBLAS) on each GEMM shape")
-    ap.add_argument("--only", default="", help="comma list: gemm,attn,ln")
-    ap.add_argument("--no-dense", action="store_true", help="vision attention through the mma.sync kernel")
-    ap.add_argument("--no-graph", action="store_true", help="time eager launches (host-bound for short kernels)")
-    ap.add_argument("--nbuf", type=int, default=0, help="override the number of rotated buffers (1 = warm L2)")
-    a = ap.parse_args()
-    global USE_GRAPH
-    USE_GRAPH = not a.no_graph
-    dt = {"fp16": torch.float16, "bf16": torch.bfloat16}[a.prec]
-    lib = _lib.load()
-    dev = torch.device("cuda:0")
-    code = _lib.dtype_code(dt)
-    hbm, tf = peaks()
-    g = torch.Generator(device="cpu").manual_seed(0)
-    print(f"# kernel_bench {a.tag} prec={a.prec} peaks: {hbm:.0f} GB/s, {tf:.0f} TF/s (measured)")
-
+def gemm_shapes(arch, B, K, C, n_c=10):
+    d = ARCH_DIMS[arch]
+    Dv, S, pk, Dt = d["Dv"], d["S"], d["pk"], d["Dt"]
+    Mv, Mp, Mt = B * (S + K), B * K, C * K
     # (label, M, N, K, bias, act, residual, gelu_aux)
-    shapes = [
-        ("v.qkv", 6304, 2304, 768, 1, 0, 0, 0), ("v.q_prompt", 768, 768, 768, 1, 0, 0, 0),
-        ("v.out", 7072, 768, 768, 1, 0, 1, 0), ("v.fc", 7072, 3072, 768, 1, 1, 0, 0),
-        ("v.proj", 7072, 768, 3072, 1, 0, 1, 0), ("v.patch", 6272, 768, 768, 0, 0, 0, 0),
-        ("t.q", 2400, 512, 512, 1, 0, 0, 0), ("t.out", 2400, 512, 512, 1, 0, 1, 0),
-        ("t.fc", 2400, 2048, 512, 1, 1, 0, 0), ("t.proj", 2400, 512, 2048, 1, 0, 1, 0),
-        ("vb.dpre", 768, 3072, 768, 0, 0, 0, 1), ("vb.dh", 768, 768, 3072, 0, 0, 0, 0),
-        ("vb.sq", 768, 768, 768, 0, 0, 0, 0),
-        ("tb.dpre", 2400, 2048, 512, 0, 0, 0, 1), ("tb.dh", 2400, 512, 2048, 0, 0, 0, 0),
-        ("tb.sq", 2400, 512, 512, 0, 0, 0, 0),
+    return [
+        ("v.qkv", B * S, 3 * Dv, Dv, 1, 0, 0, 0), ("v.out", Mv, Dv, Dv, 1, 0, 1, 0), ("v.fc", Mv, 4 * Dv, Dv, 1, 1, 0, 0),
+        ("v.proj", Mv, Dv, 4 * Dv, 1, 0, 1, 0), ("v.patch", B * (S - 1), Dv, pk, 0, 0, 0, 0),
+        ("t.q", Mt, Dt, Dt, 1, 0, 0, 0), ("t.out", Mt, Dt, Dt, 1, 0, 1, 0), ("t.fc", Mt, 4 * Dt, Dt, 1, 1, 0, 0),
+        ("t.proj", Mt, Dt, 4 * Dt, 1, 0, 1, 0),
+        ("vb.dpre", Mp, 4 * Dv, Dv, 0, 0, 0, 1), ("vb.dh", Mp, Dv, 4 * Dv, 0, 0, 0, 0), ("vb.sq", Mp, Dv, Dv, 0, 0, 0, 0),
+        ("tb.dpre", Mt, 4 * Dt, Dt, 0, 0, 0, 1), ("tb.dh", Mt, Dt, 4 * Dt, 0, 0, 0, 0), ("tb.sq", Mt, Dt, Dt, 0, 0, 0, 0),
     ]
-    only = set(a.only.split(",")) if a.only else {"gemm", "attn", "ln"}
-    ws = torch.zeros(lib.rpo_gemm_workspace_bytes(), dtype=torch.uint8, device=dev)  # stream-K workspace (vision stream)
-    if "gemm" not in only:
-        shapes = []
-    for label, M, N, Kd, has_bias, act, has_res, has_aux in shapes:
+
+
+def bench_kernels(prec="fp16", arch="ViT-B/16", B=32, K=24, C=100, only=("gemm", "attn", "ln"), cublas=False,
+                  nbuf_override=0, dense=True, use_graph=True, gemm_labels=None, device="cuda:0"):
+    """Returns a list of dicts: kernel, shape, us, bound, achieved, peak, unit, frac (+ cublas_us for GEMMs)."""
+    dt = {"fp16": torch.float16, "bf16": torch.bfloat16}[prec]
+    lib = _lib.load()
+    dev = torch.device(device)
+    code = _lib.dtype_code(dt)
+    hbm, tf, _ = peaks()
+    g = torch.Generator(device=dev).manual_seed(0)
+    d = ARCH_DIMS[arch]
+    rows = []
+
+    def randn(*shape, scale=1.0):
+        return (torch.randn(*shape, generator=g, device=dev) * scale).to(dt)
+
+    ws = torch.zeros(lib.rpo_gemm_workspace_bytes(), dtype=torch.uint8, device=dev)
+    for label, M, N, Kd, has_bias, act, has_res, has_aux in (gemm_shapes(arch, B, K, C) if "gemm" in only else []):
+        if gemm_labels and label not in gemm_labels:
+            continue
         per = (M * Kd + N * Kd + M * N * (1 + has_res + has_aux)) * 2
-        nbuf = a.nbuf or max(2, min(12, int(300e6 // per) + 1))
-        A = [torch.randn(M, Kd, generator=g).to(dt).to(dev) for _ in range(nbuf)]
-        W = [(torch.randn(N, Kd, generator=g) * Kd ** -0.5).to(dt).to(dev) for _ in range(nbuf)]
+        nbuf = nbuf_override or max(2, min(12, int(300e6 // per) + 1))
+        A = [randn(M, Kd) for _ in range(nbuf)]
+        W = [randn(N, Kd, scale=Kd ** -0.5) for _ in range(nbuf)]
         Cm = [torch.empty(M, N, dtype=dt, device=dev) for _ in range(nbuf)]
         bias = torch.zeros(N, dtype=dt, device=dev) if has_bias else None
-        res = [torch.randn(M, N, generator=g).to(dt).to(dev) for _ in range(nbuf)] if has_res else None
-        aux = [torch.randn(M, N, generator=g).to(dt).to(dev) for _ in range(nbuf)] if has_aux else None
+        res = [randn(M, N) for _ in range(nbuf)] if has_res else None
+        aux = [randn(M, N) for _ in range(nbuf)] if has_aux else None
 
         def fn(i):
             j = i % nbuf
@@ -107,72 +108,122 @@ def main():
                                                 ws.data_ptr() if label.startswith("v.") else None,
                                                 _lib.stream_ptr(dev)))
 
-        t = timeit(fn)
+        t = timeit(fn, use_graph=use_graph)
         fl = 2.0 * M * N * Kd
         # library reference for the same contraction (no epilogue): torch.matmul -> cuBLAS
-        tl = timeit(lambda i: torch.matmul(A[i % nbuf], W[i % nbuf].t(), out=Cm[i % nbuf])) if a.cublas else float("nan")
-        print(f"gemm {label:10s} M={M:5d} N={N:5d} K={Kd:5d}  {t * 1e6:8.2f} us  {fl / t / 1e12:7.1f} TF/s  "
-              f"{fl / t / 1e12 / tf:5.1%} of cuBLAS burst   [cuBLAS same shape: {tl * 1e6:7.2f} us]")
+        tl = timeit(lambda i: torch.matmul(A[i % nbuf], W[i % nbuf].t(), out=Cm[i % nbuf]), use_graph=use_graph) \
+            if cublas else None
+        rows.append(dict(kernel=f"gemm {label}", shape=f"M={M} N={N} K={Kd}", us=t * 1e6, bound="tensor",
+                         achieved=fl / t / 1e12, peak=tf, unit="TFLOP/s", frac=fl / t / 1e12 / tf, flops=fl,
+                         cublas_us=tl * 1e6 if tl else None))
         del A, W, Cm, res, aux
 
     # attention: vision forward (all rows), vision backward (prompt rows), text prompt-only forward/backward
-    for label, G, H, K, n, do_ctx in ([("v.attn_fwd", 32, 12, 24, 197, 1), ("t.attn_fwd", 100, 8, 24, 10, 0)]
-                                      if "attn" in only else []):
+    attn_cases = [("v.attn", B, d["Dv"] // 64, K, d["S"], 1), ("t.attn", C, d["Dt"] // 64, K, 10, 0)]
+    for label, G, H, Kp, n, do_ctx in (attn_cases if "attn" in only else []):
         D = H * 64
-        L = (n if do_ctx else 0) + K
-        nbuf = a.nbuf or 10
-        qkv = [torch.randn(G * n, 3 * D, generator=g).to(dt).to(dev) for _ in range(nbuf)]
-        qp = [torch.randn(G * K, D, generator=g).to(dt).to(dev) for _ in range(nbuf)]
+        L = (n if do_ctx else 0) + Kp
+        per = (G * n * 3 * D + G * Kp * D * 3 + G * n * D) * 2
+        nbuf = nbuf_override or max(2, min(10, int(450e6 // per) + 1))
+        qkv = [randn(G * n, 3 * D) for _ in range(nbuf)]
+        qp = [randn(G * Kp, D) for _ in range(nbuf)]
         oc = [torch.empty(G * n, D, dtype=dt, device=dev) for _ in range(nbuf)]
-        op = [torch.empty(G * K, D, dtype=dt, device=dev) for _ in range(nbuf)]
-        dq = [torch.empty(G * K, D, dtype=dt, device=dev) for _ in range(nbuf)]
+        op = [torch.empty(G * Kp, D, dtype=dt, device=dev) for _ in range(nbuf)]
+        dq = [torch.empty(G * Kp, D, dtype=dt, device=dev) for _ in range(nbuf)]
         off = torch.arange(0, (G + 1) * n, n, dtype=torch.int32, device=dev)
-
-        dense = do_ctx and not a.no_dense
+        use_dense = bool(do_ctx and dense)
 
         def fwd(i):
             j = i % nbuf
-            if dense:
+            if use_dense:
                 _lib.check(lib.rpo_ro_attention_fwd_dense(qkv[j].data_ptr(), qp[j].data_ptr(), oc[j].data_ptr(),
-                                                          op[j].data_ptr(), G, n, K, H, code, _lib.stream_ptr(dev)))
+                                                          op[j].data_ptr(), G, n, Kp, H, code, _lib.stream_ptr(dev)))
             else:
                 _lib.check(lib.rpo_ro_attention_fwd(qkv[j].data_ptr(), qp[j].data_ptr(), oc[j].data_ptr(),
-                                                    op[j].data_ptr(), off.data_ptr(), G, K, H, n, 0, do_ctx, code,
+                                                    op[j].data_ptr(), off.data_ptr(), G, Kp, H, n, 0, do_ctx, code,
                                                     _lib.stream_ptr(dev)))
 
         def bwd(i):
             j = i % nbuf
             _lib.check(lib.rpo_ro_attention_bwd(qkv[j].data_ptr(), qp[j].data_ptr(), op[j].data_ptr(),
-                                                qp[(j + 1) % nbuf].data_ptr(), dq[j].data_ptr(), off.data_ptr(), G, K, H,
-                                                n, code, _lib.stream_ptr(dev)))
+                                                qp[(j + 1) % nbuf].data_ptr(), dq[j].data_ptr(), off.data_ptr(), G, Kp,
+                                                H, n, code, _lib.stream_ptr(dev)))
 
-        t = timeit(fwd)
+        t = timeit(fwd, use_graph=use_graph)
         by = 2 * (2 * L + 2 * n) * 64 * H * G
         fl = 4.0 * L * n * 64 * H * G
-        print(f"attn {label:10s} G={G} H={H} L={L} S={n}  {t * 1e6:8.2f} us  {by / t / 1e9:7.1f} GB/s "
-              f"({by / t / 1e9 / hbm:5.1%} of copy peak)  {fl / t / 1e12:6.1f} TF/s")
-        t = timeit(bwd)
-        by = 2 * (3 * K + 2 * n) * 64 * H * G
-        print(f"attn {label.replace('fwd', 'bwd'):10s} G={G} H={H} K={K} S={n}  {t * 1e6:8.2f} us  {by / t / 1e9:7.1f} GB/s "
-              f"({by / t / 1e9 / hbm:5.1%} of copy peak)")
+        rows.append(dict(kernel=f"attn {label}_fwd" + ("" if not do_ctx else (" (tcgen05)" if use_dense else " (mma.sync)")),
+                         shape=f"G={G} H={H} L={L} S={n}", us=t * 1e6, bound="hbm", achieved=by / t / 1e9, peak=hbm,
+                         unit="GB/s", frac=by / t / 1e9 / hbm, bytes=by, flops=fl, tensor_tflops=fl / t / 1e12))
+        t = timeit(bwd, use_graph=use_graph)
+        by = 2 * (3 * Kp + 2 * n) * 64 * H * G
+        rows.append(dict(kernel=f"attn {label}_bwd", shape=f"G={G} H={H} K={Kp} S={n}", us=t * 1e6, bound="hbm",
+                         achieved=by / t / 1e9, peak=hbm, unit="GB/s", frac=by / t / 1e9 / hbm, bytes=by))
         del qkv, qp, oc, op, dq
 
-    # LayerNorm forward
-    for rows, D in ([(7072, 768), (2400, 512), (768, 768)] if "ln" in only else []):
-        nbuf = a.nbuf or 12
-        x = [torch.randn(rows, D, generator=g).to(dt).to(dev) for _ in range(nbuf)]
-        y = [torch.empty(rows, D, dtype=dt, device=dev) for _ in range(nbuf)]
+    # LayerNorm forward / backward
+    ln_cases = [(B * (d["S"] + K), d["Dv"]), (C * K, d["Dt"]), (B * K, d["Dv"])]
+    for nrows, D in (ln_cases if "ln" in only else []):
+        nbuf = nbuf_override or 12
+        x = [randn(nrows, D) for _ in range(nbuf)]
+        y = [torch.empty(nrows, D, dtype=dt, device=dev) for _ in range(nbuf)]
         w = torch.ones(D, dtype=torch.float32, device=dev)
         b = torch.zeros(D, dtype=torch.float32, device=dev)
 
         def ln(i):
             j = i % nbuf
-            _lib.check(lib.rpo_layernorm_fwd(x[j].data_ptr(), w.data_ptr(), b.data_ptr(), y[j].data_ptr(), rows, D,
+            _lib.check(lib.rpo_layernorm_fwd(x[j].data_ptr(), w.data_ptr(), b.data_ptr(), y[j].data_ptr(), nrows, D,
                                              code, _lib.stream_ptr(dev)))
 
-        t = timeit(ln)
-        by = 2 * rows * D * 2
-        print(f"ln_fwd rows={rows} D={D}  {t * 1e6:8.2f} us  {by / t / 1e9:7.1f} GB/s ({by / t / 1e9 / hbm:5.1%})")
+        def lnb(i):
+            j = i % nbuf
+            _lib.check(lib.rpo_layernorm_bwd(x[j].data_ptr(), x[(j + 1) % nbuf].data_ptr(), w.data_ptr(),
+                                             x[(j + 2) % nbuf].data_ptr(), y[j].data_ptr(), nrows, D, code,
+                                             _lib.stream_ptr(dev)))
+
+        t = timeit(ln, use_graph=use_graph)
+        by = 2 * nrows * D * 2
+        rows.append(dict(kernel="ln_fwd", shape=f"rows={nrows} D={D}", us=t * 1e6, bound="hbm", achieved=by / t / 1e9,
+                         peak=hbm, unit="GB/s", frac=by / t / 1e9 / hbm, bytes=by))
+        if nrows != ln_cases[0][0]:  # the backward only ever runs over prompt rows
+            t = timeit(lnb, use_graph=use_graph)
+            by = 4 * nrows * D * 2  # dy, x, residual gradient in; dx out
+            rows.append(dict(kernel="ln_bwd", shape=f"rows={nrows} D={D}", us=t * 1e6, bound="hbm",
+                             achieved=by / t / 1e9, peak=hbm, unit="GB/s", frac=by / t / 1e9 / hbm, bytes=by))
+    return rows
+
+
+def format_row(r):
+    s = f"{r['kernel']:28s} {r['shape']:28s} {r['us']:8.2f} us  {r['achieved']:8.1f} {r['unit']:8s} {r['frac']:6.1%} of peak"
+    if r.get("cublas_us"):
+        s += f"   [cuBLAS same shape: {r['cublas_us']:7.2f} us -> {r['cublas_us'] / r['us']:.2f}x]"
+    if r.get("tensor_tflops"):
+        s += f"   {r['tensor_tflops']:6.1f} TF/s"
+    return s
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--prec", default="fp16")
+    ap.add_argument("--arch", default="ViT-B/16")
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--K", type=int, default=24)
+    ap.add_argument("--classes", type=int, default=100)
+    ap.add_argument("--tag", default="")
+    ap.add_argument("--cublas", action="store_true", help="also time torch.matmul (cuBLAS) on each GEMM shape")
+    ap.add_argument("--only", default="", help="comma list: gemm,attn,ln")
+    ap.add_argument("--gemms", default="", help="comma list of GEMM labels (v.qkv, t.q, ...)")
+    ap.add_argument("--no-dense", action="store_true", help="vision attention through the mma.sync kernel")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches (host-bound for short kernels)")
+    ap.add_argument("--nbuf", type=int, default=0, help="override the number of rotated buffers (1 = warm L2)")
+    a = ap.parse_args()
+    hbm, tf, src = peaks()
+    print(f"# kernel_bench {a.tag} prec={a.prec} arch={a.arch} B={a.batch} K={a.K} C={a.classes} "
+          f"peaks: {hbm:.0f} GB/s, {tf:.0f} TF/s ({src})")
+    only = tuple(a.only.split(",")) if a.only else ("gemm", "attn", "ln")
+    for r in bench_kernels(a.prec, a.arch, a.batch, a.K, a.classes, only, a.cublas, a.nbuf, not a.no_dense,
+                           not a.no_graph, set(a.gemms.split(",")) if a.gemms else None):
+        print(format_row(r), flush=True)
 
 
 if __name__ == "__main__":
