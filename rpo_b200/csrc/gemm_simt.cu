@@ -52,6 +52,10 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const T *__restrict__ A,
     }
     __syncthreads();
     if (k0 + SBK < Kd) fetch(k0 + SBK);
+    // blocked summation: the 16 products of a slab are summed on their own and then added to the running sum, so
+    // the rounding error grows with K/16 + 16 terms instead of K (the fp32 parity bar is 1e-5 on gradients that
+    // pass through a dozen K = 768 .. 3072 contractions)
+    float part[4][4];
 #pragma unroll
     for (int k = 0; k < SBK; ++k) {
       float4 a = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
@@ -61,8 +65,12 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const T *__restrict__ A,
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) part[i][j] = k == 0 ? av[i] * bv[j] : fmaf(av[i], bv[j], part[i][j]);
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] += part[i][j];
     __syncthreads();
   }
 #pragma unroll
