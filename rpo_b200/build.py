@@ -19,13 +19,18 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
 
+def _flags():
+    """RPO_DIAG=1: a diagnostics build (phase-trace hooks of the tools/ scripts).  Release builds carry none of it."""
+    return NVCC_FLAGS + (["-DRPO_DIAG"] if os.environ.get("RPO_DIAG") == "1" else [])
+
+
 def _nvcc():
     return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 
 
 def _digest():
     h = hashlib.sha256()
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(_flags()).encode())
     for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
         for name in sorted(os.listdir(root)):
             if name.endswith((".cu", ".cuh", ".h")):
@@ -47,7 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [_nvcc(), *_flags(), "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -1,27 +1,27 @@
 // tcgen05 form of the read-only masked attention forward for the vision tower (every group has the same
 // number n of context rows, no causal mask): clip/model.py:186 under visual_mask of trainers/rpo.py:153-159.
+// The metric's masked-attention kernel.
 //
-// One CTA = one (image, head, 128-query tile).  The query tile holds context rows and -- in the last
-// tile -- the K prompt rows right behind them; keys / values are the n context rows only (the mask).
-//   warp 0, one thread : TMA (cp.async.bulk.tensor, 128B swizzle) of the Q tile, K and V of the head
-//                        straight out of the [rows, 3D] q|k|v matrix and the [G*K, D] prompt-q matrix;
-//                        S = Q K^T   as 4 x tcgen05.mma (M=128, N=n16, K=16), f32 accumulator in TMEM;
-//                        O = P V     as n16/16 x tcgen05.mma (M=128, N=64, K=16): A = P from shared
-//                        memory (K-major, 32B swizzle, one 128x16 block per MMA), B = V as loaded
-//                        (keys x head-dim rows = MN-major operand, no transpose pass), accumulator
-//                        over the TMEM columns of the consumed S.
-//   warps 1..8         : softmax, TWO threads per query row (TMEM lane; warps w and w+4 share a lane
-//                        quarter and split the keys 7 : 6 in 16-key blocks): pass 1 reads S for the row
-//                        maximum (halves exchanged through shared memory), pass 2 re-reads it,
-//                        p = ex2((s - max) / 8 log2 e), accumulates the f32 row sum, rounds p to the
-//                        dtype and stores it as the A operand of P V.  TMEM loads are software
-//                        pipelined (block b+1 in flight while block b is processed).
-//                        epilogue: each thread takes 32 of the row's 64 output columns from TMEM,
-//                        times 1/sum, 64 contiguous bytes to global.
-// No shuffles and no ldmatrix: the tensor core reads operands from shared memory itself, so the SM's
-// issue slots carry only the softmax (the mma.sync kernel in attention_mma.cu is issue-bound: ~3400
-// instructions per 16 query rows).  Shared memory: K 26 KB + V 26 KB + max(Q 16 KB, P 52 KB) = 104 KB and
-// 256 TMEM columns, so two CTAs share an SM and hide each other's load / MMA latency.
+// One CTA per SM walks a contiguous range of (image, head, 128-query tile) work items.  The query rows of an (image,
+// head) are its n context rows followed by its K prompt rows (the last tile holds both); keys / values are the n
+// context rows only -- that IS the mask.  K and V of a head are loaded once and serve all its query tiles.
+//
+//   warp 0 (one thread)   TMA producer: K | V of the next (image, head) into a 2-deep buffer, Q tiles into a ring
+//                         (cp.async.bulk.tensor, 128B swizzle, straight out of the [rows, 3D] q|k|v matrix and the
+//                         [G*K, D] prompt-q matrix).
+//   warp 1 (one thread)   MMA issuer: S = Q K^T (M=128, N=n16 in one or two instructions per 16-wide k step, f32 in
+//                         TMEM slot i%SLOTS), and -- one tile behind -- O = P V with P read FROM TENSOR MEMORY
+//                         (tcgen05.mma, A operand in TMEM) and V consumed as loaded (MN-major B operand).
+//   warps 4..11           softmax, two threads per query row (TMEM lane): ONE pass over S -- the thread's half of the
+//                         row is loaded into registers, row maximum (halves exchanged through shared memory),
+//                         p = ex2((s - max) / 8 log2 e), f32 row sum, p rounded to the dtype and written back to
+//                         tensor memory over the dead S columns (tcgen05.st) as the A operand of P V.
+//   warps 12..15          epilogue, one thread per query row: O out of TMEM, times 1/sum, 128 contiguous bytes to
+//                         global; frees the slot for the S of two tiles later.
+// With two TMEM slots (n16 <= 256: ViT-B/16) the S MMA of tile i+1 and the P V MMA / epilogue of tile i-1 run beside
+// the softmax of tile i; the exponentials (MUFU) are the only serial resource.  n16 > 256 (ViT-L/14: 257 keys) uses one
+// 512-column slot and two N blocks per S.
+// Registers: the three roles re-partition the register file with setmaxnreg (softmax threads hold up to 9 x 16 scores).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -35,10 +35,26 @@ using namespace tc;
 
 static constexpr int HD = 64;
 static constexpr int ROW_BYTES = HD * 2;
-static constexpr int QT = 128;  // query rows per CTA = UMMA M
-static constexpr int SM_WARPS = 8;  // softmax warps
-static constexpr int THREADS = 32 + SM_WARPS * 32;
-static constexpr int TMEM_COLS = 256;
+static constexpr int QT = 128;                 // query rows per tile = UMMA M
+static constexpr int Q_TILE_BYTES = QT * ROW_BYTES;
+static constexpr int PROD_WARPS = 4, SM_WARPS = 16, EPI_WARPS = 4;
+static constexpr int PARTS = SM_WARPS / 4;  // softmax threads per query row: each takes a quarter of the key blocks
+static constexpr int THREADS = 32 * (PROD_WARPS + SM_WARPS + EPI_WARPS);
+static constexpr int TMEM_COLS = 512;
+// The CTA is launched with 80 registers per thread (768 threads); setmaxnreg moves registers between the roles. What
+// the softmax warps gain must come out of the CTA's own pool, i.e. out of what the other roles give back:
+// 512 x (104 - 80) = 128 x (80 - 24) + 128 x (80 - 40).
+// 512 x (S - 80) = 128 x (80 - P) + 128 x (80 - E):  4 blocks per softmax thread (ViT-B/16): S 96, P 56, E 40;
+// 5 blocks (ViT-L/14): S 104, P 24, E 40.
+static constexpr int REGS_EPI = 40;
+template <int MAXB>
+struct Regs {
+  static constexpr int SOFTMAX = MAXB <= 4 ? 96 : 104;
+  static constexpr int PROD = MAXB <= 4 ? 56 : 24;
+};
+static constexpr int MAX_Q_RING = 4;
+static constexpr int MAX_ROUNDS = 5;            // key blocks per softmax thread, at most
+static constexpr int KV_RING = 3;               // K and V tiles rotate through three buffers (see the kernel)
 static constexpr int P_BLOCK_BYTES = QT * 32;  // one 128 x 16 block of P, 32-byte rows
 
 // K-major operand with 32-byte rows (16 x 16-bit = one UMMA K step), 32B swizzle, 8-row groups 256 B apart
@@ -87,73 +103,154 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
                :
                : "memory");
 }
-// packed f32x2 arithmetic (sm_100: FFMA2 / FADD2, two lanes per issue slot): (a, b) = (a, b) * s + o ; (a, b) += (c, d)
-__device__ __forceinline__ void ffma2(float &a, float &b, float s, float o) {
-  asm("{ .reg .b64 x, y, z; mov.b64 x, {%0, %1}; mov.b64 y, {%2, %2}; mov.b64 z, {%3, %3}; fma.rn.f32x2 x, x, y, z; "
-      "mov.b64 {%0, %1}, x; }"
-      : "+f"(a), "+f"(b)
-      : "f"(s), "f"(o));
+// explicit shared-space accesses with 32-bit addresses (a generic pointer into the dynamic shared memory makes the
+// compiler emit generic ST.E / LD.E and carry 64-bit addresses through the softmax loop)
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
-__device__ __forceinline__ void fadd2(float &a, float &b, float c, float d) {
-  asm("{ .reg .b64 x, y; mov.b64 x, {%0, %1}; mov.b64 y, {%2, %3}; add.rn.f32x2 x, x, y; mov.b64 {%0, %1}, x; }"
-      : "+f"(a), "+f"(b)
-      : "f"(c), "f"(d));
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
-__device__ __forceinline__ void pair_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+// named barrier of the PARTS warps that share a TMEM lane quarter
+__device__ __forceinline__ void quad_bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(PARTS * 32) : "memory"); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
+#ifdef RPO_DIAG
+__device__ int g_attn_abl = 0;  // ablation bits (timing experiments only: results are wrong)
+// phase timestamps of CTA 0 (tools/attn_trace.py): trace[tile * 16 + event] = SM clock
+__device__ long long *g_attn_trace = nullptr;
+#define ATTN_TRACE(j, ev)                                                                  \
+  do {                                                                                     \
+    if (blockIdx.x == 0 && trace_buf && (j) < 64) trace_buf[(j) * 16 + (ev)] = clock64(); \
+  } while (0)
+#else
+#define ATTN_TRACE(j, ev) \
+  do {                    \
+  } while (0)
+#endif
 
 struct Geo {
   int n;            // context rows (keys) per group
   int n16;          // keys rounded up to the UMMA K step
+  int nblk;         // n16 / 16
   int K;            // prompt rows per group
   int prompt_tile;  // query tile that holds the prompt rows ...
   int prompt_row;   // ... starting at this row of the tile (== context rows in that tile)
   int H;
   int tiles;        // query tiles per (group, head)
-  int phase_delay;  // SM clocks the second CTA of an SM holds back its first loads (0: none), see the kernel
-  int flags;        // bit 0: packed f32x2 arithmetic in the probability pass
+  int q_ring;       // Q tile buffers
+  int n_first;      // keys of the first N block of S (the second holds n16 - n_first; 0 columns if n16 <= 256)
 };
 
-template <typename T>
-__global__ void __launch_bounds__(THREADS, 2)
+struct Item {
+  int unit, t, h, g, c_rows, p_rows;
+};
+__device__ __forceinline__ Item item_of(const Geo &geo, int id) {
+  Item it;
+  it.unit = id / geo.tiles;
+  it.t = id - it.unit * geo.tiles;
+  it.h = it.unit % geo.H;
+  it.g = it.unit / geo.H;
+  it.c_rows = min(max(geo.n - it.t * QT, 0), QT);     // context query rows of this tile
+  it.p_rows = (it.t == geo.prompt_tile) ? geo.K : 0;   // prompt query rows, right behind them
+  return it;
+}
+
+// the next work item without divisions (the loops of the softmax / epilogue warps run once per tile)
+__device__ __forceinline__ void advance(const Geo &geo, Item &it) {
+  if (++it.t == geo.tiles) {
+    it.t = 0;
+    ++it.unit;
+    if (++it.h == geo.H) {
+      it.h = 0;
+      ++it.g;
+    }
+  }
+  it.c_rows = min(max(geo.n - it.t * QT, 0), QT);
+  it.p_rows = (it.t == geo.prompt_tile) ? geo.K : 0;
+}
+
+// MAXB: 16-key blocks a softmax thread keeps in registers (>= ceil(nblk / PARTS)); SLOTS: S slots in tensor memory
+template <typename T, int MAXB, int SLOTS>
+__global__ void __launch_bounds__(THREADS, 1)
     ro_attn_fwd_tc(const __grid_constant__ CUtensorMap map_full,   // q|k|v matrix, box 64 x 128
                    const __grid_constant__ CUtensorMap map_kvt,    // q|k|v matrix, box 64 x (n16 % 128)
                    const __grid_constant__ CUtensorMap map_qt,     // q|k|v matrix, box 64 x (n % 128)
                    const __grid_constant__ CUtensorMap map_prompt, // prompt-q matrix, box 64 x K
-                   T *__restrict__ out_ctx, T *__restrict__ out_prompt, Geo geo, int num_items, long long *trace) {
+                   T *__restrict__ out_ctx, T *__restrict__ out_prompt, Geo geo, int total_items) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int n = geo.n, n16 = geo.n16, K = geo.K, H = geo.H;
+  // tensor memory: S slot s at columns [s * SLOT_COLS, ...), O in the last 64 columns
+  constexpr int SLOT_COLS = SLOTS == 2 ? 224 : 0;
+  constexpr uint32_t O_COL = TMEM_COLS - HD;
+  const int n = geo.n, n16 = geo.n16, K = geo.K, H = geo.H, NQ = geo.q_ring;
   const int D = H * HD;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kv_bytes = n16 * ROW_BYTES;
-  const int p_bytes = (n16 >> 4) * P_BLOCK_BYTES;
-  const int qp_bytes = p_bytes > QT * ROW_BYTES ? p_bytes : QT * ROW_BYTES;
-  const uint32_t Ks = smem_u32(smem), Vs = Ks + kv_bytes, QPs = Vs + kv_bytes;
-  uint8_t *QP_gen = smem + 2 * kv_bytes;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * kv_bytes + qp_bytes);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 7);
-  float *red_max = reinterpret_cast<float *>(bars + 8);  // [2][QT]
-  float *red_sum = red_max + 2 * QT;                      // [2][QT]
-  // one phase of every barrier per work item: K landed, Q landed, V landed, S ready, P stored, O ready, O read
-  const uint32_t bar_k = smem_u32(bars), bar_q = bar_k + 8, bar_v = bar_k + 16, bar_s = bar_k + 24, bar_p = bar_k + 32,
-                 bar_o = bar_k + 40, bar_e = bar_k + 48;
-  const int tiles = geo.tiles;
-  // phase timestamps of the first item of each CTA (tuning aid, RPO_ATTN_TRACE): [cta][8] SM clock values
-  long long *tr = trace ? trace + (size_t)blockIdx.x * 8 : nullptr;
-  if (tr && threadIdx.x == 0) tr[0] = clock64();
+  // shared memory: [K|V ring of 3 | P | Q ring | barriers | row maxima | row sums]
+  const uint32_t kv_base = smem_u32(smem);
+  const uint32_t p_base = kv_base + KV_RING * kv_bytes;
+  const int p_bytes = geo.nblk * P_BLOCK_BYTES;
+  const uint32_t q_base = p_base + p_bytes;
+  uint8_t *tail = smem + KV_RING * kv_bytes + p_bytes + NQ * Q_TILE_BYTES;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(tail);
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int idx) { return bar0 + 8u * idx; };
+  // K or V landed / its ring entry free again; Q landed / Q slot free; S complete / S in registers (slot free);
+  // P stored / P consumed; O complete / O read
+  // (P consumed: one barrier per ROUND of the P V issue order, see the P V issuer)
+  constexpr int B_KVFULL = 0, B_KVFREE = 3, B_QFULL = 6, B_QFREE = 10, B_SFULL = 14, B_SFREE = 16, B_PFULL = 18,
+                B_OFULL = 19, B_OFREE = 20, B_PFREE = 21, N_BARS = 21 + MAX_ROUNDS;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + N_BARS);
+  const uint32_t red_max = smem_u32(bars + N_BARS + 1);        // f32 [2][PARTS][QT]  (tile parity, key part, row)
+  const uint32_t red_sum = red_max + 2 * PARTS * QT * 4;        // f32 [4][PARTS][QT]  (tile & 3, key part, row)
+  uint8_t *pv_order = reinterpret_cast<uint8_t *>(bars + N_BARS + 1) + 6 * PARTS * QT * 4;  // [32] issue order of P V
+
+  // this CTA's contiguous range of work items: consecutive tiles of an (image, head) share its K / V
+  const int item0 = (int)((long long)total_items * blockIdx.x / gridDim.x);
+  const int item1 = (int)((long long)total_items * (blockIdx.x + 1) / gridDim.x);
+  const int count = item1 - item0;
+#ifdef RPO_DIAG
+  long long *const trace_buf = g_attn_trace;
+  const int abl = g_attn_abl;
+  if (threadIdx.x == 0) ATTN_TRACE(0, 12);
+#else
+  constexpr int abl = 0;
+#endif
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_full)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_kvt)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_qt)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_prompt)) : "memory");
-    mbar_init(bar_k, 1);
-    mbar_init(bar_q, 1);
-    mbar_init(bar_v, 1);
-    mbar_init(bar_s, 1);
-    mbar_init(bar_p, SM_WARPS);
-    mbar_init(bar_o, 1);
-    mbar_init(bar_e, SM_WARPS);
+    for (int i = 0; i < KV_RING; ++i) {
+      mbar_init(BAR(B_KVFULL + i), 1);
+      mbar_init(BAR(B_KVFREE + i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(BAR(B_SFULL + i), 1);
+      mbar_init(BAR(B_SFREE + i), SM_WARPS);
+    }
+    mbar_init(BAR(B_PFULL), SM_WARPS);
+    for (int i = 0; i < MAX_ROUNDS; ++i) mbar_init(BAR(B_PFREE + i), 1);
+    mbar_init(BAR(B_OFULL), 1);
+    mbar_init(BAR(B_OFREE), EPI_WARPS);
+    for (int i = 0; i < MAX_Q_RING; ++i) {
+      mbar_init(BAR(B_QFULL + i), 1);
+      mbar_init(BAR(B_QFREE + i), 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -166,241 +263,346 @@ __global__ void __launch_bounds__(THREADS, 2)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_trigger();
-  if (tr && threadIdx.x == 0) tr[1] = clock64();
+  if (threadIdx.x == 0) ATTN_TRACE(0, 13);
 
-  // work items: (query tile, head, image), tile fastest so that the two tiles of a head run side by side
-  // on neighbouring CTAs and share K/V through L2
-  struct Item {
-    int t, h, g, c_rows, p_rows;
-  };
-  auto item_of = [&](int id) {
-    Item it;
-    it.t = id % tiles;
-    it.h = (id / tiles) % H;
-    it.g = id / (tiles * H);
-    it.c_rows = min(max(n - it.t * QT, 0), QT);       // context query rows of this tile
-    it.p_rows = (it.t == geo.prompt_tile) ? K : 0;     // prompt query rows, right behind them
-    return it;
-  };
-
-  if (warp == 0) {
-    if (lane == 0) {
-      auto load_k = [&](const Item &it) {
-        mbar_arrive_expect_tx(bar_k, (uint32_t)kv_bytes);
-        for (int r = 0; r < n16; r += 128)
-          tma_load_2d(Ks + r * ROW_BYTES, (n16 - r >= 128) ? &map_full : &map_kvt, bar_k, D + it.h * HD, it.g * n + r);
-      };
-      auto load_qv = [&](const Item &it) {
-        mbar_arrive_expect_tx(bar_q, (uint32_t)((it.c_rows + it.p_rows) * ROW_BYTES));
-        if (it.c_rows == QT)
-          tma_load_2d(QPs, &map_full, bar_q, it.h * HD, it.g * n + it.t * QT);
-        else if (it.c_rows > 0)
-          tma_load_2d(QPs, &map_qt, bar_q, it.h * HD, it.g * n + it.t * QT);
-        if (it.p_rows > 0) tma_load_2d(QPs + geo.prompt_row * ROW_BYTES, &map_prompt, bar_q, it.h * HD, it.g * K);
-        mbar_arrive_expect_tx(bar_v, (uint32_t)kv_bytes);
-        for (int r = 0; r < n16; r += 128)
-          tma_load_2d(Vs + r * ROW_BYTES, (n16 - r >= 128) ? &map_full : &map_kvt, bar_v, 2 * D + it.h * HD, it.g * n + r);
-      };
-      const uint32_t fmt = Num<T>::dtype == RPO_BF16 ? 1u : 0u;
-      const uint32_t idesc_s = make_idesc((int)fmt, QT, n16);
-      const uint32_t idesc_o = make_idesc((int)fmt, QT, HD) | (1u << 16);  // B (= V) is MN-major
-      const int nsteps = n16 >> 4;
+  // unit (= image, head) bookkeeping of tile j of this CTA: index of its unit within the range, first / last tile of
+  // that unit inside the range.  K of unit u lives in ring entry (2u) % 3, V in (2u + 1) % 3: V of unit u+1 takes over
+  // the entry of K of unit u (dead after the unit's last S), K of unit u+2 the entry of V of unit u.
+  const int tiles = geo.tiles;
+  const int unit0 = item0 / tiles;
+  auto unit_idx = [&](int j) { return (item0 + j) / tiles - unit0; };
+  auto first_of_unit = [&](int j) { return j == 0 || (item0 + j) % tiles == 0; };
+  auto last_of_unit = [&](int j) { return j + 1 == count || (item0 + j + 1) % tiles == 0; };
+  // the c-th use (c = 0, 1, ...) of ring entry e = c-th element of {2u, 2u+1 : ...} congruent to e: element index x
+  // (x = 2u for K, 2u + 1 for V) is use number x / 3 of entry x % 3
+  if (warp < PROD_WARPS) {
+    setmaxnreg_dec<Regs<MAXB>::PROD>();
+    if (warp == 0 && lane == 0) {
+      // ===== TMA producer =====
       pdl_wait();
-      // Two CTAs share an SM and would otherwise run in lockstep -- both in the MUFU-bound probability pass at the
-      // same time, both waiting on the tensor core at the same time.  The CTA that got the upper half of the SM's
-      // tensor memory starts late by a fraction of an item so that one CTA's exponentials run beside the other's
-      // MMA / row-maximum / epilogue phases.
-      if (geo.phase_delay > 0 && (tmem_base & 0xFFFFu) >= (uint32_t)TMEM_COLS) {
-        const long long t0 = clock64();
-        while (clock64() - t0 < (long long)geo.phase_delay) __nanosleep(100);
-      }
-      int id = blockIdx.x;
-      if (id < num_items) {
-        const Item first = item_of(id);
-        load_k(first);
-        load_qv(first);
-      }
-      for (uint32_t i = 0; id < num_items; id += gridDim.x, ++i) {
-        const uint32_t par = i & 1;
-        const int next = id + gridDim.x;
-        // ---- S = Q K^T (the previous item's O has been read out of TMEM) ----
-        mbar_wait(bar_k, par);
-        mbar_wait(bar_q, par);
-        if (i > 0) mbar_wait(bar_e, par ^ 1);
-        tc_fence_after();
-        if (tr && i == 0) tr[2] = clock64();
-        {
-          const uint64_t adesc = make_smem_desc(QPs), bdesc = make_smem_desc(Ks);
+      for (int j = 0; j < count; ++j) {
+        const Item it = item_of(geo, item0 + j);
+        if (first_of_unit(j)) {
+          const int u = unit_idx(j);
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k) umma_f16(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc_s, k != 0);
-          umma_commit(bar_s);
+          for (int kv = 0; kv < 2; ++kv) {  // K, then V
+            const int x = 2 * u + kv, e = x % KV_RING, use = x / KV_RING;
+            if (use >= 1) mbar_wait(BAR(B_KVFREE + e), (uint32_t)((use - 1) & 1));
+            const uint32_t dst = kv_base + e * kv_bytes;
+            mbar_arrive_expect_tx(BAR(B_KVFULL + e), (uint32_t)kv_bytes);
+            for (int r = 0; r < n16; r += 128)
+              tma_load_2d(dst + r * ROW_BYTES, (n16 - r >= 128) ? &map_full : &map_kvt, BAR(B_KVFULL + e),
+                          (1 + kv) * D + it.h * HD, it.g * n + r);
+          }
+          ATTN_TRACE(j, 9);
         }
-        // ---- K is free once S is complete: prefetch the next item's K behind this item's softmax ----
-        if (next < num_items) {
-          mbar_wait(bar_s, par);
-          load_k(item_of(next));
-        }
-        // ---- O = P V (P written by the softmax warps over the Q tile) ----
-        mbar_wait(bar_p, par);
-        if (tr && i == 0) tr[5] = clock64();
-        mbar_wait(bar_v, par);
+        const int qs = j % NQ;
+        if (j >= NQ) mbar_wait(BAR(B_QFREE + qs), (uint32_t)(((j / NQ) - 1) & 1));
+        const uint32_t Qs = q_base + qs * Q_TILE_BYTES;
+        mbar_arrive_expect_tx(BAR(B_QFULL + qs), (uint32_t)((it.c_rows + it.p_rows) * ROW_BYTES));
+        if (it.c_rows == QT)
+          tma_load_2d(Qs, &map_full, BAR(B_QFULL + qs), it.h * HD, it.g * n + it.t * QT);
+        else if (it.c_rows > 0)
+          tma_load_2d(Qs, &map_qt, BAR(B_QFULL + qs), it.h * HD, it.g * n + it.t * QT);
+        if (it.p_rows > 0)
+          tma_load_2d(Qs + geo.prompt_row * ROW_BYTES, &map_prompt, BAR(B_QFULL + qs), it.h * HD, it.g * K);
+        ATTN_TRACE(j, 10);
+      }
+    } else if (warp == 1 && elect_one()) {
+      // ===== S = Q K^T issuer =====
+      const uint32_t fmt = Num<T>::dtype == RPO_BF16 ? 1u : 0u;
+      const uint32_t idesc_s0 = make_idesc((int)fmt, QT, geo.n_first);
+      const uint32_t idesc_s1 = make_idesc((int)fmt, QT, n16 - geo.n_first > 0 ? n16 - geo.n_first : 16);
+      const bool two_blocks = n16 > geo.n_first;
+      for (int j = 0; j < count; ++j) {
+        const int slot = j % SLOTS, qs = j % NQ;
+        const int x = 2 * unit_idx(j), e = x % KV_RING;
+        mbar_wait(BAR(B_QFULL + qs), (uint32_t)((j / NQ) & 1));
+        if (first_of_unit(j)) mbar_wait(BAR(B_KVFULL + e), (uint32_t)((x / KV_RING) & 1));
+        ATTN_TRACE(j, 11);
+        // the slot's previous S is in the softmax threads' registers
+        if (j >= SLOTS) mbar_wait(BAR(B_SFREE + slot), (uint32_t)(((j / SLOTS) - 1) & 1));
         tc_fence_after();
-        for (int j = 0; j < nsteps; ++j)
-          umma_f16(tmem_base, make_smem_desc_sw32(QPs + j * P_BLOCK_BYTES), make_smem_desc(Vs + j * 16 * ROW_BYTES),
-                   idesc_o, j != 0);
-        umma_commit(bar_o);
-        // ---- V and the Q/P region are free once O is complete: next item's Q and V ----
-        if (next < num_items) {
-          mbar_wait(bar_o, par);
-          load_qv(item_of(next));
+        const uint32_t Qs = q_base + qs * Q_TILE_BYTES, Ks = kv_base + e * kv_bytes;
+        const uint32_t tslot = tmem_base + (uint32_t)(slot * SLOT_COLS);
+        const uint64_t adesc = make_smem_desc(Qs), bdesc0 = make_smem_desc(Ks);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_f16(tslot, adesc + 2u * k, bdesc0 + 2u * k, idesc_s0, k != 0);
+        if (two_blocks) {
+          const uint64_t bdesc1 = make_smem_desc(Ks + geo.n_first * ROW_BYTES);
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k)
+            umma_f16(tslot + (uint32_t)geo.n_first, adesc + 2u * k, bdesc1 + 2u * k, idesc_s1, k != 0);
         }
+        umma_commit(BAR(B_SFULL + slot));
+        umma_commit(BAR(B_QFREE + qs));
+        if (last_of_unit(j)) umma_commit(BAR(B_KVFREE + e));  // K of the unit is dead once this S is complete
+        ATTN_TRACE(j, 0);
+      }
+    } else if (warp == 2 && elect_one()) {
+      // ===== O = P V issuer: A = P from shared memory (K-major 128 x 16 blocks, 32B swizzle), B = V as loaded =====
+      const uint32_t fmt = Num<T>::dtype == RPO_BF16 ? 1u : 0u;
+      const uint32_t idesc_o = make_idesc((int)fmt, QT, HD) | (1u << 16);  // B (= V) is MN-major
+      const uint64_t pdesc = make_smem_desc_sw32(p_base);
+      // Issue order: round r takes the r-th key block of each of the PARTS softmax threads of a row.  The softmax
+      // threads write their blocks in the same order, so a thread may overwrite its r-th block of the single P buffer
+      // as soon as round r of the previous tile has been consumed (B_PFREE + r) instead of waiting for the whole P V.
+      // the order as a table in shared memory: entry i = key block, bit 7 set on the last block of a round
+      {
+        const int base_nb = geo.nblk / PARTS, extra = geo.nblk % PARTS;
+        const int rounds = base_nb + (extra ? 1 : 0);
+        int i = 0;
+        for (int r = 0; r < rounds; ++r) {
+          for (int pt = 0; pt < PARTS; ++pt) {
+            const int nbp = base_nb + (pt < extra ? 1 : 0);
+            if (r < nbp) pv_order[i++] = (uint8_t)(pt * base_nb + (pt < extra ? pt : extra) + r);
+          }
+          pv_order[i - 1] |= 0x80;
+        }
+      }
+      const int nsteps = geo.nblk;
+      for (int j = 0; j < count; ++j) {
+        const int x = 2 * unit_idx(j) + 1, e = x % KV_RING;
+        mbar_wait(BAR(B_PFULL), (uint32_t)(j & 1));
+        ATTN_TRACE(j, 1);
+        if (first_of_unit(j)) mbar_wait(BAR(B_KVFULL + e), (uint32_t)((x / KV_RING) & 1));
+        if (j >= 1) mbar_wait(BAR(B_OFREE), (uint32_t)((j - 1) & 1));  // the previous tile's O is out of tensor memory
+        tc_fence_after();
+        const uint64_t vdesc = make_smem_desc(kv_base + e * kv_bytes);
+        int round = 0;
+        for (int i = 0; i < nsteps; ++i) {
+          const int ent = pv_order[i], blk = ent & 0x7f;  // 16 keys: 4 KB of P, 2 KB of V
+          umma_f16(tmem_base + O_COL, pdesc + (uint64_t)(blk * (P_BLOCK_BYTES >> 4)), vdesc + (uint64_t)(blk * 128),
+                   idesc_o, i != 0);
+          if (ent & 0x80) umma_commit(BAR(B_PFREE + round++));
+        }
+        umma_commit(BAR(B_OFULL));
+        if (last_of_unit(j)) umma_commit(BAR(B_KVFREE + e));  // V of the unit is dead once this O is complete
+        ATTN_TRACE(j, 2);
+      }
+    }
+  } else if (warp < PROD_WARPS + SM_WARPS) {
+    // ===== softmax: warps w, w+4, w+8, w+12 own TMEM lanes (= query rows) 32*(w%4) .. +31 and split the key blocks =====
+    // Four warps per scheduler hide each other's MUFU / TMEM latencies.  Software-pipelined over tiles: a block's
+    // registers take the next tile's scores as soon as its probabilities are stored, so the tensor-memory reads (the
+    // scarcest resource: 64 B/clk per SM) run beside the exponentials.
+    setmaxnreg_inc<Regs<MAXB>::SOFTMAX>();
+    const int q = warp & 3;
+    const int part = (warp - PROD_WARPS) >> 2;
+    const int row = q * 32 + lane;
+    const bool tracer = threadIdx.x == PROD_WARPS * 32;
+    const float sl2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+    const int nblk = geo.nblk;
+    // this thread's 16-key blocks [b0, b0 + nb): the first (nblk % PARTS) parts hold one block more
+    const int base_nb = nblk / PARTS, extra = nblk % PARTS;
+    const int b0 = part * base_nb + min(part, extra), nb = base_nb + (part < extra ? 1 : 0);
+    // the block (local index) and element from which this thread's columns are padding (>= n); -1: none
+    const int pad_block = (n < n16 && (nblk - 1) >= b0 && (nblk - 1) < b0 + nb) ? nblk - 1 - b0 : -1;
+    const int pad_first = n - (nblk - 1) * 16;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    // P block b of this row: 32 bytes at row * 32 of the block, the two 16-byte chunks swapped on odd 4-row groups
+    const uint32_t sw = (uint32_t)((row >> 2) & 1);
+    const uint32_t prow0 = p_base + (uint32_t)(row * 32) + ((0u ^ sw) << 4), prow1 = p_base + (uint32_t)(row * 32) + ((1u ^ sw) << 4);
+    // one S slot: the next S is issued when this one is in registers, poll for it half way through the blocks
+    constexpr int PF_AT = SLOTS == 2 ? 0 : MAXB / 2;
+    uint32_t s[MAXB][16];
+    bool loaded = false;  // s[] holds the scores of the tile about to be processed
+    Item it = item_of(geo, item0), nx = it;
+    for (int j = 0; j < count; ++j, it = nx) {
+      advance(geo, nx);
+      const int slot = j % SLOTS;
+      const int rows_here = it.c_rows + it.p_rows;
+      const bool valid = q * 32 < rows_here;  // warp-uniform, identical for the warps of a lane quarter
+      if (!loaded) {
+        // every warp waits for S and arrives on "S in registers", also warps without valid rows
+        mbar_wait(BAR(B_SFULL + slot), (uint32_t)((j / SLOTS) & 1));
+        if (valid) {
+          tc_fence_after();
+          const uint32_t taddr = lane_base + (uint32_t)(slot * SLOT_COLS);
+#pragma unroll
+          for (int b = 0; b < MAXB; ++b)
+            if (b < nb) tmem_ld16_nowait(taddr + (uint32_t)((b0 + b) * 16), s[b]);
+#pragma unroll
+          for (int b = 0; b < MAXB; ++b)
+            if (b < nb) tmem_ld_wait(s[b]);
+          tc_fence_before();
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(B_SFREE + slot));
+      }
+      loaded = false;
+      if (tracer) ATTN_TRACE(j, 4);
+      bool nvalid = false;
+      int nslot = 0;
+      uint32_t npar = 0;
+      const bool have_next = j + 1 < count;
+      if (have_next) {
+        nvalid = q * 32 < nx.c_rows + nx.p_rows;
+        nslot = (j + 1) % SLOTS;
+        npar = (uint32_t)(((j + 1) / SLOTS) & 1);
+      }
+      const uint32_t ntaddr = lane_base + (uint32_t)(nslot * SLOT_COLS);
+      bool pf = false;  // the next tile's scores are being prefetched into the freed registers
+      if (valid) {
+        // ---- padding columns (>= n, in the row's last key block) become -inf once: no special cases below ----
+#pragma unroll
+        for (int b = 0; b < MAXB; ++b) {
+          if (b == pad_block) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (e >= pad_first) s[b][e] = 0xff800000u;
+          }
+        }
+        // ---- row maximum over this thread's keys (four independent chains) ----
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int b = 0; b < MAXB; ++b) {
+          if (b < nb) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 4)
+              m4[e >> 2] = fmaxf(m4[e >> 2], fmaxf(fmaxf(__uint_as_float(s[b][e]), __uint_as_float(s[b][e + 1])),
+                                                   fmaxf(__uint_as_float(s[b][e + 2]), __uint_as_float(s[b][e + 3]))));
+          }
+        }
+        float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        const uint32_t rmax = red_max + (uint32_t)(((j & 1) * PARTS * QT + row) * 4);
+        sts_f32(rmax + (uint32_t)(part * QT * 4), mx);
+        if (!(abl & 4)) quad_bar_sync(1 + q);
+        mx = fmaxf(fmaxf(lds_f32(rmax), lds_f32(rmax + QT * 4)), fmaxf(lds_f32(rmax + 2 * QT * 4), lds_f32(rmax + 3 * QT * 4)));
+        if (tracer) ATTN_TRACE(j, 5);
+        const float off = mx * sl2;
+        // ---- probabilities -> P blocks in shared memory, row sum ----
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int b = 0; b < MAXB; ++b) {
+          if (b == PF_AT && nvalid) {
+            if (SLOTS == 2) {
+              mbar_wait(BAR(B_SFULL + nslot), npar);  // issued long ago: the slot was free as soon as it was read
+              pf = true;
+            } else {
+              pf = __all_sync(0xffffffffu, mbar_try_wait(BAR(B_SFULL + nslot), npar));
+            }
+            if (pf) {
+              tc_fence_after();
+#pragma unroll
+              for (int c = 0; c < PF_AT; ++c)
+                if (c < nb) tmem_ld16_nowait(ntaddr + (uint32_t)((b0 + c) * 16), s[c]);
+            }
+          }
+          if (b < nb) {
+            // the single P buffer: round b of the previous tile's P V has consumed this block
+            if (j >= 1 && !(abl & 8)) mbar_wait(BAR(B_PFREE + b), (uint32_t)((j - 1) & 1));
+            uint32_t pk[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float p0 = fmaf(__uint_as_float(s[b][2 * e]), sl2, -off), p1 = fmaf(__uint_as_float(s[b][2 * e + 1]), sl2, -off);
+              if (!(abl & 1)) {
+                p0 = ex2_approx(p0);  // ex2(-inf) = 0
+                p1 = ex2_approx(p1);
+              }
+              l0 += p0;
+              l1 += p1;
+              pk[e] = pack2<T>(p0, p1);
+            }
+            if (!(abl & 2)) {
+              sts128(prow0 + (uint32_t)((b0 + b) * P_BLOCK_BYTES), pk[0], pk[1], pk[2], pk[3]);
+              sts128(prow1 + (uint32_t)((b0 + b) * P_BLOCK_BYTES), pk[4], pk[5], pk[6], pk[7]);
+            } else if (pk[0] == 0x12345u) {
+              sts128(prow0, pk[0], pk[1], pk[2], pk[3]);
+              sts128(prow1, pk[4], pk[5], pk[6], pk[7]);
+            }
+            if (pf) tmem_ld16_nowait(ntaddr + (uint32_t)((b0 + b) * 16), s[b]);
+          }
+        }
+        sts_f32(red_sum + (uint32_t)((((j & 3) * PARTS + part) * QT + row) * 4), l0 + l1);
+        // make the generic-proxy stores of P visible to the tensor core (async proxy)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      } else if (j >= 1) {
+        // a warp without valid rows must not arrive for this tile while the previous tile's phase of "P stored" is
+        // still open: the previous P V (which waited for that phase) has at least started
+        mbar_wait(BAR(B_PFREE), (uint32_t)((j - 1) & 1));
+      }
+      __syncwarp();
+      if (tracer) ATTN_TRACE(j, 6);
+      if (lane == 0) mbar_arrive(BAR(B_PFULL));
+      if (have_next && (pf || nvalid)) {
+        if (!pf) {
+          mbar_wait(BAR(B_SFULL + nslot), npar);
+          tc_fence_after();
+#pragma unroll
+          for (int b = 0; b < MAXB; ++b)
+            if (b < nb) tmem_ld16_nowait(ntaddr + (uint32_t)((b0 + b) * 16), s[b]);
+        }
+#pragma unroll
+        for (int b = 0; b < MAXB; ++b)
+          if (b < nb) tmem_ld_wait(s[b]);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(B_SFREE + nslot));
+        loaded = true;
+        if (tracer) ATTN_TRACE(j + 1, 3);
       }
     }
   } else {
-    // ===== softmax + epilogue: warps w and w+4 own TMEM lanes (= query rows) 32*(w%4) .. +31 =====
+    // ===== epilogue: one thread per query row =====
+    setmaxnreg_dec<REGS_EPI>();
     const int q = warp & 3;
-    const int hf = (warp - 1) >> 2;  // which share of the key blocks / of the output columns
     const int row = q * 32 + lane;
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const float sl2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-    const int nblk = n16 >> 4;
-    const int b_mid = (nblk + 1) >> 1;
-    const int b0 = hf ? b_mid : 0, b1 = hf ? nblk : b_mid;  // this thread's 16-key blocks
-    const uint32_t sw = (uint32_t)((row >> 2) & 1);  // 32B swizzle: 16-byte chunk index ^= address bit 7
-    uint8_t *prow = QP_gen + row * 32;
-    uint32_t i = 0;
-    for (int id = blockIdx.x; id < num_items; id += gridDim.x, ++i) {
-      const uint32_t par = i & 1;
-      const Item it = item_of(id);
+    const bool tracer = threadIdx.x == (PROD_WARPS + SM_WARPS) * 32;
+    const uint32_t taddr = tmem_base + O_COL + ((uint32_t)(q * 32) << 16);
+    pdl_wait();
+    Item it = item_of(geo, item0);
+    for (int j = 0; j < count; ++j, advance(geo, it)) {
       const int rows_here = it.c_rows + it.p_rows;
-      const bool warp_valid = q * 32 < rows_here;  // warp-uniform, identical for the two partner warps
-      // every warp waits for S, also those without valid rows: S(i) exists only after all warps arrived for item
-      // i-1, so no warp can arrive twice in one barrier phase
-      mbar_wait(bar_s, par);
-      if (warp_valid) {
-        tc_fence_after();
-        if (tr && i == 0 && threadIdx.x == 32) tr[3] = clock64();
-        // ---- pass 1: row maximum over this thread's keys ----
-        float mx = -INFINITY;
-        {
-          uint32_t cur[16], nxt[16];
-          tmem_ld16_nowait(taddr + (uint32_t)(b0 * 16), cur);
-          tmem_ld_wait(cur);
-          for (int b = b0; b < b1; ++b) {
-            if (b + 1 < b1) tmem_ld16_nowait(taddr + (uint32_t)((b + 1) * 16), nxt);
-            if (b * 16 + 16 <= n) {
-#pragma unroll
-              for (int e = 0; e < 16; e += 2)
-                mx = fmaxf(mx, fmaxf(__uint_as_float(cur[e]), __uint_as_float(cur[e + 1])));
-            } else {
-#pragma unroll
-              for (int e = 0; e < 16; ++e)
-                if (b * 16 + e < n) mx = fmaxf(mx, __uint_as_float(cur[e]));
-            }
-            if (b + 1 < b1) {
-              tmem_ld_wait(nxt);
-#pragma unroll
-              for (int e = 0; e < 16; ++e) cur[e] = nxt[e];
-            }
-          }
-        }
-        red_max[hf * QT + row] = mx;
-        pair_bar_sync(1 + q);
-        if (tr && i == 0 && threadIdx.x == 32) tr[4] = clock64();
-        mx = fmaxf(red_max[row], red_max[QT + row]);  // every row sees key 0, so the maximum is finite
-        const float off = mx * sl2;
-        // ---- pass 2: probabilities -> P blocks, row sum ----
-        float l = 0.f, l_odd = 0.f;
-        {
-          uint32_t cur[16], nxt[16];
-          tmem_ld16_nowait(taddr + (uint32_t)(b0 * 16), cur);
-          tmem_ld_wait(cur);
-          for (int b = b0; b < b1; ++b) {
-            if (b + 1 < b1) tmem_ld16_nowait(taddr + (uint32_t)((b + 1) * 16), nxt);
-            uint32_t pk[8];
-            if (b * 16 + 16 <= n && (geo.flags & 1)) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                float x0 = __uint_as_float(cur[2 * e]), x1 = __uint_as_float(cur[2 * e + 1]);
-                ffma2(x0, x1, sl2, -off);
-                const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
-                fadd2(l, l_odd, p0, p1);
-                pk[e] = pack2<T>(p0, p1);
-              }
-            } else if (b * 16 + 16 <= n) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float p0 = ex2_approx(fmaf(__uint_as_float(cur[2 * e]), sl2, -off));
-                const float p1 = ex2_approx(fmaf(__uint_as_float(cur[2 * e + 1]), sl2, -off));
-                l += p0 + p1;
-                pk[e] = pack2<T>(p0, p1);
-              }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const int col = b * 16 + 2 * e;
-                const float p0 = col < n ? ex2_approx(fmaf(__uint_as_float(cur[2 * e]), sl2, -off)) : 0.f;
-                const float p1 = col + 1 < n ? ex2_approx(fmaf(__uint_as_float(cur[2 * e + 1]), sl2, -off)) : 0.f;
-                l += p0 + p1;
-                pk[e] = pack2<T>(p0, p1);
-              }
-            }
-            uint8_t *dst = prow + b * P_BLOCK_BYTES;
-            *reinterpret_cast<uint4 *>(dst + ((0u ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint4 *>(dst + ((1u ^ sw) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-            if (b + 1 < b1) {
-              tmem_ld_wait(nxt);
-#pragma unroll
-              for (int e = 0; e < 16; ++e) cur[e] = nxt[e];
-            }
-          }
-        }
-        red_sum[hf * QT + row] = l + l_odd;
-        // make the generic-proxy stores of P visible to the tensor core (async proxy), release S
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        tc_fence_before();
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_p);
-      if (warp_valid) {
-        mbar_wait(bar_o, par);
-        tc_fence_after();
-        if (tr && i == 0 && threadIdx.x == 32) tr[6] = clock64();
-        const float inv = 1.0f / (red_sum[row] + red_sum[QT + row]);
+      mbar_wait(BAR(B_PFULL), (uint32_t)(j & 1));  // the row sums are in shared memory
+      mbar_wait(BAR(B_OFULL), (uint32_t)(j & 1));
+      tc_fence_after();
+      if (tracer) ATTN_TRACE(j, 7);
+      if (q * 32 < rows_here) {
+        const uint32_t rsum = red_sum + (uint32_t)(((j & 3) * PARTS * QT + row) * 4);
+        const float inv = 1.0f / ((lds_f32(rsum) + lds_f32(rsum + QT * 4)) + (lds_f32(rsum + 2 * QT * 4) + lds_f32(rsum + 3 * QT * 4)));
         T *dst = nullptr;
         if (row < it.c_rows)
           dst = out_ctx + ((long long)it.g * n + it.t * QT + row) * D + it.h * HD;
         else if (row < rows_here)
           dst = out_prompt + ((long long)it.g * K + (row - it.c_rows)) * D + it.h * HD;
-        uint32_t acc[32];
-        tmem_ld32(taddr + (uint32_t)(hf * 32), acc);  // this thread's 32 of the 64 output columns
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_e);  // O is out of TMEM: the next S may overwrite it
-        if (dst) {
 #pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            uint4 o;
-            o.x = pack2<T>(__uint_as_float(acc[8 * v + 0]) * inv, __uint_as_float(acc[8 * v + 1]) * inv);
-            o.y = pack2<T>(__uint_as_float(acc[8 * v + 2]) * inv, __uint_as_float(acc[8 * v + 3]) * inv);
-            o.z = pack2<T>(__uint_as_float(acc[8 * v + 4]) * inv, __uint_as_float(acc[8 * v + 5]) * inv);
-            o.w = pack2<T>(__uint_as_float(acc[8 * v + 6]) * inv, __uint_as_float(acc[8 * v + 7]) * inv);
-            *reinterpret_cast<uint4 *>(dst + hf * 32 + v * 8) = o;
+        for (int c = 0; c < 4; ++c) {  // 16 columns at a time: this role runs on 40 registers
+          uint32_t acc[16];
+          tmem_ld16(taddr + (uint32_t)(c * 16), acc);
+          if (dst) {
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+              uint4 o;
+              o.x = pack2<T>(__uint_as_float(acc[8 * v + 0]) * inv, __uint_as_float(acc[8 * v + 1]) * inv);
+              o.y = pack2<T>(__uint_as_float(acc[8 * v + 2]) * inv, __uint_as_float(acc[8 * v + 3]) * inv);
+              o.z = pack2<T>(__uint_as_float(acc[8 * v + 4]) * inv, __uint_as_float(acc[8 * v + 5]) * inv);
+              o.w = pack2<T>(__uint_as_float(acc[8 * v + 6]) * inv, __uint_as_float(acc[8 * v + 7]) * inv);
+              *reinterpret_cast<uint4 *>(dst + c * 16 + v * 8) = o;
+            }
           }
         }
-      } else {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_e);
       }
+      // O is out of tensor memory: the next P V may overwrite it
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(B_OFREE));
+      if (tracer) ATTN_TRACE(j, 8);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (tr && threadIdx.x == 0) tr[7] = clock64();
+  if (threadIdx.x == 0) ATTN_TRACE(0, 14);
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
+  if (threadIdx.x == 0) ATTN_TRACE(0, 15);
+}
+
+static int smem_bytes(int n16, int q_ring) {
+  return KV_RING * n16 * ROW_BYTES + (n16 >> 4) * P_BLOCK_BYTES + q_ring * Q_TILE_BYTES + 8 * 28 +
+         (2 + 4) * PARTS * QT * 4 + 32 + 1024;
 }
 
 }  // namespace atc
@@ -409,10 +611,10 @@ bool ro_attention_fwd_dense_supported(int dtype, int n, int K, int H) {
   if (dtype != RPO_F16 && dtype != RPO_BF16) return false;
   if (n < 1 || K < 0 || H < 1) return false;
   const int n16 = (n + 15) & ~15;
-  if (n16 > 256) return false;                 // one UMMA N, 256 TMEM columns
+  if (n16 > 288) return false;                     // 18 key blocks: 5 per softmax thread at most; S + O within 512 TMEM columns
   if (K > 0 && (n % 128) + K > 128) return false;  // all prompt rows in one query tile
-  static const bool off = [] { const char *e = getenv("RPO_ATTN_NO_TC"); return e && e[0] == '1'; }();
-  return !off;
+  if (atc::smem_bytes(n16, 2) > 227 * 1024) return false;
+  return true;
 }
 
 template <typename T>
@@ -432,15 +634,20 @@ int ro_attention_fwd_dense(const T *qkv_ctx, const T *q_prompt, T *out_ctx, T *o
     Geo geo;
     geo.n = n;
     geo.n16 = n16;
+    geo.nblk = n16 >> 4;
     geo.K = K;
     geo.prompt_tile = n / 128;
     geo.prompt_row = n % 128;
     geo.H = H;
-    geo.phase_delay = 0;
-    geo.flags = 0;
-    if (const char *e = getenv("RPO_ATTN_PHASE_DELAY")) geo.phase_delay = atoi(e);
-    if (const char *e = getenv("RPO_ATTN_F32X2")) geo.flags |= (e[0] == '1') ? 1 : 0;
-    const int tiles = K > 0 ? geo.prompt_tile + 1 : (n + 127) / 128;
+    geo.tiles = K > 0 ? geo.prompt_tile + 1 : (n + 127) / 128;
+    // S as one UMMA N block up to 256 keys, else two (144 + the rest: both multiples of 16, the second starts on an
+    // 8-row group of the 128B-swizzled K tile)
+    geo.n_first = n16 <= 256 ? n16 : 144;
+    const bool two_slots = n16 <= 224;  // two S / P slots of 224 columns beside the 64 columns of O
+    int q_ring = MAX_Q_RING;
+    while (q_ring > 2 && smem_bytes(n16, q_ring) > 227 * 1024) --q_ring;
+    geo.q_ring = q_ring;
+    const int smem = smem_bytes(n16, q_ring);
     CUtensorMap map_full, map_kvt, map_qt, map_prompt;
     const long long Mc = (long long)G * n;
     RPO_TRY(make_map(&map_full, Num<T>::dtype, qkv_ctx, Mc, 3 * D, 3LL * D, 128));
@@ -450,28 +657,42 @@ int ro_attention_fwd_dense(const T *qkv_ctx, const T *q_prompt, T *out_ctx, T *o
       RPO_TRY(make_map(&map_prompt, Num<T>::dtype, q_prompt, (long long)G * K, D, D, K));
     else
       map_prompt = map_full;
-    const int kv_bytes = n16 * ROW_BYTES;
-    const int p_bytes = (n16 >> 4) * P_BLOCK_BYTES;
-    const int smem = 2 * kv_bytes + (p_bytes > QT * ROW_BYTES ? p_bytes : QT * ROW_BYTES) + 64 + 4 * QT * 4 + 1024;
-    static int configured = 0;
-    if (smem > configured) {
-      RPO_CHECK_CUDA(cudaFuncSetAttribute(ro_attn_fwd_tc<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      configured = smem;
-    }
-    geo.tiles = tiles;
-    const long long items = (long long)tiles * H * G;
+    const long long items = (long long)geo.tiles * H * G;
     RPO_REQUIRE(items <= 0x7fffffffLL, "grid limits");
-    const int slots = 2 * sm_count();  // two CTAs per SM (104 KB of shared memory, 256 TMEM columns each)
-    dim3 grid((unsigned)(items < slots ? items : slots));
-    long long *trace = nullptr;
-    if (const char *e = getenv("RPO_ATTN_TRACE")) trace = reinterpret_cast<long long *>(strtoull(e, nullptr, 0));
+    const int sms = sm_count();
+    dim3 grid((unsigned)(items < sms ? items : sms));
     prof_tag("attn_fwd_tc G=%d H=%d K=%d n=%d", G, H, K, n);
-    RPO_CHECK_CUDA(launch_pdl(ro_attn_fwd_tc<T>, grid, dim3(THREADS), (size_t)smem, st, map_full, map_kvt, map_qt,
-                              map_prompt, out_ctx, out_prompt, geo, (int)items, trace));
+    auto launch = [&](auto kernel) -> int {
+      static int configured = 0;  // one per instantiation of the lambda's argument type
+      if (smem > configured) {
+        RPO_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = smem;
+      }
+      RPO_CHECK_CUDA(launch_pdl(kernel, grid, dim3(THREADS), (size_t)smem, st, map_full, map_kvt, map_qt, map_prompt,
+                                out_ctx, out_prompt, geo, (int)items));
+      return RPO_OK;
+    };
+    int s;
+    if (two_slots)
+      s = launch(ro_attn_fwd_tc<T, 4, 2>);
+    else
+      s = launch(ro_attn_fwd_tc<T, 5, 1>);
+    RPO_TRY(s);
     RPO_LAUNCH_CHECK();
     return RPO_OK;
   }
 }
+
+#ifdef RPO_DIAG
+extern "C" int rpo_diag_set_attn_ablation(int bits) {
+  RPO_CHECK_CUDA(cudaMemcpyToSymbol(atc::g_attn_abl, &bits, sizeof(bits)));
+  return RPO_OK;
+}
+extern "C" int rpo_diag_set_attn_trace(long long *buf) {
+  RPO_CHECK_CUDA(cudaMemcpyToSymbol(atc::g_attn_trace, &buf, sizeof(buf)));
+  return RPO_OK;
+}
+#endif
 
 template int ro_attention_fwd_dense<float>(const float *, const float *, float *, float *, int, int, int, int,
                                            cudaStream_t);

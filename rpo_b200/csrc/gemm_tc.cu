@@ -650,7 +650,7 @@ __global__ void __launch_bounds__(Thr<BN>::THREADS, (Cfg<BN, LIGHT>::MIN_CTAS))
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync: ptxas emits the UTCHMMAs straight from uniform registers, no per-lane loop
       constexpr uint32_t idesc = make_idesc(Num<T>::dtype == RPO_BF16 ? 1 : 0, BM, BN);
       uint32_t it = 0, t = 0;
       TileFeed feed;
@@ -970,7 +970,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
     }
   } else if (warp == 1) {
     // ===== MMA issuer: one thread of the leader CTA drives both SMs' tensor cores =====
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && elect_one()) {
       constexpr uint32_t idesc = make_idesc(Num<T>::dtype == RPO_BF16 ? 1 : 0, 2 * BM, C_::MMA_N);
       Sched sch;
       sch.init(stream_k, num_tiles, num_kb, cluster_id, num_clusters, num_n_tiles, dyn, clc_base, TileFeed::THREAD);
@@ -1302,7 +1302,7 @@ __global__ void __cluster_dims__(SPLIT, 1, 1) __launch_bounds__(64 + GROUP_THREA
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc(Num<T>::dtype == RPO_BF16 ? 1 : 0, BM, BN);
       uint32_t it = 0;
       for (int kb = kb0; kb < kb1; ++kb, ++it) {

@@ -360,7 +360,11 @@ DENSE_CASES = [
     # (name, G, n_ctx, K, H): the vision tower's shapes and the edges of what the tcgen05 kernel accepts
     ("vitb16_k24", 3, 197, 24, 12), ("vitb16_k4", 2, 197, 4, 12), ("vitb16_k48", 2, 197, 48, 12),
     ("one_tile", 2, 50, 24, 2), ("exact_128", 2, 128, 16, 2), ("n256", 2, 256, 100, 1), ("tiny", 1, 17, 5, 2),
-    ("no_prompts", 2, 197, 0, 2),
+    ("no_prompts", 2, 197, 0, 2), ("vitb16_k8", 2, 197, 8, 12), ("vitb16_k16", 2, 197, 16, 12),
+    # several work items per CTA: K/V double buffer, Q ring and both TMEM slots wrap around (config 2 / 5 sizes)
+    ("vitb16_k24_b32", 32, 197, 24, 12), ("vitb16_k48_b64", 64, 197, 48, 12), ("vitb16_ctx_only_b32", 32, 197, 0, 12),
+    # ViT-L/14 (BASELINE config 3): 257 keys = two UMMA N blocks in one 512-column TMEM slot, three query tiles
+    ("vitl14_k24", 2, 257, 24, 16), ("vitl14_k24_b16", 16, 257, 24, 16), ("n288", 3, 288, 0, 2), ("n16_one_block", 3, 9, 3, 1),
 ]
 
 
@@ -398,9 +402,11 @@ def test_ro_attention_fwd_dense_tcgen05(prec, case):
 def test_ro_attention_fwd_dense_rejects_unsupported():
     lib = _lib.load()
     x = torch.zeros(8, dtype=torch.float16, device=dev())
-    # 257 context rows (ViT-L/14) need two UMMA N blocks: not on this path
-    assert lib.rpo_ro_attention_fwd_dense(x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), 1, 257, 24, 16,
+    # more than 288 context rows do not fit S + O into the 512 tensor-memory columns
+    assert lib.rpo_ro_attention_fwd_dense(x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), 1, 300, 24, 16,
                                           _lib.RPO_F16, st()) == -1
+    assert lib.rpo_ro_attention_fwd_dense_supported(_lib.RPO_F16, 257, 24, 16) == 1   # ViT-L/14
+    assert lib.rpo_ro_attention_fwd_dense_supported(_lib.RPO_F16, 300, 24, 16) == 0
     # prompts that would straddle two query tiles
     assert lib.rpo_ro_attention_fwd_dense(x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), 1, 197, 64, 12,
                                           _lib.RPO_F16, st()) == -1

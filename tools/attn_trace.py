@@ -1,36 +1,79 @@
-"""Phase timeline of the tcgen05 attention CTAs (tuning aid): launches the kernel once with RPO_ATTN_TRACE set to a
-device buffer and prints the mean SM-clock cycles each CTA spends per phase."""
-import os, sys
+"""Phase timeline of CTA 0 of the tcgen05 attention kernel (diagnostics build: RPO_DIAG=1 python -m rpo_b200.build).
+
+    RPO_DIAG=1 python -m rpo_b200.build --force && python tools/attn_trace.py [--arch ViT-B/16] [--batch 32] [--K 24]
+
+Events per work item (SM clock, relative to the first event): producer K/V issued, Q issued; MMA thread: S issued,
+P-full seen, PV issued; softmax warp 4: S-full seen, scores in registers, maxima exchanged, P stored; epilogue warp 12:
+O-full seen, stores done."""
+import argparse
+import ctypes as C
+import os
+import sys
+
 import torch
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from rpo_b200 import _lib
-G, H, K, n = 32, 12, 24, 197
-D = H * 64
-dev = torch.device("cuda:0")
-lib = _lib.load()
-g = torch.Generator().manual_seed(0)
-qkv = torch.randn(G * n, 3 * D, generator=g).half().to(dev)
-qp = torch.randn(G * K, D, generator=g).half().to(dev)
-oc = torch.empty(G * n, D, dtype=torch.float16, device=dev)
-op = torch.empty(G * K, D, dtype=torch.float16, device=dev)
-ncta = 2 * 148
-trace = torch.zeros(ncta, 8, dtype=torch.int64, device=dev)
-for warm in range(3):
-    _lib.check(lib.rpo_ro_attention_fwd_dense(qkv.data_ptr(), qp.data_ptr(), oc.data_ptr(), op.data_ptr(), G, n, K, H, 1,
-                                              _lib.stream_ptr(dev)))
-torch.cuda.synchronize()
-os.environ["RPO_ATTN_TRACE"] = hex(trace.data_ptr())
-_lib.check(lib.rpo_ro_attention_fwd_dense(qkv.data_ptr(), qp.data_ptr(), oc.data_ptr(), op.data_ptr(), G, n, K, H, 1,
-                                          _lib.stream_ptr(dev)))
-torch.cuda.synchronize()
-t = trace.cpu().double()
-names = ["setup (barriers, TMEM alloc, sync)", "loads Q+K landed", "S MMA done (seen by softmax)", "pass 1 (max) done",
-         "pass 2 + P stored + all warps arrived", "PV MMA done (seen by softmax)", "epilogue + teardown sync"]
-order = [0, 1, 2, 3, 4, 5, 6, 7]
-for tile in (0, 1):
-    tt = t[tile::2]  # first item of CTA b is item b: even CTAs start on tile 0, odd on tile 1
-    print(f"tile {tile}: total {float((tt[:, 7] - tt[:, 0]).mean()):.0f} cycles")
-    for i, nm in enumerate(names):
-        a, b = order[i], order[i + 1]
-        print(f"   {nm:42s} {float((tt[:, b] - tt[:, a]).mean()):8.0f}")
+from rpo_b200 import _lib  # noqa: E402
+
+EV = {9: "kv_issue", 10: "q_issue", 11: "s_wait_ofree", 0: "s_issue", 3: "sm_sfull", 4: "sm_loaded", 5: "sm_maxx",
+      6: "sm_pdone", 1: "pv_pfull", 2: "pv_issued", 7: "ep_ofull", 8: "ep_done"}
+ORDER = [9, 10, 11, 0, 3, 4, 5, 6, 1, 2, 7, 8]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--arch", default="ViT-B/16")
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--K", type=int, default=24)
+    ap.add_argument("--prec", default="fp16")
+    ap.add_argument("--ablation", type=int, default=0)
+    a = ap.parse_args()
+    lib = _lib.load()
+    if a.ablation:
+        _lib.check(lib.rpo_diag_set_attn_ablation(a.ablation))
+    if not hasattr(lib, "rpo_diag_set_attn_trace"):
+        raise SystemExit("not a diagnostics build: RPO_DIAG=1 python -m rpo_b200.build --force")
+    dt = {"fp16": torch.float16, "bf16": torch.bfloat16}[a.prec]
+    dev = torch.device("cuda:0")
+    H, n = (12, 197) if a.arch == "ViT-B/16" else (16, 257)
+    D, G, K = H * 64, a.batch, a.K
+    qkv = torch.randn(G * n, 3 * D, device=dev).to(dt)
+    qp = torch.randn(G * K, D, device=dev).to(dt)
+    oc = torch.empty(G * n, D, dtype=dt, device=dev)
+    op = torch.empty(G * K, D, dtype=dt, device=dev)
+    trace = torch.zeros(64 * 16, dtype=torch.int64, device=dev)
+    code = _lib.dtype_code(dt)
+
+    def run():
+        _lib.check(lib.rpo_ro_attention_fwd_dense(qkv.data_ptr(), qp.data_ptr(), oc.data_ptr(), op.data_ptr(), G, n, K, H,
+                                                  code, _lib.stream_ptr(dev)))
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"20 back-to-back eager launches: {e0.elapsed_time(e1) / 20 * 1e3:.2f} us per launch")
+    lib.rpo_diag_set_attn_trace.argtypes = [C.c_void_p]
+    _lib.check(lib.rpo_diag_set_attn_trace(trace.data_ptr()))
+    run()
+    torch.cuda.synchronize()
+    _lib.check(lib.rpo_diag_set_attn_trace(None))
+    t = trace.cpu().view(64, 16)
+    nz = t[t > 0]
+    t0 = int(nz.min())
+    print(f"kernel entry {int(t[0, 12]) - t0}, prologue done {int(t[0, 13]) - t0}, all roles done {int(t[0, 14]) - t0}, "
+          f"tmem released {int(t[0, 15]) - t0} (SM clocks)")
+    print("tile  " + " ".join(f"{EV[e]:>12s}" for e in ORDER))
+    for j in range(64):
+        if int(t[j].max()) == 0:
+            break
+        print(f"{j:4d}  " + " ".join(f"{(int(t[j, e]) - t0) if t[j, e] > 0 else -1:12d}" for e in ORDER))
+
+
+if __name__ == "__main__":
+    main()
