@@ -24,6 +24,8 @@
 // Registers: the three roles re-partition the register file with setmaxnreg (softmax threads hold up to 9 x 16 scores).
 #include <stdlib.h>
 
+#include <map>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -55,18 +57,8 @@ struct Regs {
 static constexpr int MAX_Q_RING = 4;
 static constexpr int MAX_ROUNDS = 5;            // key blocks per softmax thread, at most
 static constexpr int KV_RING = 3;               // K and V tiles rotate through three buffers (see the kernel)
-static constexpr int P_BLOCK_BYTES = QT * 32;  // one 128 x 16 block of P, 32-byte rows
+static constexpr int P_TILE_BYTES = QT * ROW_BYTES;  // P as A operand: 128 x 64-key tiles, K-major, 128B swizzle (like Q)
 
-// K-major operand with 32-byte rows (16 x 16-bit = one UMMA K step), 32B swizzle, 8-row groups 256 B apart
-__device__ __forceinline__ uint64_t make_smem_desc_sw32(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(256 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)6 << 61;  // SWIZZLE_32B
-  return d;
-}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -128,7 +120,6 @@ __device__ __forceinline__ void setmaxnreg_dec() {
 }
 
 #ifdef RPO_DIAG
-__device__ int g_attn_abl = 0;  // ablation bits (timing experiments only: results are wrong)
 // phase timestamps of CTA 0 (tools/attn_trace.py): trace[tile * 16 + event] = SM clock
 __device__ long long *g_attn_trace = nullptr;
 #define ATTN_TRACE(j, ev)                                                                  \
@@ -202,7 +193,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   // shared memory: [K|V ring of 3 | P | Q ring | barriers | row maxima | row sums]
   const uint32_t kv_base = smem_u32(smem);
   const uint32_t p_base = kv_base + KV_RING * kv_bytes;
-  const int p_bytes = geo.nblk * P_BLOCK_BYTES;
+  const int p_bytes = ((geo.nblk + 3) / 4) * P_TILE_BYTES;  // 64-key tiles
   const uint32_t q_base = p_base + p_bytes;
   uint8_t *tail = smem + KV_RING * kv_bytes + p_bytes + NQ * Q_TILE_BYTES;
   uint64_t *bars = reinterpret_cast<uint64_t *>(tail);
@@ -215,8 +206,9 @@ __global__ void __launch_bounds__(THREADS, 1)
                 B_OFULL = 19, B_OFREE = 20, B_PFREE = 21, N_BARS = 21 + MAX_ROUNDS;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + N_BARS);
   const uint32_t red_max = smem_u32(bars + N_BARS + 1);        // f32 [2][PARTS][QT]  (tile parity, key part, row)
-  const uint32_t red_sum = red_max + 2 * PARTS * QT * 4;        // f32 [4][PARTS][QT]  (tile & 3, key part, row)
-  uint8_t *pv_order = reinterpret_cast<uint8_t *>(bars + N_BARS + 1) + 6 * PARTS * QT * 4;  // [32] issue order of P V
+  // (two buffers are enough: the softmax of tile j+2 writes its sums after the P V of tile j+1 has been issued, which
+  // waited for the epilogue of tile j to have read O -- and with it these sums)
+  const uint32_t red_sum = red_max + 2 * PARTS * QT * 4;        // f32 [2][PARTS][QT]  (tile parity, key part, row)
 
   // this CTA's contiguous range of work items: consecutive tiles of an (image, head) share its K / V
   const int item0 = (int)((long long)total_items * blockIdx.x / gridDim.x);
@@ -224,10 +216,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   const int count = item1 - item0;
 #ifdef RPO_DIAG
   long long *const trace_buf = g_attn_trace;
-  const int abl = g_attn_abl;
   if (threadIdx.x == 0) ATTN_TRACE(0, 12);
-#else
-  constexpr int abl = 0;
 #endif
 
   if (threadIdx.x == 0) {
@@ -343,24 +332,13 @@ __global__ void __launch_bounds__(THREADS, 1)
       // ===== O = P V issuer: A = P from shared memory (K-major 128 x 16 blocks, 32B swizzle), B = V as loaded =====
       const uint32_t fmt = Num<T>::dtype == RPO_BF16 ? 1u : 0u;
       const uint32_t idesc_o = make_idesc((int)fmt, QT, HD) | (1u << 16);  // B (= V) is MN-major
-      const uint64_t pdesc = make_smem_desc_sw32(p_base);
+      const uint64_t pdesc = make_smem_desc(p_base);
       // Issue order: round r takes the r-th key block of each of the PARTS softmax threads of a row.  The softmax
       // threads write their blocks in the same order, so a thread may overwrite its r-th block of the single P buffer
       // as soon as round r of the previous tile has been consumed (B_PFREE + r) instead of waiting for the whole P V.
-      // the order as a table in shared memory: entry i = key block, bit 7 set on the last block of a round
-      {
-        const int base_nb = geo.nblk / PARTS, extra = geo.nblk % PARTS;
-        const int rounds = base_nb + (extra ? 1 : 0);
-        int i = 0;
-        for (int r = 0; r < rounds; ++r) {
-          for (int pt = 0; pt < PARTS; ++pt) {
-            const int nbp = base_nb + (pt < extra ? 1 : 0);
-            if (r < nbp) pv_order[i++] = (uint8_t)(pt * base_nb + (pt < extra ? pt : extra) + r);
-          }
-          pv_order[i - 1] |= 0x80;
-        }
-      }
-      const int nsteps = geo.nblk;
+      // Uniform arithmetic on kernel parameters only (no table, no vector-register operands).
+      const int base_nb = geo.nblk / PARTS, extra = geo.nblk % PARTS;
+      const int rounds = base_nb + (extra ? 1 : 0);
       for (int j = 0; j < count; ++j) {
         const int x = 2 * unit_idx(j) + 1, e = x % KV_RING;
         mbar_wait(BAR(B_PFULL), (uint32_t)(j & 1));
@@ -369,12 +347,20 @@ __global__ void __launch_bounds__(THREADS, 1)
         if (j >= 1) mbar_wait(BAR(B_OFREE), (uint32_t)((j - 1) & 1));  // the previous tile's O is out of tensor memory
         tc_fence_after();
         const uint64_t vdesc = make_smem_desc(kv_base + e * kv_bytes);
-        int round = 0;
-        for (int i = 0; i < nsteps; ++i) {
-          const int ent = pv_order[i], blk = ent & 0x7f;  // 16 keys: 4 KB of P, 2 KB of V
-          umma_f16(tmem_base + O_COL, pdesc + (uint64_t)(blk * (P_BLOCK_BYTES >> 4)), vdesc + (uint64_t)(blk * 128),
-                   idesc_o, i != 0);
-          if (ent & 0x80) umma_commit(BAR(B_PFREE + round++));
+        uint32_t acc = 0;
+        for (int r = 0; r < rounds; ++r) {
+#pragma unroll
+          for (int pt = 0; pt < PARTS; ++pt) {
+            const int nbp = base_nb + (pt < extra ? 1 : 0);
+            if (r < nbp) {
+              // key block blk: 32 bytes along K inside the 128-byte row of P tile blk / 4, 2 KB of V
+              const int blk = pt * base_nb + (pt < extra ? pt : extra) + r;
+              umma_f16(tmem_base + O_COL, pdesc + (uint64_t)((blk >> 2) * (P_TILE_BYTES >> 4) + 2 * (blk & 3)),
+                       vdesc + (uint64_t)(blk * 128), idesc_o, acc);
+              acc = 1;
+            }
+          }
+          umma_commit(BAR(B_PFREE + r));
         }
         umma_commit(BAR(B_OFULL));
         if (last_of_unit(j)) umma_commit(BAR(B_KVFREE + e));  // V of the unit is dead once this O is complete
@@ -393,38 +379,50 @@ __global__ void __launch_bounds__(THREADS, 1)
     const bool tracer = threadIdx.x == PROD_WARPS * 32;
     const float sl2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
     const int nblk = geo.nblk;
-    // this thread's 16-key blocks [b0, b0 + nb): the first (nblk % PARTS) parts hold one block more
+    // this thread's 16-key blocks [b0, b0 + nb): the first (nblk % PARTS) parts hold one block more.  The kernel is
+    // instantiated with MAXB = the larger count, so blocks 0 .. MAXB-2 exist for every thread and only the last one is
+    // conditional (has_last): the hot loop carries one warp-uniform branch instead of one per block.
     const int base_nb = nblk / PARTS, extra = nblk % PARTS;
-    const int b0 = part * base_nb + min(part, extra), nb = base_nb + (part < extra ? 1 : 0);
-    // the block (local index) and element from which this thread's columns are padding (>= n); -1: none
-    const int pad_block = (n < n16 && (nblk - 1) >= b0 && (nblk - 1) < b0 + nb) ? nblk - 1 - b0 : -1;
+    const int b0 = part * base_nb + min(part, extra);
+    const bool has_last = (base_nb + (part < extra ? 1 : 0)) == MAXB;
+    // columns >= n are padding: they sit at the end of the last key block, which the last part holds
+    const bool pads = part == PARTS - 1 && n < n16;
     const int pad_first = n - (nblk - 1) * 16;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    // P block b of this row: 32 bytes at row * 32 of the block, the two 16-byte chunks swapped on odd 4-row groups
-    const uint32_t sw = (uint32_t)((row >> 2) & 1);
-    const uint32_t prow0 = p_base + (uint32_t)(row * 32) + ((0u ^ sw) << 4), prow1 = p_base + (uint32_t)(row * 32) + ((1u ^ sw) << 4);
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b0 * 16);
+    // P as the A operand of P V: 128 x 64-key tiles, K-major, 128-byte rows, 16-byte chunk index ^ (row & 7) -- the
+    // layout TMA gives the Q tile.  Key block g of this row = chunks 2 (g & 3), 2 (g & 3) + 1 of row `row` of tile g / 4.
+    const uint32_t p_row = p_base + (uint32_t)(row * ROW_BYTES);
+    const uint32_t sw = (uint32_t)(row & 7);
     // one S slot: the next S is issued when this one is in registers, poll for it half way through the blocks
     constexpr int PF_AT = SLOTS == 2 ? 0 : MAXB / 2;
     uint32_t s[MAXB][16];
+    auto load_scores = [&](uint32_t taddr) {  // all of this thread's blocks; completion: wait_scores()
+#pragma unroll
+      for (int b = 0; b < MAXB - 1; ++b) tmem_ld16_nowait(taddr + (uint32_t)(b * 16), s[b]);
+      if (has_last) tmem_ld16_nowait(taddr + (uint32_t)((MAXB - 1) * 16), s[MAXB - 1]);
+    };
+    auto wait_scores = [&]() {
+#pragma unroll
+      for (int b = 0; b < MAXB; ++b) tmem_ld_wait(s[b]);
+    };
+    auto mask_pad = [&](uint32_t (&blk)[16]) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e)
+        if (e >= pad_first) blk[e] = 0xff800000u;  // -inf: drops out of the maximum, ex2 gives 0
+    };
     bool loaded = false;  // s[] holds the scores of the tile about to be processed
     Item it = item_of(geo, item0), nx = it;
     for (int j = 0; j < count; ++j, it = nx) {
       advance(geo, nx);
       const int slot = j % SLOTS;
-      const int rows_here = it.c_rows + it.p_rows;
-      const bool valid = q * 32 < rows_here;  // warp-uniform, identical for the warps of a lane quarter
+      const bool valid = q * 32 < it.c_rows + it.p_rows;  // warp-uniform, identical for the warps of a lane quarter
       if (!loaded) {
         // every warp waits for S and arrives on "S in registers", also warps without valid rows
         mbar_wait(BAR(B_SFULL + slot), (uint32_t)((j / SLOTS) & 1));
         if (valid) {
           tc_fence_after();
-          const uint32_t taddr = lane_base + (uint32_t)(slot * SLOT_COLS);
-#pragma unroll
-          for (int b = 0; b < MAXB; ++b)
-            if (b < nb) tmem_ld16_nowait(taddr + (uint32_t)((b0 + b) * 16), s[b]);
-#pragma unroll
-          for (int b = 0; b < MAXB; ++b)
-            if (b < nb) tmem_ld_wait(s[b]);
+          load_scores(lane_base + (uint32_t)(slot * SLOT_COLS));
+          wait_scores();
           tc_fence_before();
         }
         __syncwarp();
@@ -432,47 +430,58 @@ __global__ void __launch_bounds__(THREADS, 1)
       }
       loaded = false;
       if (tracer) ATTN_TRACE(j, 4);
-      bool nvalid = false;
-      int nslot = 0;
-      uint32_t npar = 0;
       const bool have_next = j + 1 < count;
-      if (have_next) {
-        nvalid = q * 32 < nx.c_rows + nx.p_rows;
-        nslot = (j + 1) % SLOTS;
-        npar = (uint32_t)(((j + 1) / SLOTS) & 1);
-      }
+      const bool nvalid = have_next && q * 32 < nx.c_rows + nx.p_rows;
+      const int nslot = (j + 1) % SLOTS;
+      const uint32_t npar = (uint32_t)(((j + 1) / SLOTS) & 1);
       const uint32_t ntaddr = lane_base + (uint32_t)(nslot * SLOT_COLS);
       bool pf = false;  // the next tile's scores are being prefetched into the freed registers
       if (valid) {
-        // ---- padding columns (>= n, in the row's last key block) become -inf once: no special cases below ----
-#pragma unroll
-        for (int b = 0; b < MAXB; ++b) {
-          if (b == pad_block) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e)
-              if (e >= pad_first) s[b][e] = 0xff800000u;
-          }
+        if (pads) {
+          if (has_last)
+            mask_pad(s[MAXB - 1]);
+          else if (MAXB >= 2)
+            mask_pad(s[MAXB >= 2 ? MAXB - 2 : 0]);
         }
         // ---- row maximum over this thread's keys (four independent chains) ----
         float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        auto max_block = [&](const uint32_t (&blk)[16]) {
 #pragma unroll
-        for (int b = 0; b < MAXB; ++b) {
-          if (b < nb) {
+          for (int e = 0; e < 16; e += 4)
+            m4[e >> 2] = fmaxf(m4[e >> 2], fmaxf(fmaxf(__uint_as_float(blk[e]), __uint_as_float(blk[e + 1])),
+                                                 fmaxf(__uint_as_float(blk[e + 2]), __uint_as_float(blk[e + 3]))));
+        };
 #pragma unroll
-            for (int e = 0; e < 16; e += 4)
-              m4[e >> 2] = fmaxf(m4[e >> 2], fmaxf(fmaxf(__uint_as_float(s[b][e]), __uint_as_float(s[b][e + 1])),
-                                                   fmaxf(__uint_as_float(s[b][e + 2]), __uint_as_float(s[b][e + 3]))));
-          }
-        }
+        for (int b = 0; b < MAXB - 1; ++b) max_block(s[b]);
+        if (has_last) max_block(s[MAXB - 1]);
         float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
         const uint32_t rmax = red_max + (uint32_t)(((j & 1) * PARTS * QT + row) * 4);
         sts_f32(rmax + (uint32_t)(part * QT * 4), mx);
-        if (!(abl & 4)) quad_bar_sync(1 + q);
+        quad_bar_sync(1 + q);
         mx = fmaxf(fmaxf(lds_f32(rmax), lds_f32(rmax + QT * 4)), fmaxf(lds_f32(rmax + 2 * QT * 4), lds_f32(rmax + 3 * QT * 4)));
         if (tracer) ATTN_TRACE(j, 5);
-        const float off = mx * sl2;
+        const float off = mx * sl2;  // finite: every row sees key 0
         // ---- probabilities -> P blocks in shared memory, row sum ----
         float l0 = 0.f, l1 = 0.f;
+        auto prob_block = [&](int b, uint32_t (&blk)[16]) {  // b: compile-time constant at every call site
+          // the single P buffer: round b of the previous tile's P V has consumed this block
+          if (j >= 1) mbar_wait(BAR(B_PFREE + b), (uint32_t)((j - 1) & 1));
+          if (tracer && b == 0 && j > 0) ATTN_TRACE(j, 14);
+          uint32_t pk[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(blk[2 * e]), sl2, -off));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(blk[2 * e + 1]), sl2, -off));
+            l0 += p0;
+            l1 += p1;
+            pk[e] = pack2<T>(p0, p1);
+          }
+          const uint32_t g = (uint32_t)(b0 + b), tile = p_row + (g >> 2) * P_TILE_BYTES, c = 2u * (g & 3u);
+          sts128(tile + ((c ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+          sts128(tile + (((c + 1u) ^ sw) << 4), pk[4], pk[5], pk[6], pk[7]);
+          if (pf) tmem_ld16_nowait(ntaddr + (uint32_t)(b * 16), blk);
+          if (tracer && b == 0 && j > 0) ATTN_TRACE(j, 15);
+        };
 #pragma unroll
         for (int b = 0; b < MAXB; ++b) {
           if (b == PF_AT && nvalid) {
@@ -485,36 +494,16 @@ __global__ void __launch_bounds__(THREADS, 1)
             if (pf) {
               tc_fence_after();
 #pragma unroll
-              for (int c = 0; c < PF_AT; ++c)
-                if (c < nb) tmem_ld16_nowait(ntaddr + (uint32_t)((b0 + c) * 16), s[c]);
+              for (int c = 0; c < PF_AT; ++c) tmem_ld16_nowait(ntaddr + (uint32_t)(c * 16), s[c]);
             }
           }
-          if (b < nb) {
-            // the single P buffer: round b of the previous tile's P V has consumed this block
-            if (j >= 1 && !(abl & 8)) mbar_wait(BAR(B_PFREE + b), (uint32_t)((j - 1) & 1));
-            uint32_t pk[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float p0 = fmaf(__uint_as_float(s[b][2 * e]), sl2, -off), p1 = fmaf(__uint_as_float(s[b][2 * e + 1]), sl2, -off);
-              if (!(abl & 1)) {
-                p0 = ex2_approx(p0);  // ex2(-inf) = 0
-                p1 = ex2_approx(p1);
-              }
-              l0 += p0;
-              l1 += p1;
-              pk[e] = pack2<T>(p0, p1);
-            }
-            if (!(abl & 2)) {
-              sts128(prow0 + (uint32_t)((b0 + b) * P_BLOCK_BYTES), pk[0], pk[1], pk[2], pk[3]);
-              sts128(prow1 + (uint32_t)((b0 + b) * P_BLOCK_BYTES), pk[4], pk[5], pk[6], pk[7]);
-            } else if (pk[0] == 0x12345u) {
-              sts128(prow0, pk[0], pk[1], pk[2], pk[3]);
-              sts128(prow1, pk[4], pk[5], pk[6], pk[7]);
-            }
-            if (pf) tmem_ld16_nowait(ntaddr + (uint32_t)((b0 + b) * 16), s[b]);
-          }
+          if (b < MAXB - 1)
+            prob_block(b, s[b]);
+          else if (has_last)
+            prob_block(b, s[b]);
         }
-        sts_f32(red_sum + (uint32_t)((((j & 3) * PARTS + part) * QT + row) * 4), l0 + l1);
+        sts_f32(red_sum + (uint32_t)((((j & 1) * PARTS + part) * QT + row) * 4), l0 + l1);
+        if (tracer && j > 0) ATTN_TRACE(j, 9);
         // make the generic-proxy stores of P visible to the tensor core (async proxy)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       } else if (j >= 1) {
@@ -525,17 +514,15 @@ __global__ void __launch_bounds__(THREADS, 1)
       __syncwarp();
       if (tracer) ATTN_TRACE(j, 6);
       if (lane == 0) mbar_arrive(BAR(B_PFULL));
-      if (have_next && (pf || nvalid)) {
+      if (tracer && j > 0) ATTN_TRACE(j, 12);
+      if (nvalid) {
         if (!pf) {
           mbar_wait(BAR(B_SFULL + nslot), npar);
           tc_fence_after();
-#pragma unroll
-          for (int b = 0; b < MAXB; ++b)
-            if (b < nb) tmem_ld16_nowait(ntaddr + (uint32_t)((b0 + b) * 16), s[b]);
+          load_scores(ntaddr);
         }
-#pragma unroll
-        for (int b = 0; b < MAXB; ++b)
-          if (b < nb) tmem_ld_wait(s[b]);
+        wait_scores();
+        if (tracer && j > 0) ATTN_TRACE(j, 13);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(B_SFREE + nslot));
@@ -559,7 +546,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       tc_fence_after();
       if (tracer) ATTN_TRACE(j, 7);
       if (q * 32 < rows_here) {
-        const uint32_t rsum = red_sum + (uint32_t)(((j & 3) * PARTS * QT + row) * 4);
+        const uint32_t rsum = red_sum + (uint32_t)(((j & 1) * PARTS * QT + row) * 4);
         const float inv = 1.0f / ((lds_f32(rsum) + lds_f32(rsum + QT * 4)) + (lds_f32(rsum + 2 * QT * 4) + lds_f32(rsum + 3 * QT * 4)));
         T *dst = nullptr;
         if (row < it.c_rows)
@@ -601,8 +588,8 @@ __global__ void __launch_bounds__(THREADS, 1)
 }
 
 static int smem_bytes(int n16, int q_ring) {
-  return KV_RING * n16 * ROW_BYTES + (n16 >> 4) * P_BLOCK_BYTES + q_ring * Q_TILE_BYTES + 8 * 28 +
-         (2 + 4) * PARTS * QT * 4 + 32 + 1024;
+  return KV_RING * n16 * ROW_BYTES + (((n16 >> 4) + 3) / 4) * P_TILE_BYTES + q_ring * Q_TILE_BYTES + 8 * 28 +
+         (2 + 2) * PARTS * QT * 4 + 1024;
 }
 
 }  // namespace atc
@@ -663,20 +650,30 @@ int ro_attention_fwd_dense(const T *qkv_ctx, const T *q_prompt, T *out_ctx, T *o
     dim3 grid((unsigned)(items < sms ? items : sms));
     prof_tag("attn_fwd_tc G=%d H=%d K=%d n=%d", G, H, K, n);
     auto launch = [&](auto kernel) -> int {
-      static int configured = 0;  // one per instantiation of the lambda's argument type
-      if (smem > configured) {
+      // all instantiations share one function-pointer type: remember the configured size per kernel
+      static std::map<const void *, int> configured;
+      int &have = configured[reinterpret_cast<const void *>(kernel)];
+      if (smem > have) {
         RPO_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = smem;
+        have = smem;
       }
       RPO_CHECK_CUDA(launch_pdl(kernel, grid, dim3(THREADS), (size_t)smem, st, map_full, map_kvt, map_qt, map_prompt,
                                 out_ctx, out_prompt, geo, (int)items));
       return RPO_OK;
     };
-    int s;
-    if (two_slots)
-      s = launch(ro_attn_fwd_tc<T, 4, 2>);
-    else
-      s = launch(ro_attn_fwd_tc<T, 5, 1>);
+    // MAXB = key blocks of the busiest softmax thread (see the kernel)
+    const int rounds = geo.nblk / PARTS + (geo.nblk % PARTS ? 1 : 0);
+    int s = RPO_ERR_INVALID;
+    if (two_slots) {
+      switch (rounds) {
+        case 1: s = launch(ro_attn_fwd_tc<T, 1, 2>); break;
+        case 2: s = launch(ro_attn_fwd_tc<T, 2, 2>); break;
+        case 3: s = launch(ro_attn_fwd_tc<T, 3, 2>); break;
+        default: s = launch(ro_attn_fwd_tc<T, 4, 2>); break;  // n16 <= 224: at most 14 blocks
+      }
+    } else {
+      s = rounds <= 4 ? launch(ro_attn_fwd_tc<T, 4, 1>) : launch(ro_attn_fwd_tc<T, 5, 1>);  // 15 .. 18 blocks
+    }
     RPO_TRY(s);
     RPO_LAUNCH_CHECK();
     return RPO_OK;
@@ -684,10 +681,6 @@ int ro_attention_fwd_dense(const T *qkv_ctx, const T *q_prompt, T *out_ctx, T *o
 }
 
 #ifdef RPO_DIAG
-extern "C" int rpo_diag_set_attn_ablation(int bits) {
-  RPO_CHECK_CUDA(cudaMemcpyToSymbol(atc::g_attn_abl, &bits, sizeof(bits)));
-  return RPO_OK;
-}
 extern "C" int rpo_diag_set_attn_trace(long long *buf) {
   RPO_CHECK_CUDA(cudaMemcpyToSymbol(atc::g_attn_trace, &buf, sizeof(buf)));
   return RPO_OK;

@@ -16,9 +16,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from rpo_b200 import _lib  # noqa: E402
 
-EV = {9: "kv_issue", 10: "q_issue", 11: "s_wait_ofree", 0: "s_issue", 3: "sm_sfull", 4: "sm_loaded", 5: "sm_maxx",
-      6: "sm_pdone", 1: "pv_pfull", 2: "pv_issued", 7: "ep_ofull", 8: "ep_done"}
-ORDER = [9, 10, 11, 0, 3, 4, 5, 6, 1, 2, 7, 8]
+EV = {10: "q_issue", 0: "s_issue", 3: "sm_sfull", 4: "sm_loaded", 5: "sm_maxx", 14: "sm_pfree0", 15: "sm_blk0",
+      9: "sm_blocks", 6: "sm_pdone", 12: "sm_arrived", 13: "sm_nextld", 1: "pv_pfull", 2: "pv_issued", 7: "ep_ofull",
+      8: "ep_done"}
+ORDER = [10, 0, 3, 4, 5, 14, 15, 9, 6, 12, 13, 1, 2, 7, 8]
 
 
 def main():
@@ -27,11 +28,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--K", type=int, default=24)
     ap.add_argument("--prec", default="fp16")
-    ap.add_argument("--ablation", type=int, default=0)
     a = ap.parse_args()
     lib = _lib.load()
-    if a.ablation:
-        _lib.check(lib.rpo_diag_set_attn_ablation(a.ablation))
     if not hasattr(lib, "rpo_diag_set_attn_trace"):
         raise SystemExit("not a diagnostics build: RPO_DIAG=1 python -m rpo_b200.build --force")
     dt = {"fp16": torch.float16, "bf16": torch.bfloat16}[a.prec]
@@ -68,11 +66,11 @@ def main():
     t0 = int(nz.min())
     print(f"kernel entry {int(t[0, 12]) - t0}, prologue done {int(t[0, 13]) - t0}, all roles done {int(t[0, 14]) - t0}, "
           f"tmem released {int(t[0, 15]) - t0} (SM clocks)")
-    print("tile  " + " ".join(f"{EV[e]:>12s}" for e in ORDER))
+    print("tile  " + " ".join(f"{EV[e]:>10s}" for e in ORDER))
     for j in range(64):
         if int(t[j].max()) == 0:
             break
-        print(f"{j:4d}  " + " ".join(f"{(int(t[j, e]) - t0) if t[j, e] > 0 else -1:12d}" for e in ORDER))
+        print(f"{j:4d}  " + " ".join(f"{(int(t[j, e]) - t0) if t[j, e] > 0 else -1:10d}" for e in ORDER))
 
 
 if __name__ == "__main__":

@@ -216,10 +216,7 @@ def main():
     ap.add_argument("--no-dense", action="store_true", help="vision attention through the mma.sync kernel")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches (host-bound for short kernels)")
     ap.add_argument("--nbuf", type=int, default=0, help="override the number of rotated buffers (1 = warm L2)")
-    ap.add_argument("--attn-ablation", type=int, default=0, help="diagnostics build only: rpo_diag_set_attn_ablation bits")
     a = ap.parse_args()
-    if a.attn_ablation:
-        _lib.check(_lib.load().rpo_diag_set_attn_ablation(a.attn_ablation))
     hbm, tf, src = peaks()
     print(f"# kernel_bench {a.tag} prec={a.prec} arch={a.arch} B={a.batch} K={a.K} C={a.classes} "
           f"peaks: {hbm:.0f} GB/s, {tf:.0f} TF/s ({src})")
