@@ -77,24 +77,6 @@ __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float lo, float hi) {
   return *reinterpret_cast<uint32_t *>(&v);
 }
 
-__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-// The wait names the destination registers of the load it completes as read-write operands, so the
-// compiler cannot move a use of them above it.
-__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-               :
-               : "memory");
-}
 // explicit shared-space accesses with 32-bit addresses (a generic pointer into the dynamic shared memory makes the
 // compiler emit generic ST.E / LD.E and carry 64-bit addresses through the softmax loop)
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
@@ -587,6 +569,401 @@ __global__ void __launch_bounds__(THREADS, 1)
   if (threadIdx.x == 0) ATTN_TRACE(0, 15);
 }
 
+// ================================================================================================================
+// Two-slot form (n16 <= 224: ViT-B/16): the exponentials of consecutive tiles are taken by two warp groups in turn
+// (tile j -> group j % 2 -> TMEM slot j % 2), ONE THREAD PER QUERY ROW, so no thread ever exchanges anything with
+// another.  The row maximum is taken by a third group (the epilogue warps, which have the time) as soon as S is
+// complete: it pulls the row out of tensor memory seven 16-column loads at a time and leaves max / 8 log2 e in
+// shared memory.  A softmax thread then makes ONE pass: scores out of tensor memory 32 at a time (the next 32 in
+// flight), p = ex2(s / 8 log2 e - that), f32 row sum, and the rounded probabilities go back into tensor memory over
+// the scores already consumed (two 16-bit values per 32-bit column: the layout tcgen05.mma reads an A operand from).
+// O = P V takes A straight from tensor memory.  While one group waits for its next tile (P V of the slot's previous
+// tile, S, maximum: about as long as the other group's exponentials take) the other group has the MUFU pipe of the
+// scheduler to itself: that pipe (16 ex2 / clk / SM) is the resource the kernel is built to keep busy.
+//
+//   warp 0 (one thread)   TMA producer (as above)
+//   warp 1 (one thread)   S = Q K^T into slot j % 2 once P V of tile j-2 has consumed that slot's P
+//   warp 2 (one thread)   O = P V (A = P in TMEM, B = V as loaded, MN-major) into the 64 columns behind the slots
+//   warps 4..7 / 8..11    softmax groups 0 / 1
+//   warps 12..15          per tile: epilogue of tile j (O out of TMEM, times 1 / row sum, into a staging tile that
+//                         one thread hands to the TMA: cp.async.bulk.tensor store), then the row maxima of tile j+2
+// Registers (setmaxnreg, out of 512 x 128): producers 40, softmax 144, epilogue / maximum 168.
+static constexpr int PP_THREADS = 512;
+static constexpr int PP_SLOT_COLS = 224;
+static constexpr int PP_O_COL = 448;
+static constexpr int PP_Q_RING = 4;
+static constexpr int PP_O_STAGES = 3;
+static constexpr int PP_REGS_PROD = 40, PP_REGS_SOFTMAX = 144, PP_REGS_AUX = 168;
+
+// NBLK_CT: number of 16-key blocks when known at compile time (13: the 197 keys of ViT-B/16 -- the softmax pass is
+// then one straight-line block the scheduler can pipeline across key blocks), 0: taken from geo at run time
+template <typename T, int NBLK_CT>
+__global__ void __launch_bounds__(PP_THREADS, 1)
+    ro_attn_fwd_pp(const __grid_constant__ CUtensorMap map_full,   // q|k|v matrix, box 64 x 128
+                   const __grid_constant__ CUtensorMap map_kvt,    // q|k|v matrix, box 64 x (n16 % 128)
+                   const __grid_constant__ CUtensorMap map_qt,     // q|k|v matrix, box 64 x (n % 128)
+                   const __grid_constant__ CUtensorMap map_prompt, // prompt-q matrix, box 64 x K
+                   const __grid_constant__ CUtensorMap omap_full,   // context output, box 64 x 128
+                   const __grid_constant__ CUtensorMap omap_tail,   // context output, box 64 x (n % 128)
+                   const __grid_constant__ CUtensorMap omap_prompt, // prompt output, box 64 x K
+                   Geo geo, int total_items) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int n = geo.n, n16 = geo.n16, K = geo.K, H = geo.H;
+  const int D = H * HD;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kv_bytes = n16 * ROW_BYTES;
+  // shared memory: [K|V ring of 3 | Q ring | O staging x 3 | barriers | row sums | row maxima]
+  const uint32_t kv_base = smem_u32(smem);
+  const uint32_t q_base = kv_base + KV_RING * kv_bytes;
+  const uint32_t o_base = q_base + PP_Q_RING * Q_TILE_BYTES;
+  uint8_t *tail = smem + KV_RING * kv_bytes + (PP_Q_RING + PP_O_STAGES) * Q_TILE_BYTES;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(tail);
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int idx) { return bar0 + 8u * idx; };
+  constexpr int B_KVFULL = 0, B_KVFREE = 3, B_QFULL = 6, B_QFREE = 10, B_SFULL = 14, B_SFREE = 16, B_PFULL = 18,
+                B_OFULL = 20, B_OFREE = 21, B_MAXFULL = 22, N_BARS = 24;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + N_BARS);
+  // f32 [4][QT]: the row sums of tile j in buffer j % 4 (written at the end of the softmax of tile j, read by the
+  // epilogue of tile j; the softmax of tile j+4 starts after P V of tile j+2, which waited for the epilogue of j+1)
+  const uint32_t red_sum = smem_u32(bars + N_BARS + 1);
+  // f32 [2][QT]: row maximum / 8 log2 e of the S in slot s (written by the maximum pass once S is complete, read by
+  // the softmax of that tile before it stores its P; the slot's next S follows that P's P V)
+  const uint32_t row_off = red_sum + 4 * QT * 4;
+
+  const int item0 = (int)((long long)total_items * blockIdx.x / gridDim.x);
+  const int item1 = (int)((long long)total_items * (blockIdx.x + 1) / gridDim.x);
+  const int count = item1 - item0;
+#ifdef RPO_DIAG
+  long long *const trace_buf = g_attn_trace;
+  if (threadIdx.x == 0) ATTN_TRACE(0, 12);
+#endif
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_full)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_kvt)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_qt)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_prompt)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&omap_full)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&omap_tail)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&omap_prompt)) : "memory");
+    for (int i = 0; i < KV_RING; ++i) {
+      mbar_init(BAR(B_KVFULL + i), 1);
+      mbar_init(BAR(B_KVFREE + i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(BAR(B_SFULL + i), 1);
+      mbar_init(BAR(B_SFREE + i), 1);
+      mbar_init(BAR(B_PFULL + i), 4);
+      mbar_init(BAR(B_MAXFULL + i), 4);
+    }
+    mbar_init(BAR(B_OFULL), 1);
+    mbar_init(BAR(B_OFREE), 4);
+    for (int i = 0; i < PP_Q_RING; ++i) {
+      mbar_init(BAR(B_QFULL + i), 1);
+      mbar_init(BAR(B_QFREE + i), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  if (threadIdx.x == 0) ATTN_TRACE(0, 13);
+
+  // K of unit u (= image, head; counted from the CTA's first) lives in ring entry (2u) % 3, V in (2u + 1) % 3
+  const int tiles = geo.tiles;
+  const int unit0 = item0 / tiles;
+  auto unit_idx = [&](int j) { return (item0 + j) / tiles - unit0; };
+  auto first_of_unit = [&](int j) { return j == 0 || (item0 + j) % tiles == 0; };
+  auto last_of_unit = [&](int j) { return j + 1 == count || (item0 + j + 1) % tiles == 0; };
+
+  if (warp < 4) setmaxnreg_dec<PP_REGS_PROD>();
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      pdl_wait();
+      for (int j = 0; j < count; ++j) {
+        const Item it = item_of(geo, item0 + j);
+        if (first_of_unit(j)) {
+          const int u = unit_idx(j);
+#pragma unroll
+          for (int kv = 0; kv < 2; ++kv) {  // K, then V
+            const int x = 2 * u + kv, e = x % KV_RING, use = x / KV_RING;
+            if (use >= 1) mbar_wait(BAR(B_KVFREE + e), (uint32_t)((use - 1) & 1));
+            const uint32_t dst = kv_base + e * kv_bytes;
+            mbar_arrive_expect_tx(BAR(B_KVFULL + e), (uint32_t)kv_bytes);
+            for (int r = 0; r < n16; r += 128)
+              tma_load_2d(dst + r * ROW_BYTES, (n16 - r >= 128) ? &map_full : &map_kvt, BAR(B_KVFULL + e),
+                          (1 + kv) * D + it.h * HD, it.g * n + r);
+          }
+        }
+        const int qs = j % PP_Q_RING;
+        if (j >= PP_Q_RING) mbar_wait(BAR(B_QFREE + qs), (uint32_t)(((j / PP_Q_RING) - 1) & 1));
+        const uint32_t Qs = q_base + qs * Q_TILE_BYTES;
+        mbar_arrive_expect_tx(BAR(B_QFULL + qs), (uint32_t)((it.c_rows + it.p_rows) * ROW_BYTES));
+        if (it.c_rows == QT)
+          tma_load_2d(Qs, &map_full, BAR(B_QFULL + qs), it.h * HD, it.g * n + it.t * QT);
+        else if (it.c_rows > 0)
+          tma_load_2d(Qs, &map_qt, BAR(B_QFULL + qs), it.h * HD, it.g * n + it.t * QT);
+        if (it.p_rows > 0)
+          tma_load_2d(Qs + geo.prompt_row * ROW_BYTES, &map_prompt, BAR(B_QFULL + qs), it.h * HD, it.g * K);
+        ATTN_TRACE(j, 10);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // ===== S = Q K^T issuer =====
+      const uint32_t fmt = Num<T>::dtype == RPO_BF16 ? 1u : 0u;
+      const uint32_t idesc_s = make_idesc((int)fmt, QT, n16);
+      for (int j = 0; j < count; ++j) {
+        const int slot = j & 1, qs = j % PP_Q_RING;
+        const int x = 2 * unit_idx(j), e = x % KV_RING;
+        mbar_wait(BAR(B_QFULL + qs), (uint32_t)((j / PP_Q_RING) & 1));
+        if (first_of_unit(j)) mbar_wait(BAR(B_KVFULL + e), (uint32_t)((x / KV_RING) & 1));
+        // the slot's previous P has been consumed by its P V
+        if (j >= 2) mbar_wait(BAR(B_SFREE + slot), (uint32_t)(((j >> 1) - 1) & 1));
+        tc_fence_after();
+        const uint32_t tslot = tmem_base + (uint32_t)(slot * PP_SLOT_COLS);
+        const uint64_t adesc = make_smem_desc(q_base + qs * Q_TILE_BYTES), bdesc = make_smem_desc(kv_base + e * kv_bytes);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_f16(tslot, adesc + 2u * k, bdesc + 2u * k, idesc_s, k != 0);
+        umma_commit(BAR(B_SFULL + slot));
+        umma_commit(BAR(B_QFREE + qs));
+        if (last_of_unit(j)) umma_commit(BAR(B_KVFREE + e));  // K of the unit is dead once this S is complete
+        ATTN_TRACE(j, 0);
+      }
+    }
+  } else if (warp == 2) {
+    if (elect_one()) {
+      // ===== O = P V issuer =====
+      const uint32_t fmt = Num<T>::dtype == RPO_BF16 ? 1u : 0u;
+      const uint32_t idesc_o = make_idesc((int)fmt, QT, HD) | (1u << 16);  // B (= V) is MN-major
+      const int nblk = NBLK_CT ? NBLK_CT : geo.nblk;
+      for (int j = 0; j < count; ++j) {
+        const int slot = j & 1;
+        const int x = 2 * unit_idx(j) + 1, e = x % KV_RING;
+        if (first_of_unit(j)) mbar_wait(BAR(B_KVFULL + e), (uint32_t)((x / KV_RING) & 1));
+        if (j >= 1) mbar_wait(BAR(B_OFREE), (uint32_t)((j - 1) & 1));  // the previous tile's O is out of tensor memory
+        mbar_wait(BAR(B_PFULL + slot), (uint32_t)((j >> 1) & 1));
+        ATTN_TRACE(j, 1);
+        tc_fence_after();
+        const uint64_t vdesc = make_smem_desc(kv_base + e * kv_bytes);
+        const uint32_t pcol = tmem_base + (uint32_t)(slot * PP_SLOT_COLS);
+        for (int blk = 0; blk < nblk; ++blk)  // 16 keys: 8 columns of P, 2 KB of V
+          umma_f16_ts(tmem_base + PP_O_COL, pcol + (uint32_t)(blk * 8), vdesc + (uint64_t)(blk * 128), idesc_o, blk != 0);
+        umma_commit(BAR(B_OFULL));
+        umma_commit(BAR(B_SFREE + slot));
+        if (last_of_unit(j)) umma_commit(BAR(B_KVFREE + e));  // V of the unit is dead once this O is complete
+        ATTN_TRACE(j, 2);
+      }
+    }
+  } else if (warp >= 4 && warp < 12) {
+    // ===== softmax: group wg takes tiles j = wg, wg + 2, ...; thread = query row = TMEM lane =====
+    setmaxnreg_inc<PP_REGS_SOFTMAX>();
+    const int wg = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const bool tracer = (threadIdx.x & 127) == 0;
+    const float sl2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+    const int nblk = NBLK_CT ? NBLK_CT : geo.nblk;
+    const int pad_first = n - (nblk - 1) * 16;  // valid keys of the last 16-key block
+    const uint32_t sbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(wg * PP_SLOT_COLS);
+    const uint32_t my_off = row_off + (uint32_t)((wg * QT + row) * 4);
+    for (int j = wg; j < count; j += 2) {
+      const Item it = item_of(geo, item0 + j);
+      const bool valid = q * 32 < it.c_rows + it.p_rows;  // warp-uniform
+      mbar_wait(BAR(B_MAXFULL + wg), (uint32_t)((j >> 1) & 1));
+      if (tracer) ATTN_TRACE(j, 5);
+      if (valid) {
+        tc_fence_after();
+        uint32_t s0[16], s1[16], t0[16], t1[16];
+        tmem_ld16_nowait(sbase, s0);
+        if (1 < nblk) tmem_ld16_nowait(sbase + 16u, s1);
+        const float off = lds_f32(my_off);  // finite: every row sees key 0
+        const uint64_t sl2x2 = pack_f32x2(sl2, sl2), noff2 = pack_f32x2(-off, -off);
+        uint64_t lsum = pack_f32x2(0.f, 0.f);
+        // probabilities of key block blk into tensor memory (over scores already consumed), row sum
+        auto prob_block = [&](int blk, uint32_t (&sc)[16]) {
+          if (blk == nblk - 1) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (e >= pad_first) sc[e] = 0xff800000u;  // -inf: ex2 gives 0
+          }
+          uint32_t pk[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float x0, x1;
+            unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(sc[2 * e]), __uint_as_float(sc[2 * e + 1])), sl2x2, noff2), x0, x1);
+            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+            lsum = add_f32x2(lsum, pack_f32x2(p0, p1));  // even keys in the low lane, odd keys in the high lane
+            pk[e] = pack2<T>(p0, p1);
+          }
+          tmem_st8(sbase + (uint32_t)(blk * 8), pk);
+        };
+#pragma unroll
+        for (int blk = 0; blk < nblk; blk += 4) {
+          tmem_ld_wait(s0);
+          tmem_ld_wait(s1);
+          if (blk + 2 < nblk) tmem_ld16_nowait(sbase + (uint32_t)((blk + 2) * 16), t0);
+          if (blk + 3 < nblk) tmem_ld16_nowait(sbase + (uint32_t)((blk + 3) * 16), t1);
+          prob_block(blk, s0);
+          if (blk + 1 < nblk) prob_block(blk + 1, s1);
+          if (blk + 2 < nblk) {
+            tmem_ld_wait(t0);
+            tmem_ld_wait(t1);
+            if (blk + 4 < nblk) tmem_ld16_nowait(sbase + (uint32_t)((blk + 4) * 16), s0);
+            if (blk + 5 < nblk) tmem_ld16_nowait(sbase + (uint32_t)((blk + 5) * 16), s1);
+            prob_block(blk + 2, t0);
+            if (blk + 3 < nblk) prob_block(blk + 3, t1);
+          }
+        }
+        float l0, l1;
+        unpack_f32x2(lsum, l0, l1);
+        sts_f32(red_sum + (uint32_t)((((j & 3) * QT) + row) * 4), l0 + l1);
+        tmem_st_wait();
+        tc_fence_before();
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(B_PFULL + wg));
+      if (tracer) ATTN_TRACE(j, 6);
+    }
+  } else if (warp >= 12) {
+    // ===== epilogue of tile j, then the row maxima of tile j+2: one thread per query row =====
+    setmaxnreg_inc<PP_REGS_AUX>();
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const bool tracer = threadIdx.x == 12 * 32;
+    const float sl2 = 0.125f * 1.4426950408889634f;
+    const int nblk = NBLK_CT ? NBLK_CT : geo.nblk;
+    const int pad_first = n - (nblk - 1) * 16;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t taddr = lane_base + PP_O_COL;
+    // row maxima of tile jj: the row out of tensor memory, seven loads (112 columns) in flight
+    auto max_job = [&](int jj) {
+      const Item mi = item_of(geo, item0 + jj);
+      const int slot = jj & 1;
+      mbar_wait(BAR(B_SFULL + slot), (uint32_t)((jj >> 1) & 1));
+      if (tracer) ATTN_TRACE(jj, 3);
+      if (q * 32 < mi.c_rows + mi.p_rows) {
+        tc_fence_after();
+        const uint32_t sb = lane_base + (uint32_t)(slot * PP_SLOT_COLS);
+        uint32_t A[7][16];
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        auto fold = [&](int blk, uint32_t (&x)[16]) {
+          if (blk == nblk - 1) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (e >= pad_first) x[e] = 0xff800000u;  // -inf: drops out of the maximum
+          }
+#pragma unroll
+          for (int e = 0; e < 16; e += 4)
+            m4[e >> 2] = fmaxf(m4[e >> 2], fmaxf(fmaxf(__uint_as_float(x[e]), __uint_as_float(x[e + 1])),
+                                                 fmaxf(__uint_as_float(x[e + 2]), __uint_as_float(x[e + 3]))));
+        };
+#pragma unroll
+        for (int b0 = 0; b0 < 14; b0 += 7) {  // two batches of seven 16-key blocks (nblk <= 14)
+          if (b0 < nblk) {
+            // unconditional loads: columns behind the last key block are stale, inside the slot, and never folded
+#pragma unroll
+            for (int i = 0; i < 7; ++i) tmem_ld16_nowait(sb + (uint32_t)((b0 + i) * 16), A[i]);
+#pragma unroll
+            for (int i = 0; i < 7; ++i) tmem_ld_wait(A[i]);
+#pragma unroll
+            for (int i = 0; i < 7; ++i)
+              if (b0 + i < nblk) fold(b0 + i, A[i]);
+          }
+        }
+        sts_f32(row_off + (uint32_t)((slot * QT + row) * 4), fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * sl2);
+        tc_fence_before();
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(B_MAXFULL + slot));
+    };
+    Item it = item_of(geo, item0);
+    // j = -2, -1: only the maxima of tiles 0 and 1.  O of tile j is complete before S of tile j+2 (which waits for
+    // that P V): epilogue first, it ends about when that S does
+    for (int j = -2; j < count; ++j) {
+      if (j < 0) {
+        if (j + 2 < count) max_job(j + 2);
+        continue;
+      }
+      if (j == 0) pdl_wait();
+      const int rows_here = it.c_rows + it.p_rows;
+      mbar_wait(BAR(B_OFULL), (uint32_t)(j & 1));
+      tc_fence_after();
+      if (tracer) ATTN_TRACE(j, 7);
+      const bool valid = q * 32 < rows_here;
+      uint32_t acc[4][16];
+      if (valid) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld16_nowait(taddr + (uint32_t)(c * 16), acc[c]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld_wait(acc[c]);
+      }
+      // O is in registers: the next P V may overwrite it
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(B_OFREE));
+      // O times 1 / row sum into the staging tile (rows of 128 B, 16-byte chunk index ^ (row & 7): the layout a
+      // 128B-swizzled tensor map reads), then ONE thread hands the tile to the TMA: context rows and prompt rows are
+      // two boxes of it.  Three staging tiles: the tile written now was read by the store of three tiles ago, which
+      // the issuing thread has waited for before the previous tile's barrier.
+      const uint32_t stage = o_base + (uint32_t)((j % PP_O_STAGES) * Q_TILE_BYTES);
+      if (valid) {
+        const float inv = 1.0f / lds_f32(red_sum + (uint32_t)((((j & 3) * QT) + row) * 4));
+        const uint32_t srow = stage + (uint32_t)(row * ROW_BYTES);
+        const uint32_t sw = (uint32_t)(row & 7);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {
+            sts128(srow + ((((uint32_t)(2 * c + v)) ^ sw) << 4),
+                   pack2<T>(__uint_as_float(acc[c][8 * v + 0]) * inv, __uint_as_float(acc[c][8 * v + 1]) * inv),
+                   pack2<T>(__uint_as_float(acc[c][8 * v + 2]) * inv, __uint_as_float(acc[c][8 * v + 3]) * inv),
+                   pack2<T>(__uint_as_float(acc[c][8 * v + 4]) * inv, __uint_as_float(acc[c][8 * v + 5]) * inv),
+                   pack2<T>(__uint_as_float(acc[c][8 * v + 6]) * inv, __uint_as_float(acc[c][8 * v + 7]) * inv));
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 12 * 32) {
+        if (it.c_rows == QT)
+          tma_store_2d(&omap_full, stage, it.h * HD, it.g * n + it.t * QT);
+        else if (it.c_rows > 0)
+          tma_store_2d(&omap_tail, stage, it.h * HD, it.g * n + it.t * QT);
+        if (it.p_rows > 0)
+          tma_store_2d(&omap_prompt, stage + (uint32_t)(geo.prompt_row * ROW_BYTES), it.h * HD, it.g * K);
+        tma_store_commit();
+        tma_store_wait_read<1>();  // the store of the previous tile has read its staging tile
+      }
+      if (tracer) ATTN_TRACE(j, 8);
+      advance(geo, it);
+      if (j + 2 < count) max_job(j + 2);
+    }
+    if (threadIdx.x == 12 * 32) tma_store_wait_read<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) ATTN_TRACE(0, 14);
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+  if (threadIdx.x == 0) ATTN_TRACE(0, 15);
+}
+
+static int pp_smem_bytes(int n16) {
+  return KV_RING * n16 * ROW_BYTES + (PP_Q_RING + PP_O_STAGES) * Q_TILE_BYTES + 8 * 26 + (4 + 2) * QT * 4 + 1024;
+}
+
 static int smem_bytes(int n16, int q_ring) {
   return KV_RING * n16 * ROW_BYTES + (((n16 >> 4) + 3) / 4) * P_TILE_BYTES + q_ring * Q_TILE_BYTES + 8 * 28 +
          (2 + 2) * PARTS * QT * 4 + 1024;
@@ -600,7 +977,7 @@ bool ro_attention_fwd_dense_supported(int dtype, int n, int K, int H) {
   const int n16 = (n + 15) & ~15;
   if (n16 > 288) return false;                     // 18 key blocks: 5 per softmax thread at most; S + O within 512 TMEM columns
   if (K > 0 && (n % 128) + K > 128) return false;  // all prompt rows in one query tile
-  if (atc::smem_bytes(n16, 2) > 227 * 1024) return false;
+  if ((n16 <= atc::PP_SLOT_COLS ? atc::pp_smem_bytes(n16) : atc::smem_bytes(n16, 2)) > 227 * 1024) return false;
   return true;
 }
 
@@ -630,11 +1007,11 @@ int ro_attention_fwd_dense(const T *qkv_ctx, const T *q_prompt, T *out_ctx, T *o
     // S as one UMMA N block up to 256 keys, else two (144 + the rest: both multiples of 16, the second starts on an
     // 8-row group of the 128B-swizzled K tile)
     geo.n_first = n16 <= 256 ? n16 : 144;
-    const bool two_slots = n16 <= 224;  // two S / P slots of 224 columns beside the 64 columns of O
+    const bool two_slots = n16 <= PP_SLOT_COLS;  // two S / P slots of 224 columns beside the 64 columns of O
     int q_ring = MAX_Q_RING;
     while (q_ring > 2 && smem_bytes(n16, q_ring) > 227 * 1024) --q_ring;
     geo.q_ring = q_ring;
-    const int smem = smem_bytes(n16, q_ring);
+    const int smem = two_slots ? pp_smem_bytes(n16) : smem_bytes(n16, q_ring);
     CUtensorMap map_full, map_kvt, map_qt, map_prompt;
     const long long Mc = (long long)G * n;
     RPO_TRY(make_map(&map_full, Num<T>::dtype, qkv_ctx, Mc, 3 * D, 3LL * D, 128));
@@ -649,30 +1026,43 @@ int ro_attention_fwd_dense(const T *qkv_ctx, const T *q_prompt, T *out_ctx, T *o
     const int sms = sm_count();
     dim3 grid((unsigned)(items < sms ? items : sms));
     prof_tag("attn_fwd_tc G=%d H=%d K=%d n=%d", G, H, K, n);
-    auto launch = [&](auto kernel) -> int {
-      // all instantiations share one function-pointer type: remember the configured size per kernel
-      static std::map<const void *, int> configured;
-      int &have = configured[reinterpret_cast<const void *>(kernel)];
+    // all instantiations of a kernel share one function-pointer type: remember the configured size per kernel
+    static std::map<const void *, int> configured;
+    auto configure = [&](const void *kernel) -> int {
+      int &have = configured[kernel];
       if (smem > have) {
         RPO_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         have = smem;
       }
-      RPO_CHECK_CUDA(launch_pdl(kernel, grid, dim3(THREADS), (size_t)smem, st, map_full, map_kvt, map_qt, map_prompt,
-                                out_ctx, out_prompt, geo, (int)items));
       return RPO_OK;
     };
-    // MAXB = key blocks of the busiest softmax thread (see the kernel)
-    const int rounds = geo.nblk / PARTS + (geo.nblk % PARTS ? 1 : 0);
     int s = RPO_ERR_INVALID;
     if (two_slots) {
-      switch (rounds) {
-        case 1: s = launch(ro_attn_fwd_tc<T, 1, 2>); break;
-        case 2: s = launch(ro_attn_fwd_tc<T, 2, 2>); break;
-        case 3: s = launch(ro_attn_fwd_tc<T, 3, 2>); break;
-        default: s = launch(ro_attn_fwd_tc<T, 4, 2>); break;  // n16 <= 224: at most 14 blocks
-      }
+      // the output leaves through the TMA as well: context tiles (full / last) and the prompt rows
+      CUtensorMap omap_full, omap_tail, omap_prompt;
+      RPO_TRY(make_map(&omap_full, Num<T>::dtype, out_ctx, Mc, D, D, 128));
+      RPO_TRY(make_map(&omap_tail, Num<T>::dtype, out_ctx, Mc, D, D, n % 128 ? n % 128 : 128));
+      if (K > 0)
+        RPO_TRY(make_map(&omap_prompt, Num<T>::dtype, out_prompt, (long long)G * K, D, D, K));
+      else
+        omap_prompt = omap_full;
+      auto launch = [&](auto kernel) -> int {
+        RPO_TRY(configure(reinterpret_cast<const void *>(kernel)));
+        RPO_CHECK_CUDA(launch_pdl(kernel, grid, dim3(PP_THREADS), (size_t)smem, st, map_full, map_kvt, map_qt, map_prompt,
+                                  omap_full, omap_tail, omap_prompt, geo, (int)items));
+        return RPO_OK;
+      };
+      s = geo.nblk == 13 ? launch(ro_attn_fwd_pp<T, 13>) : launch(ro_attn_fwd_pp<T, 0>);
     } else {
-      s = rounds <= 4 ? launch(ro_attn_fwd_tc<T, 4, 1>) : launch(ro_attn_fwd_tc<T, 5, 1>);  // 15 .. 18 blocks
+      auto launch = [&](auto kernel) -> int {
+        RPO_TRY(configure(reinterpret_cast<const void *>(kernel)));
+        RPO_CHECK_CUDA(launch_pdl(kernel, grid, dim3(THREADS), (size_t)smem, st, map_full, map_kvt, map_qt, map_prompt,
+                                  out_ctx, out_prompt, geo, (int)items));
+        return RPO_OK;
+      };
+      // 15 .. 18 key blocks: MAXB = key blocks of the busiest softmax thread (see the kernel)
+      const int rounds = geo.nblk / PARTS + (geo.nblk % PARTS ? 1 : 0);
+      s = rounds <= 4 ? launch(ro_attn_fwd_tc<T, 4, 1>) : launch(ro_attn_fwd_tc<T, 5, 1>);
     }
     RPO_TRY(s);
     RPO_LAUNCH_CHECK();

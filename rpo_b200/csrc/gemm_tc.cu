@@ -266,16 +266,6 @@ __device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
   return v;
 }
 
-// TMA store of a staged slab (shared -> global, bulk async-group completion)
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(map)),
-               "r"(src), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-
 template <typename T, int BN, bool TMA_OK = true>
 struct Epi {
   using T2 = typename Pk<T>::T2;
@@ -513,7 +503,7 @@ struct Epi {
       if (TMA_OUT && use_tma) {
         // the next drain overwrites the OTHER buffer, last read by the store issued one slab ago: that store has
         // finished reading before anybody passes the barrier below
-        if (etid_all == 0) tma_store_wait_read();
+        if (etid_all == 0) tma_store_wait_read<0>();
         named_bar_sync<GROUP_THREADS>(2 + grp);  // slab staged, visible to the async proxy
         if (straddle) {
           // the one tile of a row-split output that holds rows of both destinations leaves through plain stores
@@ -541,7 +531,7 @@ struct Epi {
   // after the last tile: the issuing thread's stores must have READ their slabs before the CTA retires its shared memory
   __device__ __forceinline__ void finish() {
     if constexpr (TMA_OUT) {
-      if (threadIdx.x == 64) tma_store_wait_read();  // (the writes themselves complete with the grid)
+      if (threadIdx.x == 64) tma_store_wait_read<0>();  // (the writes themselves complete with the grid)
     }
   }
 };

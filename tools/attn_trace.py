@@ -66,11 +66,12 @@ def main():
     t0 = int(nz.min())
     print(f"kernel entry {int(t[0, 12]) - t0}, prologue done {int(t[0, 13]) - t0}, all roles done {int(t[0, 14]) - t0}, "
           f"tmem released {int(t[0, 15]) - t0} (SM clocks)")
-    print("tile  " + " ".join(f"{EV[e]:>10s}" for e in ORDER))
+    order = [e for e in ORDER if int(t[1:, e].max()) > 0]  # the two kernels record different sub-phases
+    print("tile  " + " ".join(f"{EV[e]:>10s}" for e in order))
     for j in range(64):
         if int(t[j].max()) == 0:
             break
-        print(f"{j:4d}  " + " ".join(f"{(int(t[j, e]) - t0) if t[j, e] > 0 else -1:10d}" for e in ORDER))
+        print(f"{j:4d}  " + " ".join(f"{(int(t[j, e]) - t0) if t[j, e] > 0 else -1:10d}" for e in order))
 
 
 if __name__ == "__main__":
