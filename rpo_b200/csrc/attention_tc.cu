@@ -25,6 +25,7 @@
 #include <stdlib.h>
 
 #include <map>
+#include <type_traits>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -570,34 +571,45 @@ __global__ void __launch_bounds__(THREADS, 1)
 }
 
 // ================================================================================================================
-// Two-slot form (n16 <= 224: ViT-B/16): the exponentials of consecutive tiles are taken by two warp groups in turn
-// (tile j -> group j % 2 -> TMEM slot j % 2), ONE THREAD PER QUERY ROW, so no thread ever exchanges anything with
-// another.  The row maximum is taken by a third group (the epilogue warps, which have the time) as soon as S is
-// complete: it pulls the row out of tensor memory seven 16-column loads at a time and leaves max / 8 log2 e in
-// shared memory.  A softmax thread then makes ONE pass: scores out of tensor memory 32 at a time (the next 32 in
-// flight), p = ex2(s / 8 log2 e - that), f32 row sum, and the rounded probabilities go back into tensor memory over
-// the scores already consumed (two 16-bit values per 32-bit column: the layout tcgen05.mma reads an A operand from).
-// O = P V takes A straight from tensor memory.  While one group waits for its next tile (P V of the slot's previous
-// tile, S, maximum: about as long as the other group's exponentials take) the other group has the MUFU pipe of the
-// scheduler to itself: that pipe (16 ex2 / clk / SM) is the resource the kernel is built to keep busy.
+// Two-slot form (n16 <= 224: ViT-B/16).  The softmax of consecutive tiles is taken by two groups of eight warps in
+// turn (tile j -> group j % 2 -> TMEM slot j % 2), TWO THREADS PER QUERY ROW, each with one half of the row's 16-key
+// blocks.  A thread first takes the maximum of its half (four 16-column tensor-memory loads in flight) and swaps it
+// with the other half's through shared memory (named barrier of the two warps), then makes the second pass: scores
+// out of tensor memory 16 at a time (the next 16 in flight), p = ex2(s / 8 log2 e - max / 8 log2 e) in packed f32x2
+// arithmetic, f32 row sum, and the rounded probabilities go back into tensor memory over the thread's OWN scores
+// (two 16-bit values per 32-bit column: the layout tcgen05.mma reads an A operand from), starting at the first column
+// of its half -- the two threads of a row never touch each other's columns.  O = P V takes A straight from tensor
+// memory, one K = 16 instruction per key block.  While one group waits for its next tile (P V of the slot's previous
+// tile, then its S) the other group's exponentials have the MUFU pipe (16 ex2 / clk / SM) to themselves.
+//
+// Measured on B200 (tools/attn_trace.py, tools/probe/): MUFU.EX2 issues once per 8 clocks per scheduler whatever
+// else runs (F2FP, FFMA2, FADD2 ride beside it); tensor-memory loads are not the limit (> 860 B/clk/SM); what the
+// 197-key tile costs beyond its 1664 MUFU clocks is the dependent chain P stored -> P V -> S of the slot's next
+// tile -> maximum, about 1.8k clocks in which only one group has work.  Rejected after measurement: the maximum on
+// the epilogue warps (their wake-up sits on that chain), one thread per row (a single warp per scheduler cannot
+// keep the MUFU pipe fed: 200 clocks per key block instead of 131), S(j+2) issued by the P V thread straight behind
+// P V(j) (completes ~1000 clocks later than from its own thread after the commit).
 //
 //   warp 0 (one thread)   TMA producer (as above)
 //   warp 1 (one thread)   S = Q K^T into slot j % 2 once P V of tile j-2 has consumed that slot's P
 //   warp 2 (one thread)   O = P V (A = P in TMEM, B = V as loaded, MN-major) into the 64 columns behind the slots
-//   warps 4..7 / 8..11    softmax groups 0 / 1
-//   warps 12..15          per tile: epilogue of tile j (O out of TMEM, times 1 / row sum, into a staging tile that
-//                         one thread hands to the TMA: cp.async.bulk.tensor store), then the row maxima of tile j+2
-// Registers (setmaxnreg, out of 512 x 128): producers 40, softmax 144, epilogue / maximum 168.
-static constexpr int PP_THREADS = 512;
+//   warps 4..11 / 12..19  softmax groups 0 / 1: warp = (half of the keys, lane quarter)
+//   warps 20..23          epilogue: O out of TMEM, times 1 / row sum, into a 128B-swizzled staging tile that one
+//                         thread hands to the TMA (cp.async.bulk.tensor store: context rows and prompt rows are two
+//                         boxes of the tile)
+// Registers (setmaxnreg, out of 768 x 80): producers 24, softmax 96, epilogue 72.
+static constexpr int PP_THREADS = 768;
 static constexpr int PP_SLOT_COLS = 224;
 static constexpr int PP_O_COL = 448;
 static constexpr int PP_Q_RING = 4;
 static constexpr int PP_O_STAGES = 3;
-static constexpr int PP_REGS_PROD = 40, PP_REGS_SOFTMAX = 144, PP_REGS_AUX = 168;
+static constexpr int PP_REGS_PROD = 24, PP_REGS_SOFTMAX = 96, PP_REGS_EPI = 72;  // out of 768 x 80
+static constexpr int PP_AUX_WARP0 = 20;
 
-// NBLK_CT: number of 16-key blocks when known at compile time (13: the 197 keys of ViT-B/16 -- the softmax pass is
-// then one straight-line block the scheduler can pipeline across key blocks), 0: taken from geo at run time
-template <typename T, int NBLK_CT>
+// N_CT: number of keys when known at compile time (197: ViT-B/16 -- the softmax passes are then straight-line code the
+// scheduler can pipeline across key blocks, and the padding keys of the last block cost no exponentials), 0: taken
+// from geo at run time
+template <typename T, int N_CT>
 __global__ void __launch_bounds__(PP_THREADS, 1)
     ro_attn_fwd_pp(const __grid_constant__ CUtensorMap map_full,   // q|k|v matrix, box 64 x 128
                    const __grid_constant__ CUtensorMap map_kvt,    // q|k|v matrix, box 64 x (n16 % 128)
@@ -609,7 +621,8 @@ __global__ void __launch_bounds__(PP_THREADS, 1)
                    Geo geo, int total_items) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int n = geo.n, n16 = geo.n16, K = geo.K, H = geo.H;
+  constexpr int NBLK_CT = (N_CT + 15) / 16;
+  const int n = N_CT ? N_CT : geo.n, n16 = geo.n16, K = geo.K, H = geo.H;
   const int D = H * HD;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kv_bytes = n16 * ROW_BYTES;
@@ -622,14 +635,13 @@ __global__ void __launch_bounds__(PP_THREADS, 1)
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int idx) { return bar0 + 8u * idx; };
   constexpr int B_KVFULL = 0, B_KVFREE = 3, B_QFULL = 6, B_QFREE = 10, B_SFULL = 14, B_SFREE = 16, B_PFULL = 18,
-                B_OFULL = 20, B_OFREE = 21, B_MAXFULL = 22, N_BARS = 24;
+                B_OFULL = 20, B_OFREE = 21, N_BARS = 22;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + N_BARS);
-  // f32 [4][QT]: the row sums of tile j in buffer j % 4 (written at the end of the softmax of tile j, read by the
+  // f32 [4][2][QT]: the two partial row sums of tile j in buffer j % 4 (written at the end of the softmax of tile j, read by the
   // epilogue of tile j; the softmax of tile j+4 starts after P V of tile j+2, which waited for the epilogue of j+1)
   const uint32_t red_sum = smem_u32(bars + N_BARS + 1);
-  // f32 [2][QT]: row maximum / 8 log2 e of the S in slot s (written by the maximum pass once S is complete, read by
-  // the softmax of that tile before it stores its P; the slot's next S follows that P's P V)
-  const uint32_t row_off = red_sum + 4 * QT * 4;
+  // f32 [2][2][QT]: the maxima the two threads of a row (group, half) found in their halves of the keys
+  const uint32_t row_max = red_sum + 4 * 2 * QT * 4;
 
   const int item0 = (int)((long long)total_items * blockIdx.x / gridDim.x);
   const int item1 = (int)((long long)total_items * (blockIdx.x + 1) / gridDim.x);
@@ -654,8 +666,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1)
     for (int i = 0; i < 2; ++i) {
       mbar_init(BAR(B_SFULL + i), 1);
       mbar_init(BAR(B_SFREE + i), 1);
-      mbar_init(BAR(B_PFULL + i), 4);
-      mbar_init(BAR(B_MAXFULL + i), 4);
+      mbar_init(BAR(B_PFULL + i), 8);
     }
     mbar_init(BAR(B_OFULL), 1);
     mbar_init(BAR(B_OFREE), 4);
@@ -725,10 +736,12 @@ __global__ void __launch_bounds__(PP_THREADS, 1)
       for (int j = 0; j < count; ++j) {
         const int slot = j & 1, qs = j % PP_Q_RING;
         const int x = 2 * unit_idx(j), e = x % KV_RING;
-        mbar_wait(BAR(B_QFULL + qs), (uint32_t)((j / PP_Q_RING) & 1));
-        if (first_of_unit(j)) mbar_wait(BAR(B_KVFULL + e), (uint32_t)((x / KV_RING) & 1));
-        // the slot's previous P has been consumed by its P V
-        if (j >= 2) mbar_wait(BAR(B_SFREE + slot), (uint32_t)(((j >> 1) - 1) & 1));
+        mbar_wait_spin(BAR(B_QFULL + qs), (uint32_t)((j / PP_Q_RING) & 1));
+        if (first_of_unit(j)) mbar_wait_spin(BAR(B_KVFULL + e), (uint32_t)((x / KV_RING) & 1));
+        // the slot's previous P has been consumed by its P V.  (Issuing this S right behind that P V from ONE thread,
+        // relying on the tensor core's issue order instead of this wait, was measured: the S then completes ~1000
+        // clocks later than it does this way.)
+        if (j >= 2) mbar_wait_spin(BAR(B_SFREE + slot), (uint32_t)(((j >> 1) - 1) & 1));
         tc_fence_after();
         const uint32_t tslot = tmem_base + (uint32_t)(slot * PP_SLOT_COLS);
         const uint64_t adesc = make_smem_desc(q_base + qs * Q_TILE_BYTES), bdesc = make_smem_desc(kv_base + e * kv_bytes);
@@ -746,195 +759,221 @@ __global__ void __launch_bounds__(PP_THREADS, 1)
       const uint32_t fmt = Num<T>::dtype == RPO_BF16 ? 1u : 0u;
       const uint32_t idesc_o = make_idesc((int)fmt, QT, HD) | (1u << 16);  // B (= V) is MN-major
       const int nblk = NBLK_CT ? NBLK_CT : geo.nblk;
+      const int split = (nblk + 1) >> 1;
       for (int j = 0; j < count; ++j) {
         const int slot = j & 1;
         const int x = 2 * unit_idx(j) + 1, e = x % KV_RING;
-        if (first_of_unit(j)) mbar_wait(BAR(B_KVFULL + e), (uint32_t)((x / KV_RING) & 1));
-        if (j >= 1) mbar_wait(BAR(B_OFREE), (uint32_t)((j - 1) & 1));  // the previous tile's O is out of tensor memory
-        mbar_wait(BAR(B_PFULL + slot), (uint32_t)((j >> 1) & 1));
+        if (first_of_unit(j)) mbar_wait_spin(BAR(B_KVFULL + e), (uint32_t)((x / KV_RING) & 1));
+        if (j >= 1) mbar_wait_spin(BAR(B_OFREE), (uint32_t)((j - 1) & 1));  // the previous tile's O is out of tensor memory
+        mbar_wait_spin(BAR(B_PFULL + slot), (uint32_t)((j >> 1) & 1));
         ATTN_TRACE(j, 1);
         tc_fence_after();
         const uint64_t vdesc = make_smem_desc(kv_base + e * kv_bytes);
         const uint32_t pcol = tmem_base + (uint32_t)(slot * PP_SLOT_COLS);
-        for (int blk = 0; blk < nblk; ++blk)  // 16 keys: 8 columns of P, 2 KB of V
-          umma_f16_ts(tmem_base + PP_O_COL, pcol + (uint32_t)(blk * 8), vdesc + (uint64_t)(blk * 128), idesc_o, blk != 0);
+        // 16 keys per instruction: 8 columns of P, 2 KB of V.  The P of the keys of each softmax thread starts where
+        // that thread's scores started: key blocks [0, split) at column 0, [split, nblk) at column 16 * split.
+        for (int blk = 0; blk < nblk; ++blk)
+          umma_f16_ts(tmem_base + PP_O_COL, pcol + (uint32_t)(blk < split ? blk * 8 : split * 8 + blk * 8),
+                      vdesc + (uint64_t)(blk * 128), idesc_o, blk != 0);
         umma_commit(BAR(B_OFULL));
         umma_commit(BAR(B_SFREE + slot));
         if (last_of_unit(j)) umma_commit(BAR(B_KVFREE + e));  // V of the unit is dead once this O is complete
         ATTN_TRACE(j, 2);
       }
     }
-  } else if (warp >= 4 && warp < 12) {
-    // ===== softmax: group wg takes tiles j = wg, wg + 2, ...; thread = query row = TMEM lane =====
+  } else if (warp >= 4 && warp < PP_AUX_WARP0) {
+    // ===== softmax: group wg takes tiles j = wg, wg + 2, ...; two threads per query row (= TMEM lane), one per half
+    // of the key blocks.  Pass 1: maximum over the thread's half (four 16-key blocks in flight), exchanged with the
+    // other half through shared memory (named barrier of the two warps).  Pass 2: p = ex2(s / 8 log2 e - max ...),
+    // f32 sum, and the rounded probabilities over the thread's OWN scores (from the first column of its half), so the
+    // two threads of a row never touch each other's columns. =====
     setmaxnreg_inc<PP_REGS_SOFTMAX>();
-    const int wg = (warp - 4) >> 2;
+    const int wg = (warp - 4) >> 3;
+    const int half = ((warp - 4) >> 2) & 1;
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const bool tracer = (threadIdx.x & 127) == 0;
+    const bool tracer = ((threadIdx.x - 128) & 255) == 0;
     const float sl2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
     const int nblk = NBLK_CT ? NBLK_CT : geo.nblk;
+    const int split = (nblk + 1) >> 1;
     const int pad_first = n - (nblk - 1) * 16;  // valid keys of the last 16-key block
-    const uint32_t sbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(wg * PP_SLOT_COLS);
-    const uint32_t my_off = row_off + (uint32_t)((wg * QT + row) * 4);
-    for (int j = wg; j < count; j += 2) {
-      const Item it = item_of(geo, item0 + j);
-      const bool valid = q * 32 < it.c_rows + it.p_rows;  // warp-uniform
-      mbar_wait(BAR(B_MAXFULL + wg), (uint32_t)((j >> 1) & 1));
-      if (tracer) ATTN_TRACE(j, 5);
-      if (valid) {
-        tc_fence_after();
-        uint32_t s0[16], s1[16], t0[16], t1[16];
-        tmem_ld16_nowait(sbase, s0);
-        if (1 < nblk) tmem_ld16_nowait(sbase + 16u, s1);
-        const float off = lds_f32(my_off);  // finite: every row sees key 0
-        const uint64_t sl2x2 = pack_f32x2(sl2, sl2), noff2 = pack_f32x2(-off, -off);
-        uint64_t lsum = pack_f32x2(0.f, 0.f);
-        // probabilities of key block blk into tensor memory (over scores already consumed), row sum
-        auto prob_block = [&](int blk, uint32_t (&sc)[16]) {
-          if (blk == nblk - 1) {
+    // this thread's scores, and (over them) its probabilities
+    const uint32_t sbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(wg * PP_SLOT_COLS + half * split * 16);
+    const uint32_t my_max = row_max + (uint32_t)(((wg * 2 + half) * QT + row) * 4);
+    const uint32_t other_max = row_max + (uint32_t)(((wg * 2 + (half ^ 1)) * QT + row) * 4);
+    const int pair_bar = 2 + wg * 4 + q;  // named barrier of the two warps that share this lane quarter
+    auto mask_pad = [&](uint32_t (&x)[16]) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e)
-              if (e >= pad_first) sc[e] = 0xff800000u;  // -inf: ex2 gives 0
-          }
-          uint32_t pk[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float x0, x1;
-            unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(sc[2 * e]), __uint_as_float(sc[2 * e + 1])), sl2x2, noff2), x0, x1);
-            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
-            lsum = add_f32x2(lsum, pack_f32x2(p0, p1));  // even keys in the low lane, odd keys in the high lane
-            pk[e] = pack2<T>(p0, p1);
-          }
-          tmem_st8(sbase + (uint32_t)(blk * 8), pk);
-        };
-#pragma unroll
-        for (int blk = 0; blk < nblk; blk += 4) {
-          tmem_ld_wait(s0);
-          tmem_ld_wait(s1);
-          if (blk + 2 < nblk) tmem_ld16_nowait(sbase + (uint32_t)((blk + 2) * 16), t0);
-          if (blk + 3 < nblk) tmem_ld16_nowait(sbase + (uint32_t)((blk + 3) * 16), t1);
-          prob_block(blk, s0);
-          if (blk + 1 < nblk) prob_block(blk + 1, s1);
-          if (blk + 2 < nblk) {
-            tmem_ld_wait(t0);
-            tmem_ld_wait(t1);
-            if (blk + 4 < nblk) tmem_ld16_nowait(sbase + (uint32_t)((blk + 4) * 16), s0);
-            if (blk + 5 < nblk) tmem_ld16_nowait(sbase + (uint32_t)((blk + 5) * 16), s1);
-            prob_block(blk + 2, t0);
-            if (blk + 3 < nblk) prob_block(blk + 3, t1);
-          }
-        }
-        float l0, l1;
-        unpack_f32x2(lsum, l0, l1);
-        sts_f32(red_sum + (uint32_t)((((j & 3) * QT) + row) * 4), l0 + l1);
-        tmem_st_wait();
-        tc_fence_before();
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(B_PFULL + wg));
-      if (tracer) ATTN_TRACE(j, 6);
-    }
-  } else if (warp >= 12) {
-    // ===== epilogue of tile j, then the row maxima of tile j+2: one thread per query row =====
-    setmaxnreg_inc<PP_REGS_AUX>();
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const bool tracer = threadIdx.x == 12 * 32;
-    const float sl2 = 0.125f * 1.4426950408889634f;
-    const int nblk = NBLK_CT ? NBLK_CT : geo.nblk;
-    const int pad_first = n - (nblk - 1) * 16;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t taddr = lane_base + PP_O_COL;
-    // row maxima of tile jj: the row out of tensor memory, seven loads (112 columns) in flight
-    auto max_job = [&](int jj) {
-      const Item mi = item_of(geo, item0 + jj);
-      const int slot = jj & 1;
-      mbar_wait(BAR(B_SFULL + slot), (uint32_t)((jj >> 1) & 1));
-      if (tracer) ATTN_TRACE(jj, 3);
-      if (q * 32 < mi.c_rows + mi.p_rows) {
-        tc_fence_after();
-        const uint32_t sb = lane_base + (uint32_t)(slot * PP_SLOT_COLS);
-        uint32_t A[7][16];
+      for (int e = 0; e < 16; ++e)
+        if (e >= pad_first) x[e] = 0xff800000u;  // -inf: drops out of the maximum, ex2 gives 0
+    };
+    // cnt = key blocks of this thread (compile-time when the kernel knows the key count); has_pad: its last block
+    // is the row's last
+    auto tile = [&](auto cnt_c, int cnt_rt, bool has_pad, int j) {
+      constexpr int CNT_CT = decltype(cnt_c)::value;
+      constexpr int CNT_MAX = CNT_CT ? CNT_CT : 7;
+      const int cnt = CNT_CT ? CNT_CT : cnt_rt;
+      uint32_t a[16], b[16];
+      float mx;
+      {
+        // ---- pass 1 ----
+        uint32_t c[16], d[16];
         float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        auto fold = [&](int blk, uint32_t (&x)[16]) {
-          if (blk == nblk - 1) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e)
-              if (e >= pad_first) x[e] = 0xff800000u;  // -inf: drops out of the maximum
-          }
+        auto fold = [&](bool last, uint32_t (&x)[16]) {
+          if (last) mask_pad(x);
 #pragma unroll
           for (int e = 0; e < 16; e += 4)
             m4[e >> 2] = fmaxf(m4[e >> 2], fmaxf(fmaxf(__uint_as_float(x[e]), __uint_as_float(x[e + 1])),
                                                  fmaxf(__uint_as_float(x[e + 2]), __uint_as_float(x[e + 3]))));
         };
 #pragma unroll
-        for (int b0 = 0; b0 < 14; b0 += 7) {  // two batches of seven 16-key blocks (nblk <= 14)
-          if (b0 < nblk) {
-            // unconditional loads: columns behind the last key block are stale, inside the slot, and never folded
-#pragma unroll
-            for (int i = 0; i < 7; ++i) tmem_ld16_nowait(sb + (uint32_t)((b0 + i) * 16), A[i]);
-#pragma unroll
-            for (int i = 0; i < 7; ++i) tmem_ld_wait(A[i]);
-#pragma unroll
-            for (int i = 0; i < 7; ++i)
-              if (b0 + i < nblk) fold(b0 + i, A[i]);
+        for (int b0 = 0; b0 < CNT_MAX; b0 += 4) {
+          if (b0 < cnt) {
+            // unconditional loads: columns behind the thread's last block are somebody else's, and never folded
+            tmem_ld16_nowait(sbase + (uint32_t)(b0 * 16), a);
+            tmem_ld16_nowait(sbase + (uint32_t)((b0 + 1) * 16), b);
+            tmem_ld16_nowait(sbase + (uint32_t)((b0 + 2) * 16), c);
+            tmem_ld16_nowait(sbase + (uint32_t)((b0 + 3) * 16), d);
+            tmem_ld_wait(a);
+            tmem_ld_wait(b);
+            tmem_ld_wait(c);
+            tmem_ld_wait(d);
+            if (tracer && b0 == 0) ATTN_TRACE(j, 4);
+            fold(has_pad && b0 == cnt - 1, a);
+            if (b0 + 1 < cnt) fold(has_pad && b0 + 1 == cnt - 1, b);
+            if (b0 + 2 < cnt) fold(has_pad && b0 + 2 == cnt - 1, c);
+            if (b0 + 3 < cnt) fold(has_pad && b0 + 3 == cnt - 1, d);
           }
         }
-        sts_f32(row_off + (uint32_t)((slot * QT + row) * 4), fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * sl2);
+        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));  // -inf if the thread has no block
+      }
+      if (tracer) ATTN_TRACE(j, 9);
+      if (cnt > 0) tmem_ld16_nowait(sbase, a);  // pass 2's first block, behind the exchange
+      sts_f32(my_max, mx);
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      const float off = fmaxf(mx, lds_f32(other_max)) * sl2;  // finite: every row sees key 0
+      if (tracer) ATTN_TRACE(j, 5);
+      // ---- pass 2 ----
+      const uint64_t sl2x2 = pack_f32x2(sl2, sl2), noff2 = pack_f32x2(-off, -off);
+      uint64_t lsum = pack_f32x2(0.f, 0.f);
+      auto prob_block = [&](int i, bool last, uint32_t (&sc)[16]) {
+        if (last) mask_pad(sc);
+        uint32_t pk[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          if (last && 2 * e >= pad_first) {  // two padding keys: p = 0 without the exponentials
+            pk[e] = 0u;
+            continue;
+          }
+          float x0, x1;
+          unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(sc[2 * e]), __uint_as_float(sc[2 * e + 1])), sl2x2, noff2), x0, x1);
+          const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+          lsum = add_f32x2(lsum, pack_f32x2(p0, p1));  // even keys in the low lane, odd keys in the high lane
+          pk[e] = pack2<T>(p0, p1);
+        }
+        tmem_st8(sbase + (uint32_t)(i * 8), pk);
+      };
+#pragma unroll
+      for (int i = 0; i < CNT_MAX; i += 2) {
+        if (i < cnt) {
+          tmem_ld_wait(a);
+          tmem_ld16_nowait(sbase + (uint32_t)((i + 1) * 16), b);  // (behind the thread's last block: never used)
+          prob_block(i, has_pad && i == cnt - 1, a);
+          if (i + 1 < cnt) {
+            tmem_ld_wait(b);
+            tmem_ld16_nowait(sbase + (uint32_t)((i + 2) * 16), a);
+            prob_block(i + 1, has_pad && i + 1 == cnt - 1, b);
+          }
+          if (tracer && i == 0) ATTN_TRACE(j, 11);
+          if (tracer && i == 2) ATTN_TRACE(j, 12);
+          if (tracer && i == 4) ATTN_TRACE(j, 13);
+        }
+      }
+      if (tracer) ATTN_TRACE(j, 14);
+      tmem_ld_wait(a);  // no load is left in flight
+      tmem_ld_wait(b);
+      float l0, l1;
+      unpack_f32x2(lsum, l0, l1);
+      sts_f32(red_sum + (uint32_t)((((j & 3) * 2 + half) * QT + row) * 4), l0 + l1);
+      tmem_st_wait();
+      if (tracer) ATTN_TRACE(j, 15);
+    };
+    for (int j = wg; j < count; j += 2) {
+      const Item it = item_of(geo, item0 + j);
+      const bool valid = q * 32 < it.c_rows + it.p_rows;  // warp-uniform, the same for the two warps of a quarter
+      mbar_wait(BAR(B_SFULL + wg), (uint32_t)((j >> 1) & 1));
+      if (tracer) ATTN_TRACE(j, 3);
+      if (valid) {
+        tc_fence_after();
+        if (NBLK_CT) {
+          constexpr int SPLIT = (NBLK_CT + 1) / 2;
+          if (half == 0)
+            tile(std::integral_constant<int, SPLIT>{}, 0, SPLIT == NBLK_CT, j);
+          else if (NBLK_CT > SPLIT)
+            tile(std::integral_constant<int, (NBLK_CT > SPLIT ? NBLK_CT - SPLIT : 1)>{}, 0, true, j);
+          else
+            tile(std::integral_constant<int, 0>{}, 0, false, j);
+        } else {
+          tile(std::integral_constant<int, 0>{}, half == 0 ? split : nblk - split, half == 0 ? split == nblk : true, j);
+        }
         tc_fence_before();
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(B_MAXFULL + slot));
-    };
+      if (lane == 0) mbar_arrive(BAR(B_PFULL + wg));
+      if (tracer) ATTN_TRACE(j, 6);
+    }
+  } else if (warp >= PP_AUX_WARP0) {
+    // ===== epilogue: one thread per query row =====
+    setmaxnreg_dec<PP_REGS_EPI>();
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const bool tracer = threadIdx.x == PP_AUX_WARP0 * 32;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + PP_O_COL;
+    pdl_wait();
     Item it = item_of(geo, item0);
-    // j = -2, -1: only the maxima of tiles 0 and 1.  O of tile j is complete before S of tile j+2 (which waits for
-    // that P V): epilogue first, it ends about when that S does
-    for (int j = -2; j < count; ++j) {
-      if (j < 0) {
-        if (j + 2 < count) max_job(j + 2);
-        continue;
-      }
-      if (j == 0) pdl_wait();
+    for (int j = 0; j < count; ++j, advance(geo, it)) {
       const int rows_here = it.c_rows + it.p_rows;
       mbar_wait(BAR(B_OFULL), (uint32_t)(j & 1));
       tc_fence_after();
       if (tracer) ATTN_TRACE(j, 7);
       const bool valid = q * 32 < rows_here;
-      uint32_t acc[4][16];
-      if (valid) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld16_nowait(taddr + (uint32_t)(c * 16), acc[c]);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld_wait(acc[c]);
-      }
-      // O is in registers: the next P V may overwrite it
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(B_OFREE));
       // O times 1 / row sum into the staging tile (rows of 128 B, 16-byte chunk index ^ (row & 7): the layout a
       // 128B-swizzled tensor map reads), then ONE thread hands the tile to the TMA: context rows and prompt rows are
       // two boxes of it.  Three staging tiles: the tile written now was read by the store of three tiles ago, which
       // the issuing thread has waited for before the previous tile's barrier.
       const uint32_t stage = o_base + (uint32_t)((j % PP_O_STAGES) * Q_TILE_BYTES);
       if (valid) {
-        const float inv = 1.0f / lds_f32(red_sum + (uint32_t)((((j & 3) * QT) + row) * 4));
+        const uint32_t rs = red_sum + (uint32_t)((((j & 3) * 2) * QT + row) * 4);
+        const float inv = 1.0f / (lds_f32(rs) + lds_f32(rs + QT * 4));
         const uint32_t srow = stage + (uint32_t)(row * ROW_BYTES);
         const uint32_t sw = (uint32_t)(row & 7);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 4; c += 2) {
+          uint32_t acc[2][16];
+          tmem_ld16_nowait(taddr + (uint32_t)(c * 16), acc[0]);
+          tmem_ld16_nowait(taddr + (uint32_t)((c + 1) * 16), acc[1]);
+          tmem_ld_wait(acc[0]);
+          tmem_ld_wait(acc[1]);
 #pragma unroll
-          for (int v = 0; v < 2; ++v) {
-            sts128(srow + ((((uint32_t)(2 * c + v)) ^ sw) << 4),
-                   pack2<T>(__uint_as_float(acc[c][8 * v + 0]) * inv, __uint_as_float(acc[c][8 * v + 1]) * inv),
-                   pack2<T>(__uint_as_float(acc[c][8 * v + 2]) * inv, __uint_as_float(acc[c][8 * v + 3]) * inv),
-                   pack2<T>(__uint_as_float(acc[c][8 * v + 4]) * inv, __uint_as_float(acc[c][8 * v + 5]) * inv),
-                   pack2<T>(__uint_as_float(acc[c][8 * v + 6]) * inv, __uint_as_float(acc[c][8 * v + 7]) * inv));
+          for (int cc = 0; cc < 2; ++cc) {
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+              sts128(srow + ((((uint32_t)(2 * (c + cc) + v)) ^ sw) << 4),
+                     pack2<T>(__uint_as_float(acc[cc][8 * v + 0]) * inv, __uint_as_float(acc[cc][8 * v + 1]) * inv),
+                     pack2<T>(__uint_as_float(acc[cc][8 * v + 2]) * inv, __uint_as_float(acc[cc][8 * v + 3]) * inv),
+                     pack2<T>(__uint_as_float(acc[cc][8 * v + 4]) * inv, __uint_as_float(acc[cc][8 * v + 5]) * inv),
+                     pack2<T>(__uint_as_float(acc[cc][8 * v + 6]) * inv, __uint_as_float(acc[cc][8 * v + 7]) * inv));
+            }
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       }
+      // O is out of tensor memory: the next P V may overwrite it
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(B_OFREE));
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 12 * 32) {
+      if (threadIdx.x == PP_AUX_WARP0 * 32) {
         if (it.c_rows == QT)
           tma_store_2d(&omap_full, stage, it.h * HD, it.g * n + it.t * QT);
         else if (it.c_rows > 0)
@@ -945,10 +984,8 @@ __global__ void __launch_bounds__(PP_THREADS, 1)
         tma_store_wait_read<1>();  // the store of the previous tile has read its staging tile
       }
       if (tracer) ATTN_TRACE(j, 8);
-      advance(geo, it);
-      if (j + 2 < count) max_job(j + 2);
     }
-    if (threadIdx.x == 12 * 32) tma_store_wait_read<0>();
+    if (threadIdx.x == PP_AUX_WARP0 * 32) tma_store_wait_read<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -961,7 +998,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1)
 }
 
 static int pp_smem_bytes(int n16) {
-  return KV_RING * n16 * ROW_BYTES + (PP_Q_RING + PP_O_STAGES) * Q_TILE_BYTES + 8 * 26 + (4 + 2) * QT * 4 + 1024;
+  return KV_RING * n16 * ROW_BYTES + (PP_Q_RING + PP_O_STAGES) * Q_TILE_BYTES + 8 * 24 + (8 + 4) * QT * 4 + 1024;
 }
 
 static int smem_bytes(int n16, int q_ring) {
@@ -975,7 +1012,7 @@ bool ro_attention_fwd_dense_supported(int dtype, int n, int K, int H) {
   if (dtype != RPO_F16 && dtype != RPO_BF16) return false;
   if (n < 1 || K < 0 || H < 1) return false;
   const int n16 = (n + 15) & ~15;
-  if (n16 > 288) return false;                     // 18 key blocks: 5 per softmax thread at most; S + O within 512 TMEM columns
+  if (n16 > 288) return false;                     // 18 key blocks: 5 per softmax thread at most; S + O within 512 TMEM columns (shared memory stops at 272)
   if (K > 0 && (n % 128) + K > 128) return false;  // all prompt rows in one query tile
   if ((n16 <= atc::PP_SLOT_COLS ? atc::pp_smem_bytes(n16) : atc::smem_bytes(n16, 2)) > 227 * 1024) return false;
   return true;
@@ -1052,7 +1089,7 @@ int ro_attention_fwd_dense(const T *qkv_ctx, const T *q_prompt, T *out_ctx, T *o
                                   omap_full, omap_tail, omap_prompt, geo, (int)items));
         return RPO_OK;
       };
-      s = geo.nblk == 13 ? launch(ro_attn_fwd_pp<T, 13>) : launch(ro_attn_fwd_pp<T, 0>);
+      s = n == 197 ? launch(ro_attn_fwd_pp<T, 197>) : launch(ro_attn_fwd_pp<T, 0>);
     } else {
       auto launch = [&](auto kernel) -> int {
         RPO_TRY(configure(reinterpret_cast<const void *>(kernel)));

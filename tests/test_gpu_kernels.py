@@ -364,7 +364,7 @@ DENSE_CASES = [
     # several work items per CTA: K/V double buffer, Q ring and both TMEM slots wrap around (config 2 / 5 sizes)
     ("vitb16_k24_b32", 32, 197, 24, 12), ("vitb16_k48_b64", 64, 197, 48, 12), ("vitb16_ctx_only_b32", 32, 197, 0, 12),
     # ViT-L/14 (BASELINE config 3): 257 keys = two UMMA N blocks in one 512-column TMEM slot, three query tiles
-    ("vitl14_k24", 2, 257, 24, 16), ("vitl14_k24_b16", 16, 257, 24, 16), ("n288", 3, 288, 0, 2), ("n16_one_block", 3, 9, 3, 1),
+    ("vitl14_k24", 2, 257, 24, 16), ("vitl14_k24_b16", 16, 257, 24, 16), ("n272", 3, 272, 0, 2), ("n16_one_block", 3, 9, 3, 1),
 ]
 
 

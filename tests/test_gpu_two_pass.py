@@ -74,7 +74,8 @@ def test_two_pass_image_forward_matches_single_pass_and_oracle(arch_name, prec, 
     assert (logits2 - logits1).abs().max().item() <= tol * scale
     # the two paths differ only in the attention kernel the prompt rows take and in the GEMM tile their q projection
     # rides in: same roundings, different accumulation order
-    gtol = {"fp32": 1e-5, "fp16": 5e-3, "bf16": 4e-2}[prec]
+    # (bf16: each path sits within FLOOR["bf16"] = 3.2e-2 of the truth, so the two may differ by twice that)
+    gtol = {"fp32": 1e-5, "fp16": 5e-3, "bf16": 6.4e-2}[prec]
     nt = eng.n_text
     print(f"{arch_name}/{prec}: dloss {abs(loss2.item() - loss1.item()):.2e} dlogits {(logits2 - logits1).abs().max().item():.2e} "
           f"text {rel_err(grad2[:nt], grad1[:nt]):.2e} image {rel_err(grad2[nt:], grad1[nt:]):.2e}")

@@ -16,10 +16,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from rpo_b200 import _lib  # noqa: E402
 
-EV = {10: "q_issue", 0: "s_issue", 3: "sm_sfull", 4: "sm_loaded", 5: "sm_maxx", 14: "sm_pfree0", 15: "sm_blk0",
-      9: "sm_blocks", 6: "sm_pdone", 12: "sm_arrived", 13: "sm_nextld", 1: "pv_pfull", 2: "pv_issued", 7: "ep_ofull",
-      8: "ep_done"}
-ORDER = [10, 0, 3, 4, 5, 14, 15, 9, 6, 12, 13, 1, 2, 7, 8]
+EV = {10: "q_issue", 0: "s_issue", 3: "sm_sfull", 4: "sm_ld1", 9: "sm_folded", 5: "sm_maxx", 11: "sm_blk2", 12: "sm_blk4",
+      13: "sm_blk6", 14: "sm_blocks", 15: "sm_stwait", 6: "sm_pdone", 1: "pv_pfull", 2: "pv_issued", 7: "ep_ofull", 8: "ep_done"}
+ORDER = [10, 0, 3, 4, 9, 5, 11, 12, 13, 14, 15, 6, 1, 2, 7, 8]
 
 
 def main():
