@@ -244,9 +244,9 @@ template <typename T>
 int ro_attention_bwd_mma(const T *qkv_ctx, const T *q_prompt, const T *o_prompt, const T *d_out, T *dq,
                          const int *ctx_off, int G, int K, int H, int max_ctx, cudaStream_t st);
 
-// RPO_ATTN_SIMT=1 forces the exact-f32 SIMT kernels for every dtype (tests cross-check the two paths)
+// RPO_ATTN_SIMT=1 (diagnostics build) forces the exact-f32 SIMT kernels for every dtype
 static bool force_simt() {
-  const char *e = getenv("RPO_ATTN_SIMT");
+  const char *e = diag_env("RPO_ATTN_SIMT");
   return e && e[0] == '1';
 }
 

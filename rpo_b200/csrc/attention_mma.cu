@@ -913,7 +913,7 @@ int ro_attention_fwd_mma(const T *qkv_ctx, const T *q_prompt, T *out_ctx, T *out
   RPO_REQUIRE(max_ctx >= 1 && max_ctx <= 288, "at most 288 context rows per group on the tensor-core path");
   RPO_REQUIRE(G <= 65535 && H <= 65535, "grid limits");
   if (G == 0 || (!do_ctx && K == 0)) return RPO_OK;
-  static const bool single_pass = [] { const char *e = getenv("RPO_ATTN_SINGLEPASS"); return e && e[0] == '1'; }();
+  static const bool single_pass = [] { const char *e = diag_env("RPO_ATTN_SINGLEPASS"); return e && e[0] == '1'; }();
   if (!single_pass)
     return amma::launch_fwd_flash<T>(qkv_ctx, q_prompt, out_ctx, out_prompt, ctx_off, G, K, H, max_ctx, causal, do_ctx, st);
   AMMA_PICK(launch_fwd, qkv_ctx, q_prompt, out_ctx, out_prompt, ctx_off, G, K, H, max_ctx, causal, do_ctx, st);
@@ -925,7 +925,7 @@ int ro_attention_bwd_mma(const T *qkv_ctx, const T *q_prompt, const T *o_prompt,
   RPO_REQUIRE(max_ctx >= 1 && max_ctx <= 288, "at most 288 context rows per group on the tensor-core path");
   RPO_REQUIRE(G <= 65535, "grid limits");
   if (G == 0 || K == 0) return RPO_OK;
-  static const bool single_pass = [] { const char *e = getenv("RPO_ATTN_SINGLEPASS"); return e && e[0] == '1'; }();
+  static const bool single_pass = [] { const char *e = diag_env("RPO_ATTN_SINGLEPASS"); return e && e[0] == '1'; }();
   if (!single_pass && max_ctx > 64) {  // short contexts (text: ~10 keys) are faster in the single-pass kernel
     // 16-key groups per warp: the groups are shared by KS = 4 / (query tiles, rounded up to 1, 2 or 4) warps
     const int rows = K < amma::QT ? K : amma::QT;

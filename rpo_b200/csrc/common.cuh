@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <string>
 
@@ -54,6 +55,14 @@ extern thread_local bool g_prof_on;
     RPO_CHECK_CUDA(cudaPeekAtLastError());                      \
     if (rpo::g_prof_on) rpo::prof_mark(__FILE__, __LINE__, st); \
   } while (0)
+
+// Tuning / fault-injection switches exist only in the diagnostics build (RPO_DIAG=1 python -m rpo_b200.build): the
+// release library answers "unset" for them, and the strings are not even in it.
+#ifdef RPO_DIAG
+inline const char *diag_env(const char *name) { return getenv(name); }
+#else
+inline const char *diag_env(const char *) { return nullptr; }
+#endif
 
 inline size_t dtype_size(int dtype) { return dtype == RPO_F32 ? 4 : 2; }
 

@@ -150,7 +150,7 @@ static Epilogue<T> frozen_ep(void *sk_ws = nullptr) {
   Epilogue<T> e{};
   // 1: weight tiles of the first ring fill are fetched ahead of the PDL dependency wait; 2 (RPO_GEMM_L2_PREFETCH=1): the
   // rest of the first tile's weight k-blocks is also prefetched into L2
-  static const int mode = [] { const char *v = getenv("RPO_GEMM_L2_PREFETCH"); return (v && v[0] == '1') ? 2 : 1; }();
+  static const int mode = [] { const char *v = diag_env("RPO_GEMM_L2_PREFETCH"); return (v && v[0] == '1') ? 2 : 1; }();
   e.b_frozen = mode;
   e.sk_ws = sk_ws;
   return e;
@@ -183,7 +183,7 @@ static int tower_forward(RpoHandle *hd, Tower &tw, bool do_ctx, bool do_prompt, 
     // One launch for the in-projection of context AND prompt rows when both are live and the tcgen05 path takes the
     // shape: the epilogue sends the prompt rows' q third to `qp` and drops their k|v (prompts are never keys or
     // values) -- 8% more MMA work on this GEMM, one ~6 us kernel and one dependency bubble less per block.
-    static const bool no_fused_q = [] { const char *e = getenv("RPO_NO_FUSED_Q"); return e && e[0] == '1'; }();
+    static const bool no_fused_q = [] { const char *e = diag_env("RPO_NO_FUSED_Q"); return e && e[0] == '1'; }();
     const bool fused_q = !no_fused_q && do_ctx && do_prompt && sizeof(T) == 2 && backend != RPO_GEMM_SIMT && Mc > 0 && Mp > 0 &&
                          gemm_tcgen05_supported(Num<T>::dtype, D, D, 3 * D, Mc + Mp, 3 * D, D, h, bw.in_w, qkv);
     if (fused_q) {
@@ -717,12 +717,12 @@ int rpo_create(const RpoConfig *cfg, RpoHandle **out) {
   {
     const char *e = getenv("RPO_SINGLE_STREAM");
     h->overlap = !(e && e[0] == '1');
-    if (const char *sk = getenv("RPO_DEBUG_SKIP")) h->skip = atoi(sk);
+    if (const char *sk = diag_env("RPO_DEBUG_SKIP")) h->skip = atoi(sk);
   }
   // RPO_SIDE_PRIO=<n>: stream priority of the text tower's side stream relative to the caller's stream (0 = same
   // as a default stream, negative = higher); kernel nodes of a captured graph keep it
   int side_prio = 0;
-  if (const char *e = getenv("RPO_SIDE_PRIO")) side_prio = atoi(e);
+  if (const char *e = diag_env("RPO_SIDE_PRIO")) side_prio = atoi(e);
   if (cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, side_prio) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
@@ -1079,7 +1079,7 @@ int rpo_gemm_bias_act_ws(const void *A, int64_t lda, const void *B, int64_t ldb,
              ep.sk_ws = workspace;
              // benchmarking aid: treat B as a frozen weight (tiles fetched before the PDL dependency wait), as the
              // towers do.  Only valid when no earlier launch on the stream writes B.
-             if (const char *fz = getenv("RPO_GEMM_ASSUME_FROZEN_B")) ep.b_frozen = fz[0] == '1';
+             if (const char *fz = diag_env("RPO_GEMM_ASSUME_FROZEN_B")) ep.b_frozen = fz[0] == '1';
              return gemm_dispatch<T>(backend, (const T *)A, lda, (const T *)B, ldb, (T *)C, ldc, M, N, Kd, ep,
                                      (cudaStream_t)stream);
            }()));

@@ -276,10 +276,8 @@ struct Epi {
   static constexpr int PASSES = BM / ROWS_PER_PASS;
   static constexpr int DRAIN_HALVES = SLAB / 32;             // warps with half_id >= this idle in the drain
 
-  // Tile-local output column of TMEM slab sl.  BN = 384 (CTA pairs only) is computed as three N = 128 MMAs, each of
-  // which takes 64 B rows from either CTA of the pair: accumulator columns [128 j, 128 j + 64) are output columns
-  // [64 j, 64 j + 64) and [128 j + 64, 128 j + 128) are [192 + 64 j, ...): a permutation of whole slabs.
-  static __device__ __forceinline__ int gcol(int sl) { return BN == 384 ? 64 * (sl >> 1) + 192 * (sl & 1) : sl * SLAB; }
+  // tile-local output column of TMEM slab sl
+  static __device__ __forceinline__ int gcol(int sl) { return sl * SLAB; }
 
   static __device__ __forceinline__ uint32_t st_off(int r, int c) {
     return (uint32_t)(r * (SLAB * 2) + ((c ^ (r & (CH - 1))) << 4));
@@ -295,7 +293,6 @@ struct Epi {
   int sk_count = 0;
   size_t sk_stride = 0;  // floats between the slots of consecutive contributors
   long long t_acc = 0;   // clock when the accumulator became available (trace only)
-  int dbg_nostore = 0;   // tuning experiment (RPO_GEMM_DEBUG=0x400): skip the copy-out's global stores
   long long tile_m0 = 0;  // first row / column of the current tile (row-split outputs)
   int tile_n0 = 0;
   uint32_t slab_seq = 0;  // slabs this thread has processed (selects the staging buffer)
@@ -439,7 +436,7 @@ struct Epi {
             *reinterpret_cast<uint4 *>(p) = v;
           else if (n < ep.ncols2)
             *reinterpret_cast<uint4 *>(ep.c2 + (mm - ep.split_row) * ep.ldc2 + n) = v;
-        } else if (!dbg_nostore) {
+        } else {
           *reinterpret_cast<uint4 *>(p) = v;
         }
       }
@@ -509,7 +506,7 @@ struct Epi {
           // the one tile of a row-split output that holds rows of both destinations leaves through plain stores
           // (a TMA store cannot start at a negative row of the second destination)
           copy_out<false>(ep, slab, gcol(sl), r0, c, pre);
-        } else if (etid_all == 0 && !dbg_nostore) {
+        } else if (etid_all == 0) {
           const int col = n0 + gcol(sl);
           if (!ep.c2 || m0 < ep.split_row)
             tma_store_2d(map_c, slab, col, (int)m0);  // map_c ends at M, or at split_row for a row-split output
@@ -839,12 +836,10 @@ __device__ __forceinline__ void st_release_gpu(int *p, int v) {
 
 template <int BN>
 struct Cfg2 {
-  static constexpr int STAGES = BN == 384 ? 4 : (BN >= 192 ? 6 : 8);
-  // BN = 384: ONE accumulator of 384 TMEM columns, three N = 128 MMAs per k-step -- for problems whose 256 x 384
-  // tiles all fit in one round of SM pairs (no next tile to overlap the epilogue with anyway)
-  static constexpr int ACC_BUFS = BN == 384 ? 1 : 2;
-  static constexpr int NMMA = BN == 384 ? 3 : 1;
-  static constexpr int MMA_N = BN / NMMA;
+  static constexpr int STAGES = BN >= 192 ? 6 : 8;
+  static constexpr int ACC_BUFS = 2;
+  static constexpr int NMMA = 1;
+  static constexpr int MMA_N = BN;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / 2) * BK * 2;  // this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -872,8 +867,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
   float *bias_s = reinterpret_cast<float *>(cstage + C_::CSTAGE_BYTES);
   uint64_t *bars = reinterpret_cast<uint64_t *>(cstage + C_::CSTAGE_BYTES + C_::BIAS_BYTES);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * C_::STAGES + 4);
-  // tuning experiments (RPO_GEMM_DEBUG): 0x100 = no epilogue work, 0x200 = no MMA issue.  Results are garbage.
-  const int dbg = stream_k & 0xF00;
   const int dyn = (stream_k >> 1) & 1;  // one pair per tile, cluster launch control (see TileFeed)
   stream_k &= 1;
 
@@ -979,14 +972,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
           const uint32_t a_addr = smem_base + s * C_::STAGE_BYTES;
           const uint64_t adesc = make_smem_desc(a_addr);
           const uint64_t bdesc = make_smem_desc(a_addr + C_::A_BYTES);
-          if (!(dbg & 0x200)) {
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k)
-#pragma unroll
-              for (int j = 0; j < C_::NMMA; ++j)  // B rows [MMA_N/2 * j, +MMA_N/2) of either CTA: 128-byte rows
-                umma_f16_pair(tmem_d + (uint32_t)(j * C_::MMA_N), adesc + 2u * k,
-                              bdesc + 2u * k + (uint32_t)(j * (C_::MMA_N / 2) * 128 / 16), idesc, (kb != sg.k0) || (k != 0));
-          }
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_f16_pair(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb != sg.k0) || (k != 0));
           umma_commit_pair(empty_bar(s));
         }
         umma_commit_pair(acc_full(a));
@@ -1050,15 +1038,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
         }
         named_bar_sync<Thr<BN>::EPI_WARPS * 32>(1);
       }
-      if (dbg & 0x100) {
-        mbar_wait(acc_full(a), acc_par);
-        tc_fence_after();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(lead_empty);
-        continue;
-      }
-      epi.dbg_nostore = dbg & 0x400;
       epi.sk_partial = n_contrib ? sk_slots + ((size_t)(cluster_id + sch.lanes) * 2 + rank) * (BM * 256) : nullptr;
       epi.sk_count = n_contrib;
       epi.sk_stride = (size_t)sch.lanes * (2 * BM * 256);
@@ -1129,7 +1108,7 @@ static int launch(const T *A, long long lda, const T *B, long long ldb, T *C, lo
   const int num_n_tiles = N / BN;
   const long long num_tiles = ((M + BM - 1) / BM) * num_n_tiles;
   long long *trace = nullptr;
-  if (const char *e = getenv("RPO_GEMM_TRACE")) trace = reinterpret_cast<long long *>(strtoull(e, nullptr, 0));
+  if (const char *e = diag_env("RPO_GEMM_TRACE")) trace = reinterpret_cast<long long *>(strtoull(e, nullptr, 0));
   const long long slots = (long long)sm_count() * C_::MIN_CTAS;
   // more tiles than SMs (one-CTA-per-SM configurations): one CTA per tile, taken over dynamically (see TileFeed)
   const int dyn = (!LIGHT && num_tiles > slots && (dynamic_tiles() & 2)) ? 1 : 0;
@@ -1186,7 +1165,6 @@ static int launch_pair(const T *A, long long lda, const T *B, long long ldb, T *
     stream_k = 2;
     grid = 2 * (int)num_tiles;
   }
-  if (const char *d = getenv("RPO_GEMM_DEBUG")) stream_k |= (int)strtol(d, nullptr, 0) & 0xF00;
   prof_tag("gemm2 M=%lld N=%d K=%d BN=%d%s%s%s%s", M, N, Kd, BN, ep.bias ? " +bias" : "",
            ep.act == RPO_ACT_QUICKGELU ? " +gelu" : (ep.gelu_grad_aux ? " *gelu'" : ""), ep.residual ? " +res" : "",
            stream_k & 1 ? " streamK" : (stream_k & 2 ? " dyn" : ""));
@@ -1394,18 +1372,12 @@ static int launch_splitk(const T *A, long long lda, const T *B, long long ldb, T
 
 // ---- tile configuration --------------------------------------------------------------------------
 // P256/P128: CTA pairs, 256 x BN tiles.  S128/S64/S32: one CTA per SM, 128 x BN tiles, deep ring.
-// L64/L32: light 128 x BN tiles, two CTAs per SM.  RPO_GEMM_FORCE=<name> pins one (tuning sweeps).
-enum { CFG_P256 = 0, CFG_P128, CFG_S128, CFG_S64, CFG_S32, CFG_L64, CFG_L32, CFG_K4, CFG_K2, CFG_P192, CFG_P384, CFG_COUNT };
-static const char *const kCfgNames[CFG_COUNT] = {"p256", "p128", "s128", "s64", "s32", "l64",
-                                                 "l32",  "k4",   "k2",   "p192", "p384"};
+// L64/L32: light 128 x BN tiles, two CTAs per SM.  RPO_GEMM_FORCE=<name> pins one (tuning sweeps, diagnostics build).
+enum { CFG_P256 = 0, CFG_P128, CFG_S128, CFG_S64, CFG_S32, CFG_L64, CFG_L32, CFG_K4, CFG_K2, CFG_P192, CFG_COUNT };
+static const char *const kCfgNames[CFG_COUNT] = {"p256", "p128", "s128", "s64", "s32", "l64", "l32", "k4", "k2", "p192"};
 
-// P384 has a single accumulator: only for problems whose 256 x 384 tiles fit in one round of SM pairs
-static bool p384_fits(long long M, int N) {
-  return N % 384 == 0 && ((M + 2 * BM - 1) / (2 * BM)) * (N / 384) <= sm_count() / 2;
-}
 static bool cfg_valid(int cfg, long long M, int N) {
   switch (cfg) {
-    case CFG_P384: return p384_fits(M, N);
     case CFG_P256: return N % 256 == 0;
     case CFG_P192: return N % 192 == 0;
     case CFG_P128: case CFG_S128: return N % 128 == 0;
@@ -1416,7 +1388,7 @@ static bool cfg_valid(int cfg, long long M, int N) {
 
 static int pick_config(long long M, int N, int Kd) {
   static const int forced = [] {
-    const char *e = getenv("RPO_GEMM_FORCE");
+    const char *e = diag_env("RPO_GEMM_FORCE");
     if (e)
       for (int i = 0; i < CFG_COUNT; ++i)
         if (strcmp(e, kCfgNames[i]) == 0) return i;
@@ -1433,9 +1405,8 @@ static int pick_config(long long M, int N, int Kd) {
   const long long mt = (M + BM - 1) / BM;
   if (mt >= 40) {
     // (N = 768 -- out-proj, c_proj, patch embedding: 84 tiles of 256 x 256 are 2 rounds on 74 SM pairs, the second 14 %
-    // full, while 56 tiles of 256 x 384 are ONE round.  Measured SLOWER all the same -- out-proj 17.1 -> 18.9 us, c_proj
-    // 39.1 -> 41.0, patch 12.3 -> 15.6, step 3.27 -> 3.51 ms: a single accumulator leaves the 6-slab epilogue, 6-12 k
-    // cycles per tile (tools/gemm_trace.py), with no main loop to hide behind.  RPO_GEMM_FORCE=p384 keeps it reachable.)
+    // full.  256 x 384 tiles (ONE round, single accumulator) were built and measured slower -- out-proj 17.1 -> 18.9 us,
+    // c_proj 39.1 -> 41.0, step 3.27 -> 3.51 ms -- and removed: profiles/r01_gemm_config_sweep.txt.)
     if (N % 256 == 0 && (N >= 2048 || Kd >= 2048)) return CFG_P256;
     if (N % 128 == 0) return CFG_S128;
     if (N % 64 == 0) return CFG_S64;
@@ -1485,7 +1456,6 @@ int gemm_tcgen05(const T *A, long long lda, const T *B, long long ldb, T *C, lon
       case tc::CFG_P256: return tc::launch_pair<T, 256>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);
       case tc::CFG_P128: return tc::launch_pair<T, 128>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);
       case tc::CFG_P192: return tc::launch_pair<T, 192>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);
-      case tc::CFG_P384: return tc::launch_pair<T, 384>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);
       case tc::CFG_S128: return tc::launch<T, 128, false>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);
       case tc::CFG_S64: return tc::launch<T, 64, false>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);
       case tc::CFG_S32: return tc::launch<T, 32, false>(A, lda, B, ldb, C, ldc, M, N, Kd, ep, st);
