@@ -333,8 +333,8 @@ def attention_roofline(arch, K, B, dt, dev, peaks, iters=48):
     nbytes = 2 * (2 * L + 2 * S) * 64 * H * B
     flops = 4 * L * S * 64 * H * B
     return {
-        "kernel": f"ro_attn_fwd_tc = rpo_ro_attention_fwd_dense (tcgen05; vision tower, one layer: {B} images x {H} heads, "
-                  f"L={L} queries, S={S} keys)",
+        "kernel": f"ro_attn_fwd_pp / ro_attn_fwd_tc = rpo_ro_attention_fwd_dense (tcgen05; vision tower, one layer: {B} images x "
+                  f"{H} heads, L={L} queries, S={S} keys)",
         "bound": "hbm", "achieved": nbytes / t / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
         "frac": nbytes / t / 1e9 / peaks["hbm"], "traffic": ncu_traffic("ro_attn_fwd_tc") if (K, B, S) == (24, 32, 197) else None,
         "peak_source": f"{peaks['source']} copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
