@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "librpo_b200.so")
-SOURCES = ["elementwise.cu", "gemm_simt.cu", "gemm_tc.cu", "attention.cu", "attention_mma.cu", "attention_tc.cu", "logits.cu",
+SOURCES = ["elementwise.cu", "gemm_simt.cu", "gemm_tc.cu", "attention.cu", "attention_mma.cu", "attention_tc.cu", "logits.cu", "logits_tc.cu",
            "peer.cu", "engine.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

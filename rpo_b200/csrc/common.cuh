@@ -216,6 +216,13 @@ struct Epilogue {
 };
 
 // ---- kernel launchers implemented across the .cu files -------------------------------------------
+// tcgen05 form of the three K-pair contractions of the logit block (logits_tc.cu)
+bool logits_tc_supported(int dtype, int B, int C, int K, int E);
+template <typename T>
+int logits_pair_fwd_tc(const T *img_s, const T *text_n, T *pair, int B, int C, int K, int E, cudaStream_t st);
+template <typename T>
+int logits_pair_bwd_tc(const T *dl, const T *img_s, const T *text_n, T *d_img_s, T *d_text_n, int B, int C, int K,
+                       int E, cudaStream_t st);
 template <typename T>
 int gemm_simt(const T *A, long long sam, long long sak, const T *B, long long sbn, long long sbk, T *C, long long ldc,
               long long M, int N, int Kd, const Epilogue<T> &ep, int batch, long long bsa, long long bsb,

@@ -2,9 +2,10 @@
 //   text_f, img_f <- row-wise L2 normalise                                   (:215, :218)
 //   logits[b,c] = (1/K) sum_k  dtype( (dtype(exp(s)) * img_f[b,k,:]) . text_f[c,k,:] )   (:221-227)
 //   loss = mean_b CE(logits[b,:], label_b)                                   (:230)
-// The K per-pair products are K small GEMMs [B,E]x[E,C]; they run as one batched launch of the
-// strided SIMT GEMM (M = B is far below a tensor-core tile), the pair sum is accumulated in f32
-// exactly like the reference's f32 `logits` buffer.
+// The K per-pair products are K small GEMMs [B,E]x[E,C]: one batched tcgen05 launch (logits_tc.cu) for the 16-bit
+// types, the strided exact-f32 SIMT GEMM for RPO_F32 and for shapes the tensor-core kernel does not take.  Each
+// pair's product is rounded to the dtype, the pair sum is accumulated in f32 exactly like the reference's f32
+// `logits` buffer.
 #include "common.cuh"
 
 namespace rpo {
@@ -137,9 +138,19 @@ int logits_ce_fwd(const T *img_feat, const T *text_feat, const float *logit_scal
   l2norm_fwd_kernel<T><<<(unsigned)((rows_t + 7) / 8), 256, 0, st>>>(text_feat, text_n, nullptr, text_norm, nullptr,
                                                                       rows_t, E);
   RPO_LAUNCH_CHECK();
-  Epilogue<T> ep{};
-  RPO_TRY(gemm_simt<T>(img_s, (long long)K * E, 1, text_n, (long long)K * E, 1, pair_logits, C, B, C, E, ep, K, E, E,
-                       (long long)B * C, st));
+  if constexpr (sizeof(T) == 2) {
+    if (logits_tc_supported(Num<T>::dtype, B, C, K, E)) {
+      RPO_TRY(logits_pair_fwd_tc<T>(img_s, text_n, pair_logits, B, C, K, E, st));
+    } else {
+      Epilogue<T> ep{};
+      RPO_TRY(gemm_simt<T>(img_s, (long long)K * E, 1, text_n, (long long)K * E, 1, pair_logits, C, B, C, E, ep, K, E,
+                           E, (long long)B * C, st));
+    }
+  } else {
+    Epilogue<T> ep{};
+    RPO_TRY(gemm_simt<T>(img_s, (long long)K * E, 1, text_n, (long long)K * E, 1, pair_logits, C, B, C, E, ep, K, E, E,
+                         (long long)B * C, st));
+  }
   // scratch for the f32 logits row: reuse `logits` if given, else `dlogits`
   float *scratch = logits ? logits : dlogits;
   RPO_REQUIRE(scratch != nullptr, "need logits or dlogits as f32 scratch");
@@ -167,13 +178,22 @@ int logits_ce_bwd(const float *dlogits, const T *img_feat, const T *text_feat, c
   // `logits /= K` then the dtype cast of the gradient flowing into each per-pair GEMM output
   scale_cast_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dlogits, dl_t, n, grad_scale / (float)K);
   RPO_LAUNCH_CHECK();
-  Epilogue<T> ep{};
-  // d img_s[b,k,:] = sum_c dl[b,c] text_n[c,k,:]
-  RPO_TRY(gemm_simt<T>(dl_t, C, 1, text_n, 1, (long long)K * E, d_img_s, (long long)K * E, B, E, C, ep, K, 0, E, E,
-                       st));
-  // d text_n[c,k,:] = sum_b dl[b,c] img_s[b,k,:]
-  RPO_TRY(gemm_simt<T>(dl_t, 1, C, img_s, 1, (long long)K * E, d_text_n, (long long)K * E, C, E, B, ep, K, 0, E, E,
-                       st));
+  bool on_tc = false;
+  if constexpr (sizeof(T) == 2) {
+    if (logits_tc_supported(Num<T>::dtype, B, C, K, E)) {
+      RPO_TRY(logits_pair_bwd_tc<T>(dl_t, img_s, text_n, d_img_s, d_text_n, B, C, K, E, st));
+      on_tc = true;
+    }
+  }
+  if (!on_tc) {
+    Epilogue<T> ep{};
+    // d img_s[b,k,:] = sum_c dl[b,c] text_n[c,k,:]
+    RPO_TRY(gemm_simt<T>(dl_t, C, 1, text_n, 1, (long long)K * E, d_img_s, (long long)K * E, B, E, C, ep, K, 0, E, E,
+                         st));
+    // d text_n[c,k,:] = sum_b dl[b,c] img_s[b,k,:]
+    RPO_TRY(gemm_simt<T>(dl_t, 1, C, img_s, 1, (long long)K * E, d_text_n, (long long)K * E, C, E, B, ep, K, 0, E, E,
+                         st));
+  }
   long long rows_i = (long long)B * K, rows_t = (long long)C * K;
   l2norm_bwd_kernel<T><<<(unsigned)((rows_i + 7) / 8), 256, 0, st>>>(d_img_s, img_n, img_norm, logit_scale, d_img_feat,
                                                                       rows_i, E);
