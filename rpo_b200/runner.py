@@ -192,7 +192,11 @@ class StepRunner:
                 (2 if self.peer is not None and self.sharded else 0)
             if self.use_graph:
                 own_kernels_only = self.world == 1 or self.peer is not None
-                self.graph = self._try_capture(self._enqueue)
+                # One graph for the whole step only when every node is a kernel of librpo_b200.  Capturing NCCL's
+                # collectives into the step graph hung on 2 x B200 (NCCL 2.28.9, torch 2.11: both ranks stall in
+                # the first replay, gpurun_out/n2/mode_*_False.log); the NCCL fallback therefore keeps the
+                # collectives eager between graph segments, as round 1 ran it on 2 / 4 / 8 GPUs.
+                self.graph = self._try_capture(self._enqueue) if own_kernels_only else None
                 if self.graph is None and own_kernels_only:
                     raise _lib.RpoError(f"CUDA-graph capture of the step failed: {self.capture_error}")
                 if self.graph is None:
@@ -211,8 +215,6 @@ class StepRunner:
                         with torch.cuda.graph(g):
                             self._chain(None)
                         self.segments = g
-                elif self.world > 1 and self.peer is None:
-                    self.collectives = "nccl-graph"
             self._restore(snap)
             torch.cuda.synchronize()
         return self
