@@ -1402,8 +1402,12 @@ static int pick_config(long long M, int N, int Kd) {
   //  * smaller M (text tower C*K rows, the prompt-row backward): latency-bound chains -- the light
   //    128 x 64 configuration (two CTAs per SM) is best or within 5% of best on every such shape; long-K,
   //    few-tile problems get 128 x 32 tiles to put more SMs on the serial K loop.
+  //  * ViT-L/14 at batch 16 (M = 4112 / 4496, 36 row tiles) belongs with the all-row GEMMs: pairs 22.2 / 29.4 / 29.8 us
+  //    against 36.8 / 48.9 / 48.4 us for the light tiles on QKV / c_fc / c_proj; its text tower (M = 2400, N = 768:
+  //    114 tiles of 128 x 128 = one wave) is 10-25 % faster on 128 x 128 tiles, N = 3072 on pairs
+  //    (profiles/r02_gemm_config_sweep_vitl14.txt).  ViT-B/16's text tower (N = 512 / 2048) stays on the light tiles.
   const long long mt = (M + BM - 1) / BM;
-  if (mt >= 40) {
+  if (mt >= 32) {
     // (N = 768 -- out-proj, c_proj, patch embedding: 84 tiles of 256 x 256 are 2 rounds on 74 SM pairs, the second 14 %
     // full.  256 x 384 tiles (ONE round, single accumulator) were built and measured slower -- out-proj 17.1 -> 18.9 us,
     // c_proj 39.1 -> 41.0, step 3.27 -> 3.51 ms -- and removed: profiles/r01_gemm_config_sweep.txt.)
@@ -1411,6 +1415,11 @@ static int pick_config(long long M, int N, int Kd) {
     if (N % 128 == 0) return CFG_S128;
     if (N % 64 == 0) return CFG_S64;
     return CFG_S32;
+  }
+  if (mt >= 16) {
+    const long long tiles128 = mt * (N / 128);
+    if (N % 256 == 0 && N >= 3072) return CFG_P256;
+    if (N % 128 == 0 && tiles128 >= 100 && tiles128 <= 160) return CFG_S128;
   }
   if (N % 64 == 0 && Kd >= 2048 && mt * (N / 64) * 4 <= 2LL * sm_count())
     // long serial K loops on few tiles (backward MLP of the vision prompt rows, 72 tiles x 48 k-blocks): split K over a

@@ -138,26 +138,34 @@ __global__ void __launch_bounds__(THREADS, 2)
         const int kd0 = seg * SEG;
         const int kd_end = min(p.Kd, kd0 + SEG);
         const int steps = (min(num_kb * 64, kd0 + SEG) - kd0) >> 4;  // 16 contraction elements per step, whole 64-blocks
-        for (int st = 0; st < steps; ++st) {
-          const int kd = kd0 + st * 16;
-          uint32_t pk[8];
-          if (valid && p.a_vec && kd + 16 <= kd_end) {
-            const uint4 v0 = *reinterpret_cast<const uint4 *>(arow + kd);
-            const uint4 v1 = *reinterpret_cast<const uint4 *>(arow + kd + 8);
-            pk[0] = v0.x, pk[1] = v0.y, pk[2] = v0.z, pk[3] = v0.w;
-            pk[4] = v1.x, pk[5] = v1.y, pk[6] = v1.z, pk[7] = v1.w;
-          } else {
+        // all of the segment's loads first (they are independent: one memory latency per segment, not per step), then
+        // the tensor-memory stores
+        uint32_t pk[SEG / 16][8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              unsigned short lo = 0, hi = 0;
-              if (valid && kd + 2 * e < kd_end) lo = *reinterpret_cast<const unsigned short *>(arow + (long long)(kd + 2 * e) * p.a_k);
-              if (valid && kd + 2 * e + 1 < kd_end)
-                hi = *reinterpret_cast<const unsigned short *>(arow + (long long)(kd + 2 * e + 1) * p.a_k);
-              pk[e] = (uint32_t)lo | ((uint32_t)hi << 16);
+        for (int st = 0; st < SEG / 16; ++st) {
+          const int kd = kd0 + st * 16;
+          if (st < steps) {
+            if (valid && p.a_vec && kd + 16 <= kd_end) {
+              const uint4 v0 = *reinterpret_cast<const uint4 *>(arow + kd);
+              const uint4 v1 = *reinterpret_cast<const uint4 *>(arow + kd + 8);
+              pk[st][0] = v0.x, pk[st][1] = v0.y, pk[st][2] = v0.z, pk[st][3] = v0.w;
+              pk[st][4] = v1.x, pk[st][5] = v1.y, pk[st][6] = v1.z, pk[st][7] = v1.w;
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                unsigned short lo = 0, hi = 0;
+                if (valid && kd + 2 * e < kd_end)
+                  lo = *reinterpret_cast<const unsigned short *>(arow + (long long)(kd + 2 * e) * p.a_k);
+                if (valid && kd + 2 * e + 1 < kd_end)
+                  hi = *reinterpret_cast<const unsigned short *>(arow + (long long)(kd + 2 * e + 1) * p.a_k);
+                pk[st][e] = (uint32_t)lo | ((uint32_t)hi << 16);
+              }
             }
           }
-          tmem_st8(lane_base + (uint32_t)(buf * A_COLS + st * 8), pk);
         }
+#pragma unroll
+        for (int st = 0; st < SEG / 16; ++st)
+          if (st < steps) tmem_st8(lane_base + (uint32_t)(buf * A_COLS + st * 8), pk[st]);
         tmem_st_wait();
         tc_fence_before();
       }

@@ -17,7 +17,7 @@ for c in cfgs:
     for line in open(f"gpurun_out/${TAG}_kb_{c}.log"):
         if line.startswith("gemm"):
             p=line.split()
-            rows.setdefault(p[1],{})[c]=p[8]
+            rows.setdefault(p[1],{})[c]=p[5]  # microseconds
 print("shape".ljust(12)+" ".join(c.rjust(7) for c in cfgs))
 for k,v in rows.items():
     print(k.ljust(12)+" ".join(v.get(c,'-').rjust(7) for c in cfgs))
