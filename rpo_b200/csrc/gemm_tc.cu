@@ -1411,6 +1411,9 @@ static int pick_config(long long M, int N, int Kd) {
     // (N = 768 -- out-proj, c_proj, patch embedding: 84 tiles of 256 x 256 are 2 rounds on 74 SM pairs, the second 14 %
     // full.  256 x 384 tiles (ONE round, single accumulator) were built and measured slower -- out-proj 17.1 -> 18.9 us,
     // c_proj 39.1 -> 41.0, step 3.27 -> 3.51 ms -- and removed: profiles/r01_gemm_config_sweep.txt.)
+    // (graph-timed re-sweep of round 2, profiles/r02_gemm_config_sweep_vitb16.txt: c_proj -- N = 768, K = 3072 -- takes
+    // 32.4 us on 256 x 192 pair tiles, 112 tiles = 1.5 rounds, against 36.5 us on 256 x 256)
+    if (N % 192 == 0 && N < 2048 && Kd >= 2048) return CFG_P192;
     if (N % 256 == 0 && (N >= 2048 || Kd >= 2048)) return CFG_P256;
     if (N % 128 == 0) return CFG_S128;
     if (N % 64 == 0) return CFG_S64;
@@ -1420,6 +1423,9 @@ static int pick_config(long long M, int N, int Kd) {
     const long long tiles128 = mt * (N / 128);
     if (N % 256 == 0 && N >= 3072) return CFG_P256;
     if (N % 128 == 0 && tiles128 >= 100 && tiles128 <= 160) return CFG_S128;
+    // text tower c_proj and its input-gradient twin (M = 2400, N = 512, K = 2048): 12.5 / 11.7 us on 128 x 128 tiles
+    // against 15.1 / 14.5 us on the light 128 x 64 ones (same sweep)
+    if (N % 128 == 0 && Kd >= 2048) return CFG_S128;
   }
   if (N % 64 == 0 && Kd >= 2048 && mt * (N / 64) * 4 <= 2LL * sm_count())
     // long serial K loops on few tiles (backward MLP of the vision prompt rows, 72 tiles x 48 k-blocks): split K over a
