@@ -396,9 +396,18 @@ static int logits_forward_stage(RpoHandle *hd, const int64_t *label, float *logi
   return RPO_OK;
 }
 
-// fp16 gradients of this path sit around 1e-5 .. 1e-3, i.e. in the subnormal range of the format: the
-// backward runs on gradients scaled by 2^12 (exact) and the f32 reductions at the end divide it out
-static float grad_prescale(const RpoConfig &c) { return (c.dtype == RPO_F16) ? 4096.0f : 1.0f; }
+// fp16 gradients of this path sit around 1e-5 .. 1e-3, i.e. in the subnormal range of the format: the backward
+// runs on gradients scaled by a power of two (exact) and the f32 reductions at the end divide it out.  dlogits
+// carries 1 / (K * B) (mean over the batch, /K over the pairs), so the scale follows K * B: 2^12 from K * B = 512
+// (config 2: 768) down to 2^6 for a single pair and image, where 2^12 would push exp(logit_scale) * d_img_s
+// (about scale * 100 / (K * B) * 0.1) to the edge of the fp16 range.
+static float grad_prescale(const RpoConfig &c, int B) {
+  if (c.dtype != RPO_F16) return 1.0f;
+  const long long s = 8LL * c.K * (B > 0 ? B : 1);
+  float p = 64.0f;
+  while (p * 2.0f <= (float)s && p < 4096.0f) p *= 2.0f;
+  return p;
+}
 
 template <typename T>
 static int logits_backward_stage(RpoHandle *hd, cudaStream_t st) {
@@ -407,7 +416,7 @@ static int logits_backward_stage(RpoHandle *hd, cudaStream_t st) {
   RPO_TRY(logits_ce_bwd<T>(hd->dlogits, (const T *)hd->img_feat, (const T *)hd->text_feat, (const T *)hd->img_n,
                            (const T *)hd->img_s, (const T *)hd->text_n, hd->img_norm, hd->text_norm, hd->w.logit_scale,
                            hd->B, c.n_cls, c.K, c.embed_dim, (T *)hd->dl_t, (T *)hd->d_img_s, (T *)hd->d_text_n,
-                           (T *)hd->d_img_feat, (T *)hd->d_text_feat, grad_prescale(c), st));
+                           (T *)hd->d_img_feat, (T *)hd->d_text_feat, grad_prescale(c, hd->B), st));
   hd->have_logits_bwd = true;
   hd->launches[3] = g_launch_count;
   return RPO_OK;
@@ -428,7 +437,7 @@ static int text_backward_stage(RpoHandle *hd, float *grad_flat, cudaStream_t st)
   RPO_TRY(layernorm_bwd<T>((const T *)t.dh, xt_out, hd->w.ln_final_w, nullptr, (T *)t.dx, Mp_t, Dt, st));
   if (hd->skip != 1) RPO_TRY(tower_backward<T>(hd, t, st));
   // d text_prompt: the prompt is shared by all classes (trainers/rpo.py:176-177)
-  RPO_TRY(reduce_groups_f32<T>((const T *)t.dx, grad_flat, Cl, K, Dt, 1.0f / grad_prescale(c), st));
+  RPO_TRY(reduce_groups_f32<T>((const T *)t.dx, grad_flat, Cl, K, Dt, 1.0f / grad_prescale(c, hd->B), st));
   hd->launches[4] = g_launch_count;
   return RPO_OK;
 }
@@ -448,7 +457,7 @@ static int image_backward_stage(RpoHandle *hd, float *grad_flat, cudaStream_t st
   RPO_TRY(layernorm_bwd<T>((const T *)v.dh, xv_out, hd->w.ln_post_w, nullptr, (T *)v.dx, Mp_v, Dv, st));
   if (hd->skip != 2) RPO_TRY(tower_backward<T>(hd, v, st));
   // d img_prompt: sum over images, then through ln_pre (trainers/rpo.py:204-206)
-  RPO_TRY(reduce_groups_f32<T>((const T *)v.dx, hd->dsum_v, B, K, Dv, 1.0f / grad_prescale(c), st));
+  RPO_TRY(reduce_groups_f32<T>((const T *)v.dx, hd->dsum_v, B, K, Dv, 1.0f / grad_prescale(c, hd->B), st));
   RPO_TRY(lnpre_prompt_bwd<T>(hd->dsum_v, (const T *)hd->img_prompt, hd->w.ln_pre_w, grad_flat + (size_t)K * Dt, K, Dv,
                               st));
   hd->launches[5] = g_launch_count;

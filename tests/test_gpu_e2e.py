@@ -290,13 +290,14 @@ def _long_tokens(n_words, width=77):
 
 
 @pytest.mark.parametrize("prec", ["fp32", "fp16"])
-@pytest.mark.parametrize("case", ["k1", "one_class_one_image", "max_length", "ragged_with_max"])
+@pytest.mark.parametrize("case", ["k1", "k1_b1", "one_class_one_image", "max_length", "ragged_with_max"])
 def test_edge_shapes_match_oracle(prec, case):
     """Edges of the reference's index arithmetic (trainers/rpo.py:137,149,177): a single prompt pair, a single
     class / image, a class prompt whose K prompt slots end exactly at position 76 (len_prompts + K == 77), and a
     class list mixing the shortest and the longest admissible prompts."""
-    K, B = {"k1": (1, 3), "one_class_one_image": (3, 1), "max_length": (4, 2), "ragged_with_max": (4, 3)}[case]
-    if case == "k1":
+    K, B = {"k1": (1, 3), "k1_b1": (1, 1), "one_class_one_image": (3, 1), "max_length": (4, 2),
+            "ragged_with_max": (4, 3)}[case]
+    if case in ("k1", "k1_b1"):  # k1_b1: one pair, one image -- the largest dlogits the fp16 backward can see
         tokens = class_tokens([5, 600])
     elif case == "one_class_one_image":
         tokens = class_tokens([42])
