@@ -2,8 +2,9 @@
 //   forward   pair[k][b][c]      = dtype( img_s[b,k,:] . text_n[c,k,:] )            M = C, N = B, Kd = E
 //   backward  d_img_s[b,k,:]     = dtype( sum_c dl[b,c] text_n[c,k,:] )            M = B, N = E, Kd = C
 //             d_text_n[c,k,:]    = dtype( sum_b dl[b,c] img_s[b,k,:] )             M = C, N = E, Kd = B
-// One batched launch each (grid.y = pair k).  The shapes are small and odd (B = 16..64 rows, C = 100 classes, dl rows
-// of 200 bytes), so the operand that has them goes the way the attention kernel sends its probabilities: the 128
+// One batched launch each (grid.y = pair k).  Forward: both operands are 16-byte aligned K-major feature matrices and
+// both go through the TMA ring (plain SS MMA).  Backward: the shapes are small and odd (B = 16..64 rows, dl rows of
+// 2 C = 200 bytes), so the operand that has them goes the way the attention kernel sends its probabilities: the 128
 // threads that own the 128 rows (= TMEM lanes) of the tile read it from global memory with whatever strides it has,
 // and write it into TENSOR MEMORY as the A operand (tcgen05.st, two 16-bit values per column; 128 contraction
 // elements per segment, two segments in flight).  The other operand is always one of the two big, aligned feature
@@ -24,7 +25,9 @@ using namespace tc;
 
 static constexpr int THREADS = 192;      // warps 0..3: rows (A operand, epilogue); warp 4: TMA; warp 5: MMA issue
 static constexpr int STAGES = 4;
-static constexpr int STAGE_BYTES = 64 * 128;  // K-major: <= 64 rows x 128 B; MN-major: 64 contraction rows x 128 B
+static constexpr int B_STAGE_BYTES = 64 * 128;  // K-major: <= 64 rows x 128 B; MN-major: 64 contraction rows x 128 B
+static constexpr int A_STAGE_BYTES = 128 * 128;  // forward only: the A tile through TMA as well (128 rows x 64 columns)
+static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 static constexpr int SEG = 128;          // contraction elements of A per TMEM buffer (64 columns)
 static constexpr int KB_PER_SEG = SEG / 64;
 static constexpr int A_COLS = SEG / 2;
@@ -41,12 +44,15 @@ struct Args {
   int M, N, Kd;                // problem size per batch; N <= 64 per tile
   int n_tiles;                 // tiles along N (64 wide) -- 1 for the forward
   int b_col_batch;             // TMA column coordinate of B: batch * b_col_batch + (MN-major: n0; K-major: kd0)
+  int a_col_batch;             // A through TMA (forward): column coordinate batch * a_col_batch + kd0, row m0
   int nb;                      // UMMA N (multiple of 16, <= 64)
 };
 
-template <typename T, bool B_MN>
+// A_TMA (forward): both operands are aligned K-major feature matrices, so A takes the TMA ring too (plain SS MMA) and
+// the row threads only run the epilogue
+template <typename T, bool B_MN, bool A_TMA>
 __global__ void __launch_bounds__(THREADS, 2)
-    pair_gemm_kernel(const __grid_constant__ CUtensorMap map_b, Args p) {
+    pair_gemm_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_a, Args p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t ring = smem_u32(smem);
@@ -91,13 +97,14 @@ __global__ void __launch_bounds__(THREADS, 2)
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
         if (kb >= STAGES) mbar_wait(BAR(B_EMPTY + s), (uint32_t)(((kb / STAGES) - 1) & 1));
-        const uint32_t dst = ring + s * STAGE_BYTES;
+        const uint32_t dst = ring + s * STAGE_BYTES + A_STAGE_BYTES;
         if (B_MN) {
           mbar_arrive_expect_tx(BAR(B_FULL + s), 64 * 128);
           tma_load_2d(dst, &map_b, BAR(B_FULL + s), batch * p.b_col_batch + n0, kb * 64);
         } else {
-          mbar_arrive_expect_tx(BAR(B_FULL + s), (uint32_t)(p.nb * 128));
+          mbar_arrive_expect_tx(BAR(B_FULL + s), (uint32_t)(p.nb * 128) + (A_TMA ? (uint32_t)A_STAGE_BYTES : 0u));
           tma_load_2d(dst, &map_b, BAR(B_FULL + s), batch * p.b_col_batch + kb * 64, 0);
+          if (A_TMA) tma_load_2d(ring + s * STAGE_BYTES, &map_a, BAR(B_FULL + s), batch * p.a_col_batch + kb * 64, m0);
         }
       }
     }
@@ -108,17 +115,23 @@ __global__ void __launch_bounds__(THREADS, 2)
       const uint32_t idesc = make_idesc((int)fmt, 128, p.nb) | (B_MN ? (1u << 16) : 0u);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int seg = kb / KB_PER_SEG, buf = seg & 1, s = kb % STAGES;
-        if (kb % KB_PER_SEG == 0) mbar_wait(BAR(A_FULL + buf), (uint32_t)((seg >> 1) & 1));
+        if (!A_TMA && kb % KB_PER_SEG == 0) mbar_wait(BAR(A_FULL + buf), (uint32_t)((seg >> 1) & 1));
         mbar_wait(BAR(B_FULL + s), (uint32_t)((kb / STAGES) & 1));
         tc_fence_after();
-        const uint64_t bdesc = make_smem_desc(ring + s * STAGE_BYTES);
-        const uint32_t acol = tmem_base + (uint32_t)(buf * A_COLS + (kb % KB_PER_SEG) * 32);
+        const uint64_t bdesc = make_smem_desc(ring + s * STAGE_BYTES + A_STAGE_BYTES);
+        if (A_TMA) {
+          const uint64_t adesc = make_smem_desc(ring + s * STAGE_BYTES);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // 16 contraction elements: 8 columns of A; K-major B: 32 bytes along the row, MN-major: 16 rows
-          umma_f16_ts(tmem_base + D_COL, acol + (uint32_t)(k * 8), bdesc + (uint64_t)(B_MN ? k * 128 : k * 2), idesc,
-                      (kb | k) != 0);
+          for (int k = 0; k < 4; ++k) umma_f16(tmem_base + D_COL, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0);
+        } else {
+          const uint32_t acol = tmem_base + (uint32_t)(buf * A_COLS + (kb % KB_PER_SEG) * 32);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // 16 contraction elements: 8 columns of A; K-major B: 32 bytes along the row, MN-major: 16 rows
+            umma_f16_ts(tmem_base + D_COL, acol + (uint32_t)(k * 8), bdesc + (uint64_t)(B_MN ? k * 128 : k * 2), idesc,
+                        (kb | k) != 0);
+        }
         umma_commit(BAR(B_EMPTY + s));
-        if (kb % KB_PER_SEG == KB_PER_SEG - 1 || kb == num_kb - 1) umma_commit(BAR(A_FREE + buf));
+        if (!A_TMA && (kb % KB_PER_SEG == KB_PER_SEG - 1 || kb == num_kb - 1)) umma_commit(BAR(A_FREE + buf));
       }
       umma_commit(BAR(D_FULL));
     }
@@ -130,7 +143,7 @@ __global__ void __launch_bounds__(THREADS, 2)
     const bool warp_valid = m0 + warp * 32 < p.M;
     const T *arow = reinterpret_cast<const T *>(p.a) + (long long)m * p.a_m + (long long)batch * p.a_b;
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-    for (int seg = 0; seg < num_seg; ++seg) {
+    for (int seg = 0; seg < (A_TMA ? 0 : num_seg); ++seg) {
       const int buf = seg & 1;
       if (seg >= 2) mbar_wait(BAR(A_FREE + buf), (uint32_t)(((seg >> 1) - 1) & 1));
       if (warp_valid) {
@@ -219,15 +232,16 @@ __global__ void __launch_bounds__(THREADS, 2)
 }
 
 // 2D row-major [rows, cols] 16-bit tensor, box = [box_rows, 64 cols], 128B swizzle (tc::make_map with the row count free)
-template <typename T, bool B_MN>
-static int launch(const CUtensorMap &map_b, const Args &p, int batches, cudaStream_t st) {
+template <typename T, bool B_MN, bool A_TMA>
+static int launch(const CUtensorMap &map_b, const CUtensorMap &map_a, const Args &p, int batches, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    RPO_CHECK_CUDA(cudaFuncSetAttribute(pair_gemm_kernel<T, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    RPO_CHECK_CUDA(cudaFuncSetAttribute(pair_gemm_kernel<T, B_MN, A_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        SMEM_BYTES));
     attr_set = true;
   }
   dim3 grid((unsigned)(((p.M + 127) / 128) * p.n_tiles), (unsigned)batches);
-  pair_gemm_kernel<T, B_MN><<<grid, THREADS, SMEM_BYTES, st>>>(map_b, p);
+  pair_gemm_kernel<T, B_MN, A_TMA><<<grid, THREADS, SMEM_BYTES, st>>>(map_b, map_a, p);
   RPO_LAUNCH_CHECK();
   return RPO_OK;
 }
@@ -248,14 +262,15 @@ int logits_pair_fwd_tc(const T *img_s, const T *text_n, T *pair, int B, int C, i
   RPO_REQUIRE(logits_tc_supported(Num<T>::dtype, B, C, K, E), "logit block shape for the tcgen05 path");
   RPO_REQUIRE((((uintptr_t)img_s | (uintptr_t)text_n) & 15) == 0, "feature matrices must be 16-byte aligned");
   const int nb = (B + 15) & ~15;
-  CUtensorMap map_b;  // B operand = img_s [B rows, K*E], K-major boxes of nb rows x 64 columns
+  CUtensorMap map_b, map_a;  // B operand = img_s [B rows, K*E], K-major boxes of nb rows x 64 columns; A = text_n, 128-row boxes
   RPO_TRY(tc::make_map(&map_b, Num<T>::dtype, img_s, B, K * E, (long long)K * E, nb));
+  RPO_TRY(tc::make_map(&map_a, Num<T>::dtype, text_n, C, K * E, (long long)K * E, 128));
   Args p{};
   p.a = text_n, p.a_m = (long long)K * E, p.a_k = 1, p.a_b = E, p.a_vec = 1;
   p.out = pair, p.o_m = 1, p.o_n = C, p.o_b = (long long)B * C;
-  p.M = C, p.N = B, p.Kd = E, p.n_tiles = 1, p.b_col_batch = E, p.nb = nb;
+  p.M = C, p.N = B, p.Kd = E, p.n_tiles = 1, p.b_col_batch = E, p.a_col_batch = E, p.nb = nb;
   prof_tag("logits_pair_fwd_tc B=%d C=%d K=%d E=%d", B, C, K, E);
-  return launch<T, false>(map_b, p, K, st);
+  return launch<T, false, true>(map_b, map_a, p, K, st);
 }
 
 // d_img_s[b,k,:] = dtype( sum_c dl[b,c] text_n[c,k,:] ),  d_text_n[c,k,:] = dtype( sum_b dl[b,c] img_s[b,k,:] )
@@ -274,7 +289,7 @@ int logits_pair_bwd_tc(const T *dl, const T *img_s, const T *text_n, T *d_img_s,
     p.out = d_img_s, p.o_m = (long long)K * E, p.o_n = 1, p.o_b = E;
     p.M = B, p.N = E, p.Kd = C, p.n_tiles = E / 64, p.b_col_batch = E, p.nb = 64;
     prof_tag("logits_pair_dimg_tc B=%d C=%d K=%d E=%d", B, C, K, E);
-    RPO_TRY((launch<T, true>(map_b, p, K, st)));
+    RPO_TRY((launch<T, true, false>(map_b, map_b, p, K, st)));
   }
   {
     CUtensorMap map_b;  // B operand = img_s [B rows, K*E], MN-major
@@ -284,7 +299,7 @@ int logits_pair_bwd_tc(const T *dl, const T *img_s, const T *text_n, T *d_img_s,
     p.out = d_text_n, p.o_m = (long long)K * E, p.o_n = 1, p.o_b = E;
     p.M = C, p.N = E, p.Kd = B, p.n_tiles = E / 64, p.b_col_batch = E, p.nb = 64;
     prof_tag("logits_pair_dtext_tc B=%d C=%d K=%d E=%d", B, C, K, E);
-    RPO_TRY((launch<T, true>(map_b, p, K, st)));
+    RPO_TRY((launch<T, true, false>(map_b, map_b, p, K, st)));
   }
   return RPO_OK;
 }

@@ -425,7 +425,12 @@ def ref_logits(img_feat, text_feat, logit_scale, K):
 
 
 @pytest.mark.parametrize("prec", ["fp32", "fp16", "bf16"])
-@pytest.mark.parametrize("B,Cn,K,E", [(2, 2, 4, 512), (32, 100, 24, 512), (5, 1000, 3, 128)])
+@pytest.mark.parametrize("B,Cn,K,E", [(2, 2, 4, 512), (32, 100, 24, 512), (5, 1000, 3, 128),
+                                      # edges of the tcgen05 pair kernels: full / odd batch, odd class counts (dl rows that
+                                      # are not 16-byte aligned), one pair, the ViT-L/14 embedding width, a width the
+                                      # tensor-core path does not take (falls back to the SIMT GEMM)
+                                      (64, 37, 2, 64), (16, 100, 24, 768), (1, 3, 1, 128), (33, 1000, 2, 512),
+                                      (7, 129, 3, 96)])
 def test_logits_ce_fwd_bwd(prec, B, Cn, K, E):
     lib = _lib.load()
     dt = DT[prec]
