@@ -1,4 +1,4 @@
-// tcgen05 form of the read-only masked attention forward for the vision tower (every group has the same
+// tcgen05 forms of the read-only masked attention forward for the vision tower (every group has the same
 // number n of context rows, no causal mask): clip/model.py:186 under visual_mask of trainers/rpo.py:153-159.
 // The metric's masked-attention kernel.
 //
@@ -6,22 +6,24 @@
 // head) are its n context rows followed by its K prompt rows (the last tile holds both); keys / values are the n
 // context rows only -- that IS the mask.  K and V of a head are loaded once and serve all its query tiles.
 //
-//   warp 0 (one thread)   TMA producer: K | V of the next (image, head) into a 2-deep buffer, Q tiles into a ring
-//                         (cp.async.bulk.tensor, 128B swizzle, straight out of the [rows, 3D] q|k|v matrix and the
-//                         [G*K, D] prompt-q matrix).
-//   warp 1 (one thread)   MMA issuer: S = Q K^T (M=128, N=n16 in one or two instructions per 16-wide k step, f32 in
-//                         TMEM slot i%SLOTS), and -- one tile behind -- O = P V with P read FROM TENSOR MEMORY
-//                         (tcgen05.mma, A operand in TMEM) and V consumed as loaded (MN-major B operand).
-//   warps 4..11           softmax, two threads per query row (TMEM lane): ONE pass over S -- the thread's half of the
-//                         row is loaded into registers, row maximum (halves exchanged through shared memory),
-//                         p = ex2((s - max) / 8 log2 e), f32 row sum, p rounded to the dtype and written back to
-//                         tensor memory over the dead S columns (tcgen05.st) as the A operand of P V.
-//   warps 12..15          epilogue, one thread per query row: O out of TMEM, times 1/sum, 128 contiguous bytes to
-//                         global; frees the slot for the S of two tiles later.
-// With two TMEM slots (n16 <= 256: ViT-B/16) the S MMA of tile i+1 and the P V MMA / epilogue of tile i-1 run beside
-// the softmax of tile i; the exponentials (MUFU) are the only serial resource.  n16 > 256 (ViT-L/14: 257 keys) uses one
-// 512-column slot and two N blocks per S.
-// Registers: the three roles re-partition the register file with setmaxnreg (softmax threads hold up to 9 x 16 scores).
+// Two kernels share the producer and the work decomposition:
+//   * ro_attn_fwd_pp (second half of the file): n <= 224 keys (ViT-B/16: 197).  Two S slots in tensor memory, two
+//     softmax warp groups on alternate tiles, probabilities kept in tensor memory.  Described at its definition.
+//   * ro_attn_fwd_tc (below): 225 .. 272 keys (ViT-L/14: 257), ONE 512-column slot, S in two UMMA N blocks (144 + rest).
+//
+// ro_attn_fwd_tc:
+//   warp 0 (one thread)   TMA producer: K | V of the next (image, head) through a ring of three buffers, Q tiles into a
+//                         ring (cp.async.bulk.tensor, 128B swizzle, straight out of the [rows, 3D] q|k|v matrix and
+//                         the [G*K, D] prompt-q matrix).
+//   warp 1 (one thread)   S = Q K^T (M=128, two N blocks per 16-wide k step, f32 in tensor memory)
+//   warp 2 (one thread)   O = P V, one tile behind: P from a 128B-swizzled shared-memory tile, V consumed as loaded
+//                         (MN-major B operand), into the last 64 TMEM columns
+//   warps 4..19           softmax, four threads per query row (TMEM lane), each with a quarter of the 16-key blocks held
+//                         in registers: row maximum (quarters exchanged through shared memory),
+//                         p = ex2((s - max) / 8 log2 e), f32 row sum, p rounded to the dtype into the P tile; a block's
+//                         registers take the next tile's scores as soon as its probabilities are stored
+//   warps 20..23          epilogue, one thread per query row: O out of TMEM, times 1/sum, 128 contiguous bytes to global
+// Registers: the roles re-partition the register file with setmaxnreg (softmax threads hold up to 5 x 16 scores).
 #include <stdlib.h>
 
 #include <map>
@@ -156,8 +158,8 @@ __device__ __forceinline__ void advance(const Geo &geo, Item &it) {
   it.p_rows = (it.t == geo.prompt_tile) ? geo.K : 0;
 }
 
-// MAXB: 16-key blocks a softmax thread keeps in registers (>= ceil(nblk / PARTS)); SLOTS: S slots in tensor memory
-template <typename T, int MAXB, int SLOTS>
+// MAXB: 16-key blocks a softmax thread keeps in registers (>= ceil(nblk / PARTS))
+template <typename T, int MAXB>
 __global__ void __launch_bounds__(THREADS, 1)
     ro_attn_fwd_tc(const __grid_constant__ CUtensorMap map_full,   // q|k|v matrix, box 64 x 128
                    const __grid_constant__ CUtensorMap map_kvt,    // q|k|v matrix, box 64 x (n16 % 128)
@@ -167,6 +169,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   // tensor memory: S slot s at columns [s * SLOT_COLS, ...), O in the last 64 columns
+  constexpr int SLOTS = 1;  // one S slot (the two-slot form is ro_attn_fwd_pp); the slot arithmetic below keeps the general form
   constexpr int SLOT_COLS = SLOTS == 2 ? 224 : 0;
   constexpr uint32_t O_COL = TMEM_COLS - HD;
   const int n = geo.n, n16 = geo.n16, K = geo.K, H = geo.H, NQ = geo.q_ring;
@@ -1099,7 +1102,7 @@ int ro_attention_fwd_dense(const T *qkv_ctx, const T *q_prompt, T *out_ctx, T *o
       };
       // 15 .. 18 key blocks: MAXB = key blocks of the busiest softmax thread (see the kernel)
       const int rounds = geo.nblk / PARTS + (geo.nblk % PARTS ? 1 : 0);
-      s = rounds <= 4 ? launch(ro_attn_fwd_tc<T, 4, 1>) : launch(ro_attn_fwd_tc<T, 5, 1>);
+      s = rounds <= 4 ? launch(ro_attn_fwd_tc<T, 4>) : launch(ro_attn_fwd_tc<T, 5>);
     }
     RPO_TRY(s);
     RPO_LAUNCH_CHECK();
