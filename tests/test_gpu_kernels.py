@@ -365,6 +365,9 @@ DENSE_CASES = [
     ("vitb16_k24_b32", 32, 197, 24, 12), ("vitb16_k48_b64", 64, 197, 48, 12), ("vitb16_ctx_only_b32", 32, 197, 0, 12),
     # ViT-L/14 (BASELINE config 3): 257 keys = two UMMA N blocks in one 512-column TMEM slot, three query tiles
     ("vitl14_k24", 2, 257, 24, 16), ("vitl14_k24_b16", 16, 257, 24, 16), ("n272", 3, 272, 0, 2), ("n16_one_block", 3, 9, 3, 1),
+    # the widest two-slot shape (14 key blocks, 7 per softmax thread), an odd block count with prompts, one key block more
+    # than ViT-B/16, and the first shape of the single-slot kernel
+    ("n224_k16", 2, 224, 16, 2), ("n200_k40", 3, 200, 40, 3), ("n209_k8", 2, 209, 8, 2), ("n225_k0", 2, 225, 0, 2),
 ]
 
 
