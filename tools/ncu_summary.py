@@ -1,5 +1,5 @@
 """Key metrics of an .ncu-rep (one line per metric, one column per captured launch), read with `ncu -i`.
-Used to turn the captures of tools/profile_step.sh into the text summaries committed under profiles/.
+Used to turn the captures of tools/evidence.sh into the text summaries committed under profiles/.
 
     python tools/ncu_summary.py gpurun_out/x.ncu-rep [metric-prefix ...] > profiles/x.txt
 """
