@@ -591,7 +591,9 @@ __global__ void __launch_bounds__(THREADS, 1)
 // tile -> maximum, about 1.8k clocks in which only one group has work.  Rejected after measurement: the maximum on
 // the epilogue warps (their wake-up sits on that chain), one thread per row (a single warp per scheduler cannot
 // keep the MUFU pipe fed: 200 clocks per key block instead of 131), S(j+2) issued by the P V thread straight behind
-// P V(j) (completes ~1000 clocks later than from its own thread after the commit).
+// P V(j) (completes ~1000 clocks later than from its own thread after the commit), a share of the exponentials as a
+// degree-4 polynomial on the FMA pipe (2 / 3 / 4 / 5 of every 8 key pairs: 17.2 / 17.6 / 18.2 / 18.9 us against 17.2:
+// the softmax pass is bound by instruction issue and latency, not by the MUFU pipe alone).
 //
 //   warp 0 (one thread)   TMA producer (as above)
 //   warp 1 (one thread)   S = Q K^T into slot j % 2 once P V of tile j-2 has consumed that slot's P
