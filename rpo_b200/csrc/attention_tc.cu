@@ -111,9 +111,22 @@ __device__ long long *g_attn_trace = nullptr;
   do {                                                                                     \
     if (blockIdx.x == 0 && trace_buf && (j) < 64) trace_buf[(j) * 16 + (ev)] = clock64(); \
   } while (0)
+// wall-clock stamps of EVERY CTA behind the phase table: trace[1024 + 4 * cta + k] = globaltimer (ns) at
+// k = 0 kernel entry, 1 dependency released (producer past griddepcontrol.wait), 2 all roles done, 3 exit
+#define ATTN_WALL(k)                                                                                   \
+  do {                                                                                                 \
+    if (trace_buf) {                                                                                   \
+      unsigned long long t_;                                                                           \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                           \
+      trace_buf[1024 + 4 * blockIdx.x + (k)] = (long long)t_;                                          \
+    }                                                                                                  \
+  } while (0)
 #else
 #define ATTN_TRACE(j, ev) \
   do {                    \
+  } while (0)
+#define ATTN_WALL(k) \
+  do {               \
   } while (0)
 #endif
 
@@ -653,7 +666,10 @@ __global__ void __launch_bounds__(PP_THREADS, 1)
   const int count = item1 - item0;
 #ifdef RPO_DIAG
   long long *const trace_buf = g_attn_trace;
-  if (threadIdx.x == 0) ATTN_TRACE(0, 12);
+  if (threadIdx.x == 0) {
+    ATTN_TRACE(0, 12);
+    ATTN_WALL(0);
+  }
 #endif
 
   if (threadIdx.x == 0) {
@@ -705,6 +721,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1)
     if (lane == 0) {
       // ===== TMA producer =====
       pdl_wait();
+      ATTN_WALL(1);
       for (int j = 0; j < count; ++j) {
         const Item it = item_of(geo, item0 + j);
         if (first_of_unit(j)) {
@@ -890,18 +907,18 @@ __global__ void __launch_bounds__(PP_THREADS, 1)
             prob_block(i + 1, has_pad && i + 1 == cnt - 1, b);
           }
           if (tracer && i == 0) ATTN_TRACE(j, 11);
-          if (tracer && i == 2) ATTN_TRACE(j, 12);
-          if (tracer && i == 4) ATTN_TRACE(j, 13);
+          if (tracer && i == 2 && j > 0) ATTN_TRACE(j, 12);
+          if (tracer && i == 4 && j > 0) ATTN_TRACE(j, 13);
         }
       }
-      if (tracer) ATTN_TRACE(j, 14);
+      if (tracer && j > 0) ATTN_TRACE(j, 14);
       tmem_ld_wait(a);  // no load is left in flight
       tmem_ld_wait(b);
       float l0, l1;
       unpack_f32x2(lsum, l0, l1);
       sts_f32(red_sum + (uint32_t)((((j & 3) * 2 + half) * QT + row) * 4), l0 + l1);
       tmem_st_wait();
-      if (tracer) ATTN_TRACE(j, 15);
+      if (tracer && j > 0) ATTN_TRACE(j, 15);
     };
     for (int j = wg; j < count; j += 2) {
       const Item it = item_of(geo, item0 + j);
@@ -994,12 +1011,18 @@ __global__ void __launch_bounds__(PP_THREADS, 1)
   }
   tc_fence_before();
   __syncthreads();
-  if (threadIdx.x == 0) ATTN_TRACE(0, 14);
+  if (threadIdx.x == 0) {
+    ATTN_TRACE(0, 14);
+    ATTN_WALL(2);
+  }
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
-  if (threadIdx.x == 0) ATTN_TRACE(0, 15);
+  if (threadIdx.x == 0) {
+    ATTN_TRACE(0, 15);
+    ATTN_WALL(3);
+  }
 }
 
 static int pp_smem_bytes(int n16) {

@@ -39,7 +39,7 @@ def main():
     qp = torch.randn(G * K, D, device=dev).to(dt)
     oc = torch.empty(G * n, D, dtype=dt, device=dev)
     op = torch.empty(G * K, D, dtype=dt, device=dev)
-    trace = torch.zeros(64 * 16, dtype=torch.int64, device=dev)
+    trace = torch.zeros(64 * 16 + 4 * 148 + 64, dtype=torch.int64, device=dev)
     code = _lib.dtype_code(dt)
 
     def run():
@@ -57,14 +57,35 @@ def main():
     print(f"20 back-to-back eager launches: {e0.elapsed_time(e1) / 20 * 1e3:.2f} us per launch")
     lib.rpo_diag_set_attn_trace.argtypes = [C.c_void_p]
     _lib.check(lib.rpo_diag_set_attn_trace(trace.data_ptr()))
-    run()
+    # a CUDA graph of back-to-back launches (as the step is): the stamps are those of the last launch, so the
+    # dependency timing is the steady state and the host's launch cost is out of the picture
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(6):
+            run()
+    g.replay()
     torch.cuda.synchronize()
+    trace.zero_()
+    e0.record()
+    g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"graph of 6 launches: {e0.elapsed_time(e1) / 6 * 1e3:.2f} us per launch")
     _lib.check(lib.rpo_diag_set_attn_trace(None))
-    t = trace.cpu().view(64, 16)
+    wall = trace.cpu()[1024:1024 + 4 * 148].view(148, 4)
+    t = trace.cpu()[:1024].view(64, 16)
     nz = t[t > 0]
     t0 = int(nz.min())
     print(f"kernel entry {int(t[0, 12]) - t0}, prologue done {int(t[0, 13]) - t0}, all roles done {int(t[0, 14]) - t0}, "
           f"tmem released {int(t[0, 15]) - t0} (SM clocks)")
+    w = wall[wall[:, 0] > 0].double()
+    if len(w):  # the two-slot kernel stamps every CTA with the global timer
+        w0 = float(w[:, 0].min())
+        print(f"{len(w)} CTAs, wall clock (us after the first entry): entry {float(w[:, 0].min()) - w0:.2f} .. "
+              f"{(float(w[:, 0].max()) - w0) / 1e3:.2f}; dependency released {(float(w[:, 1].min()) - w0) / 1e3:.2f} .. "
+              f"{(float(w[:, 1].max()) - w0) / 1e3:.2f}; roles done {(float(w[:, 2].min()) - w0) / 1e3:.2f} .. "
+              f"{(float(w[:, 2].max()) - w0) / 1e3:.2f}; exit {(float(w[:, 3].min()) - w0) / 1e3:.2f} .. "
+              f"{(float(w[:, 3].max()) - w0) / 1e3:.2f}")
     order = [e for e in ORDER if int(t[1:, e].max()) > 0]  # the two kernels record different sub-phases
     print("tile  " + " ".join(f"{EV[e]:>10s}" for e in order))
     for j in range(64):
