@@ -232,16 +232,6 @@ int rpo_gemm_bias_act(const void *A, int64_t lda, const void *B, int64_t ldb, vo
                       const void *gelu_grad_aux, void *aux_out, int64_t aux_row0, int32_t dtype, int32_t backend,
                       void *stream);
 
-/* The same GEMM with a stream-K workspace: `workspace` is device memory of rpo_gemm_workspace_bytes() bytes,
- * zero-filled once by the caller and then left alone.  With it the CTA-pair tcgen05 kernel may split the K loops
- * of the tiles of an incomplete last wave over all SM pairs (f32 partial sums, added in a fixed order:
- * results do not depend on timing).  Use one workspace per stream, and stream-K on ONE stream at a time. */
-size_t rpo_gemm_workspace_bytes(void);
-int rpo_gemm_bias_act_ws(const void *A, int64_t lda, const void *B, int64_t ldb, void *C, int64_t ldc, int64_t M,
-                         int32_t N, int32_t Kd, const void *bias, int32_t act, const void *residual,
-                         const void *gelu_grad_aux, void *aux_out, int64_t aux_row0, int32_t dtype, int32_t backend,
-                         void *workspace, void *stream);
-
 /* Read-only masked multi-head attention (clip/model.py:186 with the masks of trainers/rpo.py:140-159).
  * G groups (images / classes).  Group g has n_g = ctx_off[g+1]-ctx_off[g] context rows (its keys
  * and values, and -- if do_ctx -- also queries) stored at rows ctx_off[g].. of qkv_ctx [Mc, 3D]

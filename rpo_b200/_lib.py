@@ -19,7 +19,7 @@ ACT_NONE, ACT_QUICKGELU = 0, 1
 SYMBOLS = [
     "rpo_last_error", "rpo_version", "rpo_create", "rpo_destroy", "rpo_device_bytes", "rpo_bind_weights",
     "rpo_set_classes", "rpo_set_image_norm", "rpo_forward", "rpo_backward", "rpo_sgd_step", "rpo_layernorm_fwd", "rpo_layernorm_bwd",
-    "rpo_gemm_bias_act", "rpo_gemm_bias_act_ws", "rpo_gemm_workspace_bytes", "rpo_ro_attention_fwd", "rpo_ro_attention_fwd_dense", "rpo_ro_attention_fwd_dense_supported", "rpo_ro_attention_bwd", "rpo_logits_ce_fwd", "rpo_logits_ce_bwd",
+    "rpo_gemm_bias_act", "rpo_ro_attention_fwd", "rpo_ro_attention_fwd_dense", "rpo_ro_attention_fwd_dense_supported", "rpo_ro_attention_bwd", "rpo_logits_ce_fwd", "rpo_logits_ce_bwd",
     "rpo_debug_fetch", "rpo_launch_count", "rpo_profile_begin", "rpo_profile_end",
     "rpo_bind_text_exchange", "rpo_forward_text", "rpo_forward_image", "rpo_forward_logits", "rpo_backward_logits",
     "rpo_backward_text", "rpo_backward_image", "rpo_forward_image_context", "rpo_forward_image_prompts",
@@ -102,10 +102,6 @@ def load():
     lib.rpo_layernorm_fwd.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp]
     lib.rpo_layernorm_bwd.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, vp]
     lib.rpo_gemm_bias_act.argtypes = [vp, i64, vp, i64, vp, i64, i64, i32, i32, vp, i32, vp, vp, vp, i64, i32, i32, vp]
-    lib.rpo_gemm_bias_act_ws.argtypes = [vp, i64, vp, i64, vp, i64, i64, i32, i32, vp, i32, vp, vp, vp, i64, i32, i32, vp,
-                                         vp]
-    lib.rpo_gemm_workspace_bytes.argtypes = []
-    lib.rpo_gemm_workspace_bytes.restype = C.c_size_t
     lib.rpo_ro_attention_fwd.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
     lib.rpo_ro_attention_fwd_dense.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.rpo_ro_attention_fwd_dense_supported.argtypes = [i32, i32, i32, i32]

@@ -188,12 +188,6 @@ struct Epilogue {
   // operand B is a frozen weight (never written on the step's streams): its first tiles may be
   // fetched before the upstream kernel has finished (programmatic dependent launch)
   int b_frozen;
-  // Stream-K workspace (device, zero-initialised once, >= gemm_streamk_ws_bytes(); nullable).  When given,
-  // the CTA-pair kernel may split the K loops of the step's last partial wave of tiles across all SM pairs;
-  // partial accumulators and ready flags live here.  One workspace per stream: two stream-K kernels running
-  // concurrently on different streams must not share it (and only ONE stream may use stream-K at all --
-  // the finishing CTAs of a tile spin on flags set by CTAs that must become resident).
-  void *sk_ws;
   // Row split of the output (tcgen05 kernels only): rows >= split_row go to c2[(m - split_row) * ldc2 + n] for
   // columns n < ncols2 and are dropped for the other columns.  The vision tower's QKV projection uses it to run
   // over context AND prompt rows in one launch: context rows -> [Mc, 3D] q|k|v, prompt rows -> their q only
@@ -232,7 +226,6 @@ int gemm_simt(const T *A, long long sam, long long sak, const T *B, long long sb
 template <typename T>
 int gemm_tcgen05(const T *A, long long lda, const T *B, long long ldb, T *C, long long ldc, long long M, int N, int Kd,
                  const Epilogue<T> &ep, cudaStream_t st);
-size_t gemm_streamk_ws_bytes();
 bool gemm_tcgen05_supported(int dtype, long long lda, long long ldb, long long ldc, long long M, int N, int Kd,
                             const void *A, const void *B, const void *C);
 

@@ -77,7 +77,6 @@ struct Tower {
   int D = 0, H = 0, layers = 0, K = 0, causal = 0;
   int G = 0, Gmax = 0, max_ctx = 0;
   int uniform_n = 0;  // > 0: every group has exactly this many context rows (vision tower)
-  void *sk_ws = nullptr;  // stream-K workspace of this tower's stream (vision only: see Epilogue::sk_ws)
   long long Mc = 0, Mc_max = 0, Mp_max = 0, Mtot_max = 0;
   int *ctx_off = nullptr;  // device [Gmax+1]
   // per-layer saved activations
@@ -146,13 +145,12 @@ namespace rpo {
 
 // every GEMM of the towers multiplies by a frozen CLIP weight (trainers/rpo.py:258-260)
 template <typename T>
-static Epilogue<T> frozen_ep(void *sk_ws = nullptr) {
+static Epilogue<T> frozen_ep() {
   Epilogue<T> e{};
   // 1: weight tiles of the first ring fill are fetched ahead of the PDL dependency wait; 2 (RPO_GEMM_L2_PREFETCH=1): the
   // rest of the first tile's weight k-blocks is also prefetched into L2
   static const int mode = [] { const char *v = diag_env("RPO_GEMM_L2_PREFETCH"); return (v && v[0] == '1') ? 2 : 1; }();
   e.b_frozen = mode;
-  e.sk_ws = sk_ws;
   return e;
 }
 
@@ -179,7 +177,7 @@ static int tower_forward(RpoHandle *hd, Tower &tw, bool do_ctx, bool do_prompt, 
     T *fcpre = at<T>(tw.fcpre, (long long)l * tw.Mp_max * 4 * D);
     // x = x + attn(ln_1(x))                                             clip/model.py:189
     RPO_TRY(layernorm_fwd<T>(x_in + r0 * D, bw.ln1_w, bw.ln1_b, h + r0 * D, rows, D, st));
-    Epilogue<T> ep = frozen_ep<T>(tw.sk_ws);
+    Epilogue<T> ep = frozen_ep<T>();
     // One launch for the in-projection of context AND prompt rows when both are live and the tcgen05 path takes the
     // shape: the epilogue sends the prompt rows' q third to `qp` and drops their k|v (prompts are never keys or
     // values) -- 8% more MMA work on this GEMM, one ~6 us kernel and one dependency bubble less per block.
@@ -195,13 +193,13 @@ static int tower_forward(RpoHandle *hd, Tower &tw, bool do_ctx, bool do_prompt, 
       RPO_TRY(gemm_dispatch<T>(backend, h, D, (const T *)bw.in_w, D, qkv, 3 * D, Mc + Mp, 3 * D, D, ep, st));
     }
     if (do_ctx && !fused_q) {
-      ep = frozen_ep<T>(tw.sk_ws);
+      ep = frozen_ep<T>();
       ep.bias = (const T *)bw.in_b;
       RPO_TRY(gemm_dispatch<T>(backend, h, D, (const T *)bw.in_w, D, qkv, 3 * D, Mc, 3 * D, D, ep, st));
     }
     if (do_prompt && !fused_q) {
       // prompts are queries only: project with the q third of in_proj (rows 0..D-1)
-      ep = frozen_ep<T>(tw.sk_ws);
+      ep = frozen_ep<T>();
       ep.bias = (const T *)bw.in_b;
       RPO_TRY(gemm_dispatch<T>(backend, h + Mc * D, D, (const T *)bw.in_w, D, qp, D, Mp, D, D, ep, st));
     }
@@ -212,13 +210,13 @@ static int tower_forward(RpoHandle *hd, Tower &tw, bool do_ctx, bool do_prompt, 
     else
       RPO_TRY(ro_attention_fwd<T>(qkv, qp, o, o + Mc * D, tw.ctx_off, tw.G, do_prompt ? tw.K : 0, tw.H, tw.max_ctx,
                                   tw.causal, do_ctx ? 1 : 0, st));
-    ep = frozen_ep<T>(tw.sk_ws);
+    ep = frozen_ep<T>();
     ep.bias = (const T *)bw.out_b;
     ep.residual = x_in + r0 * D;
     RPO_TRY(gemm_dispatch<T>(backend, o + r0 * D, D, (const T *)bw.out_w, D, x_mid + r0 * D, D, rows, D, D, ep, st));
     // x = x + mlp(ln_2(x))                                              clip/model.py:190
     RPO_TRY(layernorm_fwd<T>(x_mid + r0 * D, bw.ln2_w, bw.ln2_b, h + r0 * D, rows, D, st));
-    ep = frozen_ep<T>(tw.sk_ws);
+    ep = frozen_ep<T>();
     ep.bias = (const T *)bw.fc_b;
     ep.act = RPO_ACT_QUICKGELU;
     if (do_prompt) {
@@ -227,7 +225,7 @@ static int tower_forward(RpoHandle *hd, Tower &tw, bool do_ctx, bool do_prompt, 
     }
     RPO_TRY(gemm_dispatch<T>(backend, h + r0 * D, D, (const T *)bw.fc_w, D, fc + r0 * 4 * D, 4 * D, rows, 4 * D, D, ep,
                              st));
-    ep = frozen_ep<T>(tw.sk_ws);
+    ep = frozen_ep<T>();
     ep.bias = (const T *)bw.proj_b;
     ep.residual = x_mid + r0 * D;
     RPO_TRY(gemm_dispatch<T>(backend, fc + r0 * 4 * D, 4 * D, (const T *)bw.proj_w, 4 * D, x_out + r0 * D, D, rows, D,
@@ -252,11 +250,11 @@ static int tower_backward(RpoHandle *hd, Tower &tw, cudaStream_t st) {
     T *qkv = at<T>(tw.qkv, (long long)l * tw.Mc_max * 3 * D);
     T *qp = at<T>(tw.qp, (long long)l * tw.Mp_max * D);
     T *fcpre = at<T>(tw.fcpre, (long long)l * tw.Mp_max * 4 * D);
-    Epilogue<T> ep = frozen_ep<T>(tw.sk_ws);
+    Epilogue<T> ep = frozen_ep<T>();
     // MLP: d gelu-input = (dx . W2) * quickgelu'(pre);  d ln2-out = that . W1
     ep.gelu_grad_aux = fcpre;
     RPO_TRY(gemm_dispatch<T>(backend, dx, D, (const T *)tw.proj_wT[l], D, dpre, 4 * D, Mp, 4 * D, D, ep, st));
-    ep = frozen_ep<T>(tw.sk_ws);
+    ep = frozen_ep<T>();
     RPO_TRY(gemm_dispatch<T>(backend, dpre, 4 * D, (const T *)tw.fc_wT[l], 4 * D, dh, D, Mp, D, 4 * D, ep, st));
     RPO_TRY(layernorm_bwd<T>(dh, x_mid, bw.ln2_w, dx, dx_mid, Mp, D, st));
     // attention: d attn-out = dx_mid . Wo ; dq ; d ln1-out = dq . Wq
@@ -305,7 +303,7 @@ static int image_forward_stage(RpoHandle *hd, const void *image, int image_dtype
   v.Mc = (long long)B * S;
   const long long Mp_v = (long long)B * K;
   RPO_TRY(im2col_patches<T>(image, image_dtype, (T *)hd->patches, B, c.v_res, c.v_patch, hd->pk_pad, hd->norm, st));
-  Epilogue<T> ep = frozen_ep<T>(v.sk_ws);
+  Epilogue<T> ep = frozen_ep<T>();
   const int pk = hd->pk_pad;
   RPO_TRY(gemm_dispatch<T>(backend, (const T *)hd->patches, pk, (const T *)hd->conv_w_eff, pk, (T *)hd->patch_emb, Dv,
                            (long long)B * hd->NP, Dv, pk, ep, st));
@@ -340,7 +338,7 @@ static int image_context_stage(RpoHandle *hd, Tower &v, const void *image, int i
   v.G = B;
   v.Mc = (long long)B * S;
   RPO_TRY(im2col_patches<T>(image, image_dtype, (T *)hd->patches, B, c.v_res, c.v_patch, hd->pk_pad, hd->norm, st));
-  Epilogue<T> ep = frozen_ep<T>(v.sk_ws);
+  Epilogue<T> ep = frozen_ep<T>();
   const int pk = hd->pk_pad;
   RPO_TRY(gemm_dispatch<T>(c.gemm_backend, (const T *)hd->patches, pk, (const T *)hd->conv_w_eff, pk,
                            (T *)hd->patch_emb, Dv, (long long)B * hd->NP, Dv, pk, ep, st));
@@ -739,21 +737,6 @@ int rpo_create(const RpoConfig *cfg, RpoHandle **out) {
     rpo_destroy(h);
     return RPO_ERR_CUDA;
   }
-  if (c.dtype != RPO_F32) {
-    // stream-K workspace of the main (vision) stream; the text tower runs on the side stream and must not
-    // use stream-K (see Epilogue::sk_ws)
-    void *ws = nullptr;
-    const size_t wsb = gemm_streamk_ws_bytes();
-    if (cudaMalloc(&ws, wsb) != cudaSuccess || cudaMemset(ws, 0, wsb) != cudaSuccess) {
-      set_error("could not allocate the stream-K workspace");
-      rpo_destroy(h);
-      return RPO_ERR_CUDA;
-    }
-    h->owned.push_back(ws);
-    h->device_bytes += wsb;
-    // with two image slots the context pass and the prompt chain run on different streams: no stream-K at all
-    if (h->slots == 1) h->vis.sk_ws = ws;
-  }
   *out = h;
   return RPO_OK;
 }
@@ -1061,20 +1044,10 @@ int rpo_layernorm_bwd(const void *dy, const void *x, const float *w, const void 
                                     (cudaStream_t)stream)));
 }
 
-size_t rpo_gemm_workspace_bytes(void) { return gemm_streamk_ws_bytes(); }
-
 int rpo_gemm_bias_act(const void *A, int64_t lda, const void *B, int64_t ldb, void *C, int64_t ldc, int64_t M,
                       int32_t N, int32_t Kd, const void *bias, int32_t act, const void *residual,
                       const void *gelu_grad_aux, void *aux_out, int64_t aux_row0, int32_t dtype, int32_t backend,
                       void *stream) {
-  return rpo_gemm_bias_act_ws(A, lda, B, ldb, C, ldc, M, N, Kd, bias, act, residual, gelu_grad_aux, aux_out, aux_row0,
-                              dtype, backend, nullptr, stream);
-}
-
-int rpo_gemm_bias_act_ws(const void *A, int64_t lda, const void *B, int64_t ldb, void *C, int64_t ldc, int64_t M,
-                         int32_t N, int32_t Kd, const void *bias, int32_t act, const void *residual,
-                         const void *gelu_grad_aux, void *aux_out, int64_t aux_row0, int32_t dtype, int32_t backend,
-                         void *workspace, void *stream) {
   RPO_REQUIRE(A && B && C, "null argument");
   RPO_REQUIRE(backend >= RPO_GEMM_AUTO && backend <= RPO_GEMM_TCGEN05, "backend");
   DISPATCH(dtype, ([&]() -> int {
@@ -1085,7 +1058,6 @@ int rpo_gemm_bias_act_ws(const void *A, int64_t lda, const void *B, int64_t ldb,
              ep.aux_out = (T *)aux_out;
              ep.aux_row0 = aux_row0;
              ep.act = act;
-             ep.sk_ws = workspace;
              // benchmarking aid: treat B as a frozen weight (tiles fetched before the PDL dependency wait), as the
              // towers do.  Only valid when no earlier launch on the stream writes B.
              if (const char *fz = diag_env("RPO_GEMM_ASSUME_FROZEN_B")) ep.b_frozen = fz[0] == '1';

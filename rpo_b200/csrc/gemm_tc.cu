@@ -289,9 +289,6 @@ struct Epi {
   long long pass_stride;  // elements between the rows of consecutive copy-out passes
   const T *src_row;  // residual / gelu' aux: row (etid / CH) of the tile, column chunk (etid % CH)
   T *dst_row;        // C: same position
-  const float *sk_partial = nullptr;  // stream-K: partial accumulators of the following clusters (this CTA's half)
-  int sk_count = 0;
-  size_t sk_stride = 0;  // floats between the slots of consecutive contributors
   long long t_acc = 0;   // clock when the accumulator became available (trace only)
   long long tile_m0 = 0;  // first row / column of the current tile (row-split outputs)
   int tile_n0 = 0;
@@ -321,21 +318,9 @@ struct Epi {
   }
 
   // 32 accumulator columns of this warp's 32 rows -> staging slab.  sc0: first column of the slab inside the tile
-  // stream-K finisher with ONE contributor (the common case): this thread's share of the partial tile for the slab
-  // starting at tile column sc0, fetched ahead of use (8 x 16 bytes: two 16-column halves x four column groups)
-  __device__ __forceinline__ void load_partial(int sc0, int warp, int lane, float4 (&pp)[8]) {  // SK only
-    const int q = warp & 3, half_id = ((warp - 2) % GROUP_WARPS) >> 2;
-    if (half_id >= DRAIN_HALVES) return;
-    const float4 *slot = reinterpret_cast<const float4 *>(sk_partial);
-    const int c0 = sc0 + half_id * 32;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) pp[j] = __ldcg(slot + (size_t)(c0 / 4 + j) * BM + q * 32 + lane);
-  }
-
-  template <bool SK>  // SK: stream-K finisher (adds the partial tiles of the contributing clusters)
   __device__ __forceinline__ void drain(const Epilogue<T> &ep, uint32_t tmem_acc, uint32_t slab, uint32_t bias_s,
-                                        long long m0, int n0, int sc0, int gsc0, long long ldc, int warp, int lane,
-                                        const float4 (&pp)[SK ? 8 : 1]) {  // sc0 / gsc0: TMEM / output column of the slab
+                                        long long m0, int n0, int sc0, int gsc0, long long ldc, int warp,
+                                        int lane) {  // sc0 / gsc0: TMEM / output column of the slab
     const int q = warp & 3;
     const int half_id = ((warp - 2) % GROUP_WARPS) >> 2;
     if (half_id >= DRAIN_HALVES) return;
@@ -349,29 +334,6 @@ struct Epi {
       const int gch = gsc0 + half_id * 32 + hh * 16;    // tile-local output column
       uint32_t acc[16];
       tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)ch, acc);
-      if constexpr (SK) {
-        if (sk_count == 1) {  // prefetched by load_partial
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 v = pp[hh * 4 + j];
-            acc[4 * j] = __float_as_uint(__uint_as_float(acc[4 * j]) + v.x);
-            acc[4 * j + 1] = __float_as_uint(__uint_as_float(acc[4 * j + 1]) + v.y);
-            acc[4 * j + 2] = __float_as_uint(__uint_as_float(acc[4 * j + 2]) + v.z);
-            acc[4 * j + 3] = __float_as_uint(__uint_as_float(acc[4 * j + 3]) + v.w);
-          }
-        }
-        for (int p = 0; p < (sk_count > 1 ? sk_count : 0); ++p) {  // general case: add the partial sums, in cluster order
-          const float4 *slot = reinterpret_cast<const float4 *>(sk_partial + (size_t)p * sk_stride);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 v = __ldcg(slot + (size_t)(ch / 4 + j) * BM + r_loc);
-            acc[4 * j] = __float_as_uint(__uint_as_float(acc[4 * j]) + v.x);
-            acc[4 * j + 1] = __float_as_uint(__uint_as_float(acc[4 * j + 1]) + v.y);
-            acc[4 * j + 2] = __float_as_uint(__uint_as_float(acc[4 * j + 2]) + v.z);
-            acc[4 * j + 3] = __float_as_uint(__uint_as_float(acc[4 * j + 3]) + v.w);
-          }
-        }
-      }
       __align__(16) T2 h[8];
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -445,7 +407,7 @@ struct Epi {
   }
 
   // Whole tile.  `arrive_acc_empty` hands the accumulator back to the MMA warp (called by one lane per warp).
-  template <bool SK, typename Arrive>
+  template <typename Arrive>
   __device__ __forceinline__ void run_tile(const Epilogue<T> &ep, uint32_t tmem_acc, uint32_t cstage, uint32_t bias_s,
                                            T *__restrict__ C, long long m0, int n0, long long M, long long ldc,
                                            uint32_t acc_full_bar, uint32_t acc_full_parity, Arrive arrive_acc_empty) {
@@ -466,12 +428,8 @@ struct Epi {
     src_row = src ? src + pos : nullptr;
     dst_row = C + pos;
     uint4 pre[PASSES];
-    float4 pp[SK ? 8 : 1];
     prefetch(gcol(grp), r0, pre);
     if constexpr (TMA_OUT) use_tma = !src;  // launch-uniform
-    if constexpr (SK) {
-      if (sk_count == 1) load_partial(grp * SLAB, warp, lane, pp);
-    }
     if (GROUPS > 1) named_bar_sync<Thr<BN>::EPI_WARPS * 32>(1);  // the other group has left the previous tile's drains
     for (int i = etid_all; i < BN; i += Thr<BN>::EPI_WARPS * 32) {
       const float bv = ep.bias ? tof<T>(ep.bias[n0 + i]) : 0.f;
@@ -488,10 +446,7 @@ struct Epi {
     for (int i = 0; i < MY_SLABS; ++i, ++slab_seq) {
       const uint32_t slab = cstage + (G::NBUF == 2 ? (slab_seq & 1u) * (uint32_t)G::SLAB_BYTES : 0u);
       const int sl = grp + i * GROUPS;
-      drain<SK>(ep, tmem_acc, slab, bias_s, m0, n0, sl * SLAB, gcol(sl), ldc, warp, lane, pp);
-      if constexpr (SK) {
-        if (sk_count == 1 && i + 1 < MY_SLABS) load_partial((sl + GROUPS) * SLAB, warp, lane, pp);
-      }
+      drain(ep, tmem_acc, slab, bias_s, m0, n0, sl * SLAB, gcol(sl), ldc, warp, lane);
       if (i == MY_SLABS - 1) {  // this warp has read its last accumulator columns
         tc_fence_before();
         __syncwarp();
@@ -682,8 +637,8 @@ __global__ void __launch_bounds__(Thr<BN>::THREADS, (Cfg<BN, LIGHT>::MIN_CTAS))
       const long long m0 = (long long)(tile / num_n_tiles) * BM;
       const int n0 = (tile % num_n_tiles) * BN;
       const uint32_t empty_a = acc_empty(a);
-      epi.template run_tile<false>(ep, tmem_base + (uint32_t)(a * BN), smem_u32(cstage), smem_u32(bias_s), C, m0, n0, M, ldc,
-                                   acc_full(a), (t >> 1) & 1, [&]() { mbar_arrive(empty_a); });
+      epi.run_tile(ep, tmem_base + (uint32_t)(a * BN), smem_u32(cstage), smem_u32(bias_s), C, m0, n0, M, ldc, acc_full(a),
+                   (t >> 1) & 1, [&]() { mbar_arrive(empty_a); });
       if (tr && t == 0 && threadIdx.x == 64) {
         tr[5] = epi.t_acc;
         tr[6] = clock64();
@@ -761,78 +716,28 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, u
 }
 
 // ---- work decomposition of the CTA-pair kernel ---------------------------------------------------------
-// Data-parallel: cluster c owns tiles c, c + NC, ...  Stream-K: the num_tiles * num_kb k-blocks of the whole
-// problem are cut into NC equal contiguous ranges, so every SM pair finishes at the same time instead of
-// 10 pairs running a second full tile while 64 idle (M=7072, N=768: 84 tiles on 74 pairs).  A range is a
-// sequence of segments (tile, k0, k1).  Its first segment may start inside a tile (k0 > 0): the cluster is a
-// CONTRIBUTOR there -- it runs first, writes its f32 partial accumulator to the workspace and raises a flag.
-// The cluster holding k-block 0 of a tile is its FINISHER: it reaches that segment last, adds the partials of
-// the following clusters in cluster order (deterministic) and runs the epilogue.  Contributors never wait, so
-// there is no cyclic dependency; waits are bounded (trap) like every other wait in this file.
+// Data-parallel: cluster c owns whole tiles -- c, c + NC, ... (static) or whatever cluster launch control hands it
+// (TileFeed).  (A stream-K schedule -- the k-blocks of the whole problem cut into NC equal ranges, partial
+// accumulators through a global workspace -- was built in round 1, measured +1.5 % on the K = 3072 GEMM and slower
+// at K = 768, made results depend on the row position, and was removed in round 2: DESIGN.md section 6.)
 struct Seg {
   int tile, k0, k1;
 };
 struct Sched {
-  // stream-K is LANE-ALIGNED: the clusters form groups of `lanes` = num_n_tiles; a group walks a contiguous range of
-  // (m-tile, k-block) units and cluster j of the group computes n-tile j of every unit.  The n-tiles of an m-tile thus
-  // stay in lockstep on neighbouring clusters and share the A tiles through L2 (splitting each tile's K range
-  // independently puts them at different K offsets: every cluster then streams its own copy of A from HBM).
-  int sk, num_tiles, num_kb, nc, lanes, grp, lane_id, groups;
-  long long pos, end, total;
+  int num_kb;
   TileFeed feed;  // whole-tile schedules (static round-robin or cluster launch control)
-  __device__ __forceinline__ void init(int stream_k, int tiles, int kb, int c, int n_clusters, int num_n_tiles,
-                                       int dynamic, uint32_t clc_base, int role) {
-    sk = stream_k; num_tiles = tiles; num_kb = kb; nc = n_clusters;
+  __device__ __forceinline__ void init(int tiles, int kb, int c, int n_clusters, int dynamic, uint32_t clc_base,
+                                       int role) {
+    num_kb = kb;
     feed.init(dynamic, c, n_clusters, tiles, clc_base, 1, role);
-    lanes = num_n_tiles;
-    groups = n_clusters / lanes;
-    grp = c / lanes;
-    lane_id = c % lanes;
-    total = (long long)(tiles / lanes) * kb;
-    if (sk && grp < groups) {
-      pos = total * grp / groups;
-      end = total * (grp + 1) / groups;
-    } else {
-      pos = end = 0;  // clusters beyond the last full group idle in stream-K mode
-    }
   }
   __device__ __forceinline__ bool next(Seg &s) {
-    if (!sk) {
-      if (!feed.next(s.tile)) return false;
-      s.k0 = 0; s.k1 = num_kb;
-      return true;
-    }
-    if (pos >= end) return false;
-    s.tile = (int)(pos / num_kb) * lanes + lane_id;
-    s.k0 = (int)(pos % num_kb);
-    const long long rem = end - pos;
-    s.k1 = rem < (long long)(num_kb - s.k0) ? s.k0 + (int)rem : num_kb;
-    pos += s.k1 - s.k0;
+    if (!feed.next(s.tile)) return false;
+    s.k0 = 0;
+    s.k1 = num_kb;
     return true;
   }
-  // number of later groups that hold the rest [k1, num_kb) of the m-tile whose head this group computes
-  __device__ __forceinline__ int contributors(const Seg &s) const {
-    const long long tile_end = (long long)(s.tile / lanes + 1) * num_kb;
-    long long p = (long long)(s.tile / lanes) * num_kb + s.k1;
-    int cnt = 0;
-    while (p < tile_end) {
-      ++cnt;
-      p = total * (grp + cnt + 1) / groups;
-    }
-    return cnt;
-  }
 };
-static constexpr int SK_MAX_CLUSTERS = 128;
-static constexpr size_t SK_FLAG_BYTES = 1024;                                      // [SK_MAX_CLUSTERS][2] ints
-static constexpr size_t SK_SLOT_BYTES = (size_t)2 * BM * 256 * sizeof(float);      // one cluster's partial, BN <= 256
-__device__ __forceinline__ int ld_acquire_gpu(const int *p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_gpu(int *p, int v) {
-  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 
 template <int BN>
 struct Cfg2 {
@@ -858,7 +763,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
     gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_c2,
                     T *__restrict__ C, long long ldc, long long M, int N, int Kd, Epilogue<T> ep, int num_n_tiles,
-                    int num_tiles, int stream_k) {
+                    int num_tiles, int dyn) {  // dyn: one pair per tile, cluster launch control (see TileFeed)
   using C_ = Cfg2<BN>;
   using T2 = typename Pk<T>::T2;
   extern __shared__ uint8_t smem_raw[];
@@ -867,8 +772,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
   float *bias_s = reinterpret_cast<float *>(cstage + C_::CSTAGE_BYTES);
   uint64_t *bars = reinterpret_cast<uint64_t *>(cstage + C_::CSTAGE_BYTES + C_::BIAS_BYTES);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * C_::STAGES + 4);
-  const int dyn = (stream_k >> 1) & 1;  // one pair per tile, cluster launch control (see TileFeed)
-  stream_k &= 1;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -916,7 +819,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
     // ===== TMA producer (both CTAs; transaction bytes of both land on the leader's barrier) =====
     if (lane == 0) {
       Sched sch;
-      sch.init(stream_k, num_tiles, num_kb, cluster_id, num_clusters, num_n_tiles, dyn, clc_base,
+      sch.init(num_tiles, num_kb, cluster_id, num_clusters, dyn, clc_base,
                rank == 0 ? TileFeed::SCHEDULER : TileFeed::THREAD);
       Seg sg;
       bool have = sch.next(sg);
@@ -956,7 +859,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
     if (rank == 0 && elect_one()) {
       constexpr uint32_t idesc = make_idesc(Num<T>::dtype == RPO_BF16 ? 1 : 0, 2 * BM, C_::MMA_N);
       Sched sch;
-      sch.init(stream_k, num_tiles, num_kb, cluster_id, num_clusters, num_n_tiles, dyn, clc_base, TileFeed::THREAD);
+      sch.init(num_tiles, num_kb, cluster_id, num_clusters, dyn, clc_base, TileFeed::THREAD);
       Seg sg;
       uint32_t it = 0, t = 0;
       for (; sch.next(sg); ++t) {
@@ -986,13 +889,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
     epi.map_c = &map_c;
     epi.map_c2 = &map_c2;
     Sched sch;
-    sch.init(stream_k, num_tiles, num_kb, cluster_id, num_clusters, num_n_tiles, dyn, clc_base, TileFeed::WARP);
+    sch.init(num_tiles, num_kb, cluster_id, num_clusters, dyn, clc_base, TileFeed::WARP);
     Seg sg;
     uint32_t t = 0;
-    int *sk_flags = reinterpret_cast<int *>(ep.sk_ws);
-    float *sk_slots = reinterpret_cast<float *>(reinterpret_cast<char *>(ep.sk_ws) + SK_FLAG_BYTES);
-    const int q = warp & 3, part = (warp - 2) >> 2, etid = threadIdx.x - 64;
-    constexpr int PART_COLS = BN / (Thr<BN>::EPI_WARPS / 4);  // accumulator columns per warp in the stream-K partial
     pdl_wait();
     for (; sch.next(sg); ++t) {
       const int a = C_::ACC_BUFS == 2 ? (int)(t & 1) : 0;
@@ -1001,56 +900,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
       const int n0 = (sg.tile % num_n_tiles) * BN;
       const uint32_t lead_empty = mapa_shared(acc_empty(a), 0);
       const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BN);
-      if (sg.k0 > 0) {
-        // ---- contributor: f32 partial of this CTA's 128 x BN half -> workspace slot of this cluster ----
-        float4 *slot = reinterpret_cast<float4 *>(sk_slots + ((size_t)cluster_id * 2 + rank) * (BM * 256));
-        mbar_wait(acc_full(a), acc_par);
-        tc_fence_after();
-#pragma unroll 1
-        for (int cc = 0; cc < PART_COLS; cc += 32) {
-          const int c0 = part * PART_COLS + cc;
-          uint32_t acc[32];
-          tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
-#pragma unroll
-          for (int j = 0; j < 8; ++j)  // [column group of 4][row]: 32 lanes = 512 contiguous bytes
-            slot[(size_t)(c0 / 4 + j) * BM + q * 32 + lane] =
-                make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]), __uint_as_float(acc[4 * j + 2]),
-                            __uint_as_float(acc[4 * j + 3]));
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(lead_empty);
-        __threadfence();
-        named_bar_sync<Thr<BN>::EPI_WARPS * 32>(1);
-        if (etid == 0) st_release_gpu(sk_flags + cluster_id * 2 + rank, 1);
-        continue;
-      }
-      int n_contrib = 0;
-      if (sg.k1 < num_kb) {
-        // ---- finisher of a split tile: the same lane of the following group(s) holds the rest of its K range ----
-        n_contrib = sch.contributors(sg);
-        if (etid < n_contrib) {
-          const int *f = sk_flags + (cluster_id + (1 + etid) * sch.lanes) * 2 + rank;
-          long long t0 = clock64();
-          while (ld_acquire_gpu(f) == 0) {
-            if (clock64() - t0 > 4000000000LL) __trap();
-          }
-        }
-        named_bar_sync<Thr<BN>::EPI_WARPS * 32>(1);
-      }
-      epi.sk_partial = n_contrib ? sk_slots + ((size_t)(cluster_id + sch.lanes) * 2 + rank) * (BM * 256) : nullptr;
-      epi.sk_count = n_contrib;
-      epi.sk_stride = (size_t)sch.lanes * (2 * BM * 256);
-      if (n_contrib)
-        epi.template run_tile<true>(ep, tmem_acc, smem_u32(cstage), smem_u32(bias_s), C, m0, n0, M, ldc, acc_full(a),
-                                    acc_par, [&]() { mbar_arrive_cluster(lead_empty); });
-      else
-        epi.template run_tile<false>(ep, tmem_acc, smem_u32(cstage), smem_u32(bias_s), C, m0, n0, M, ldc, acc_full(a),
-                                     acc_par, [&]() { mbar_arrive_cluster(lead_empty); });
-      if (n_contrib) {  // all partial reads are done (they precede the last slab barrier): re-arm the flags
-        named_bar_sync<Thr<BN>::EPI_WARPS * 32>(1);
-        if (etid < n_contrib) sk_flags[(cluster_id + (1 + etid) * sch.lanes) * 2 + rank] = 0;
-      }
+      epi.run_tile(ep, tmem_acc, smem_u32(cstage), smem_u32(bias_s), C, m0, n0, M, ldc, acc_full(a), acc_par,
+                   [&]() { mbar_arrive_cluster(lead_empty); });
     }
     epi.finish();
   }
@@ -1139,37 +990,17 @@ static int launch_pair(const T *A, long long lda, const T *B, long long ldb, T *
   const long long num_tiles = ((M + 2 * BM - 1) / (2 * BM)) * num_n_tiles;
   const int pairs = sm_count() / 2;
   int grid = 2 * (int)(num_tiles < pairs ? num_tiles : pairs);
-  // stream-K when the data-parallel schedule would leave > 8% of the SM-pair time idle in its last round and
-  // every cluster still gets at least one whole tile's worth of k-blocks (a tile is then split at most in two)
-  int stream_k = 0;
-  // Opt-in (RPO_GEMM_STREAMK=1): measured on B200 it gains 1.5% on the K=3072 GEMM and loses on the K=768 ones
-  // (the partial-accumulator round trip costs more epilogue time than the ragged wave), and splitting a tile's
-  // K range changes the f32 summation order with the row position, which breaks the bit-exact batch-permutation
-  // property the parity tests check.
-  const char *sk_env = getenv("RPO_GEMM_STREAMK");  // read per call: the parity tests switch it on for one case
-  const bool use_sk = sk_env && sk_env[0] == '1';
-  if (ep.sk_ws && use_sk && num_tiles > pairs && pairs <= SK_MAX_CLUSTERS && num_n_tiles <= pairs) {
-    const long long m_tiles = num_tiles / num_n_tiles, groups = pairs / num_n_tiles;
-    const long long rounds = (num_tiles + pairs - 1) / pairs;
-    // k-block steps per cluster: data-parallel vs lane-aligned stream-K (clusters beyond the last full group idle)
-    const int num_kb = Kd / BK;
-    const double dp = (double)rounds * num_kb, skc = (double)m_tiles * num_kb / (double)groups;
-    // K >= 2048 only: at K = 768 a tile's main loop is shorter than the partial-tile round trip (measured slower)
-    if (m_tiles >= groups && skc < 0.85 * dp && Kd >= 2048) {
-      stream_k = 1;
-      grid = 2 * pairs;
-    }
-  }
   // more tiles than SM pairs: one pair per tile, taken over dynamically by the running pairs (see TileFeed)
-  if (!stream_k && num_tiles > pairs && (dynamic_tiles() & 1)) {
-    stream_k = 2;
+  int dyn = 0;
+  if (num_tiles > pairs && (dynamic_tiles() & 1)) {
+    dyn = 1;
     grid = 2 * (int)num_tiles;
   }
   prof_tag("gemm2 M=%lld N=%d K=%d BN=%d%s%s%s%s", M, N, Kd, BN, ep.bias ? " +bias" : "",
            ep.act == RPO_ACT_QUICKGELU ? " +gelu" : (ep.gelu_grad_aux ? " *gelu'" : ""), ep.residual ? " +res" : "",
-           stream_k & 1 ? " streamK" : (stream_k & 2 ? " dyn" : ""));
+           dyn ? " dyn" : "");
   RPO_CHECK_CUDA(launch_pdl(gemm_tc2_kernel<T, BN>, dim3(grid), dim3(Thr<BN>::THREADS), C_::SMEM_BYTES, st, map_a, map_b, map_c, map_c2, C, ldc, M, N, Kd,
-                            ep, num_n_tiles, (int)num_tiles, stream_k));
+                            ep, num_n_tiles, (int)num_tiles, dyn));
   RPO_LAUNCH_CHECK();
   return RPO_OK;
 }
@@ -1437,8 +1268,6 @@ static int pick_config(long long M, int N, int Kd) {
 }
 
 }  // namespace tc
-
-size_t gemm_streamk_ws_bytes() { return tc::SK_FLAG_BYTES + (size_t)tc::SK_MAX_CLUSTERS * tc::SK_SLOT_BYTES; }
 
 bool gemm_tcgen05_supported(int dtype, long long lda, long long ldb, long long ldc, long long M, int N, int Kd,
                             const void *A, const void *B, const void *C) {

@@ -199,41 +199,6 @@ def test_gemm_dynamic_schedule_bit_identical(prec, monkeypatch):
 
 
 @pytest.mark.parametrize("prec", ["fp16", "bf16"])
-def test_gemm_streamk(prec, monkeypatch):
-    """Stream-K schedule of the CTA-pair kernel (partial accumulators through the workspace) on the shapes whose
-    data-parallel schedule has a ragged last wave; repeated launches reuse the self-resetting flags and must be
-    bit-identical (fixed summation order)."""
-    lib = _lib.load()
-    monkeypatch.setenv("RPO_GEMM_STREAMK", "1")  # opt-in schedule (librpo_b200 reads it at every call)
-    dt = DT[prec]
-    ws = torch.zeros(lib.rpo_gemm_workspace_bytes(), dtype=torch.uint8, device=dev())
-    tol = TOL[prec] * 3
-    for (M, N, Kd, with_res, act) in [(7072, 768, 3072, True, 0), (6304, 2304, 768, False, 0), (7072, 3072, 768, False, 1),
-                                      (7072, 768, 768, True, 0), (19000, 256, 192, False, 0)]:
-        A = randn(M, Kd, dtype=dt, seed=70)
-        B = randn(N, Kd, dtype=dt, seed=71, scale=Kd ** -0.5)
-        bias = randn(N, dtype=dt, seed=72, scale=0.3)
-        res = randn(M, N, dtype=dt, seed=73) if with_res else None
-        outs = []
-        for rep in range(3):
-            Cm = torch.zeros(M, N, dtype=dt, device=dev())
-            _lib.check(lib.rpo_gemm_bias_act_ws(A.data_ptr(), Kd, B.data_ptr(), Kd, Cm.data_ptr(), N, M, N, Kd,
-                                                bias.data_ptr(), act, _lib.ptr(res), None, None, 0, _lib.dtype_code(dt),
-                                                _lib.GEMM_TCGEN05, ws.data_ptr(), st()))
-            torch.cuda.synchronize()
-            outs.append(Cm)
-        ref, _ = ref_gemm(A, B, bias=bias, act=act, residual=res)
-        assert relmax(outs[0], ref) <= tol, (M, N, Kd)
-        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
-        # and identical to the data-parallel schedule up to f32 summation order
-        monkeypatch.setenv("RPO_GEMM_STREAMK", "0")
-        plain, _ = run_gemm(A, B, prec, _lib.GEMM_TCGEN05, bias=bias, act=act, residual=res)
-        monkeypatch.setenv("RPO_GEMM_STREAMK", "1")
-        assert relmax(outs[0], plain) <= TOL[prec]
-    assert int(ws[:1024].to(torch.int32).sum()) == 0  # every flag was re-armed
-
-
-@pytest.mark.parametrize("prec", ["fp16", "bf16"])
 def test_gemm_cluster_splitk_epilogues(prec):
     """Long-K, small-M problems take the cluster split-K kernel (partials reduced through distributed shared
     memory): every epilogue, ragged M, K ranges that do not divide evenly."""

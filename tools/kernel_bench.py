@@ -87,7 +87,6 @@ def bench_kernels(prec="fp16", arch="ViT-B/16", B=32, K=24, C=100, only=("gemm",
     def randn(*shape, scale=1.0):
         return (torch.randn(*shape, generator=g, device=dev) * scale).to(dt)
 
-    ws = torch.zeros(lib.rpo_gemm_workspace_bytes(), dtype=torch.uint8, device=dev)
     for label, M, N, Kd, has_bias, act, has_res, has_aux in (gemm_shapes(arch, B, K, C) if "gemm" in only else []):
         if gemm_labels and label not in gemm_labels:
             continue
@@ -102,11 +101,10 @@ def bench_kernels(prec="fp16", arch="ViT-B/16", B=32, K=24, C=100, only=("gemm",
 
         def fn(i):
             j = i % nbuf
-            _lib.check(lib.rpo_gemm_bias_act_ws(A[j].data_ptr(), Kd, W[j].data_ptr(), Kd, Cm[j].data_ptr(), N, M, N, Kd,
-                                                _lib.ptr(bias), act, _lib.ptr(res[j]) if res else None,
-                                                _lib.ptr(aux[j]) if aux else None, None, 0, code, _lib.GEMM_AUTO,
-                                                ws.data_ptr() if label.startswith("v.") else None,
-                                                _lib.stream_ptr(dev)))
+            _lib.check(lib.rpo_gemm_bias_act(A[j].data_ptr(), Kd, W[j].data_ptr(), Kd, Cm[j].data_ptr(), N, M, N, Kd,
+                                             _lib.ptr(bias), act, _lib.ptr(res[j]) if res else None,
+                                             _lib.ptr(aux[j]) if aux else None, None, 0, code, _lib.GEMM_AUTO,
+                                             _lib.stream_ptr(dev)))
 
         t = timeit(fn, use_graph=use_graph)
         fl = 2.0 * M * N * Kd
