@@ -49,19 +49,19 @@ __device__ __forceinline__ void named_bar_sync(int id) {
 }
 
 // =================================================================================================
-// Tile schedule of the persistent kernels.
-//   static : CTA (or CTA pair) c of a grid of NC takes tiles c, c + NC, ...  Fine while the kernel owns the GPU.
-//   dynamic: the grid has ONE CTA (pair) PER TILE and a running CTA takes over launches that have not started yet
+// Tile schedule of the persistent single-CTA kernel (the CTA-pair kernel is always static).
+//   static : CTA c of a grid of NC takes tiles c, c + NC, ...  Fine while the kernel owns the GPU.
+//   dynamic: the grid has ONE CTA PER TILE and a running CTA takes over launches that have not started yet
 //            through cluster launch control (clusterlaunchcontrol.try_cancel): the hardware hands it the block index
 //            of a cancelled launch, i.e. its tile.  The step runs the text tower on a second stream; its kernels
 //            hold SMs for 5-15 us at a time, and a statically scheduled GEMM whose CTAs start late on those SMs
 //            finishes late by the same amount.  With the dynamic schedule late starters simply take fewer tiles,
 //            and SMs that free up mid-kernel still pick up pending launches.  Which CTA computes a tile does not
 //            change the tile's arithmetic, so results stay bit-identical.
-// Protocol (ring of CLC_SLOTS 16-byte responses): the SCHEDULER -- the TMA producer thread of the (leader) CTA --
+// Protocol (ring of CLC_SLOTS 16-byte responses): the SCHEDULER -- the TMA producer thread of the CTA --
 // requests the tile after the one it is about to load, so the round trip hides behind a whole tile of loads; the
-// response is written (multicast for a pair) into every CTA's ring slot and completes full[slot] there.  Every other
-// role (MMA thread, epilogue warps, the pair's second producer) waits on its CTA's full[slot], decodes the response
+// response is written into the CTA's ring slot and completes full[slot] there.  Every other
+// role (MMA thread, epilogue warps) waits on full[slot], decodes the response
 // and releases the slot on the scheduler's empty[slot].  A failed request ends every role's loop; no request is
 // issued after a failure (undefined by the PTX ISA).
 // =================================================================================================
@@ -70,23 +70,21 @@ static constexpr int CLC_BYTES = CLC_SLOTS * 16 + 2 * CLC_SLOTS * 8;
 __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank);
 struct TileFeed {
   enum { SCHEDULER = 0, THREAD = 1, WARP = 2 };
-  int dyn, tile, stride, limit, pair, role;
+  int dyn, tile, stride, limit, role;
   bool started;
   uint32_t base, rel, nr, nf;
   __device__ __forceinline__ uint32_t resp(uint32_t s) const { return base + 16u * s; }
   __device__ __forceinline__ uint32_t full(uint32_t s) const { return base + 16u * CLC_SLOTS + 8u * s; }
   __device__ __forceinline__ uint32_t empty(uint32_t s) const { return base + 24u * CLC_SLOTS + 8u * s; }
   // `first` = this CTA's (pair's) first tile; static mode continues with first + step, ... < count
-  __device__ __forceinline__ void init(int dynamic, int first, int step, int count, uint32_t clc_base, int is_pair,
-                                       int who) {
-    dyn = dynamic; tile = first; stride = step; limit = count; pair = is_pair; role = who;
+  __device__ __forceinline__ void init(int dynamic, int first, int step, int count, uint32_t clc_base, int who) {
+    dyn = dynamic; tile = first; stride = step; limit = count; role = who;
     started = false;
     base = clc_base;
     nr = nf = 0;
     rel = empty(0);
-    if (is_pair) rel = mapa_shared(rel, 0);
   }
-  // one thread, once: consumers per slot = MMA thread + epilogue warps (+ second producer + its epilogue warps)
+  // one thread, once: consumers per slot = MMA thread + epilogue warps
   __device__ __forceinline__ static void init_barriers(uint32_t clc_base, int consumers) {
     for (int s = 0; s < CLC_SLOTS; ++s) {
       mbar_init(clc_base + 16u * CLC_SLOTS + 8u * s, 1);
@@ -99,22 +97,10 @@ struct TileFeed {
     const uint32_t s = nf % CLC_SLOTS, ph = (nf / CLC_SLOTS) & 1;
     mbar_wait(empty(s), ph ^ 1);
     mbar_arrive_expect_tx(full(s), 16);
-    if (pair) {
-      asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(
-                       mapa_shared(full(s), 1)),
-                   "r"(16u)
-                   : "memory");
-      asm volatile(
-          "clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 "
-          "[%0], [%1];" ::"r"(resp(s)),
-          "r"(full(s))
-          : "memory");
-    } else {
-      asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];" ::"r"(
-                       resp(s)),
-                   "r"(full(s))
-                   : "memory");
-    }
+    asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];" ::"r"(
+                     resp(s)),
+                 "r"(full(s))
+                 : "memory");
     ++nf;
   }
   __device__ __forceinline__ bool next(int &out) {
@@ -155,7 +141,7 @@ struct TileFeed {
         asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(rel + 8u * s) : "memory");
     }
     ++nr;
-    out = (int)(pair ? x >> 1 : x);
+    out = (int)x;
     return ok != 0;
   }
 };
@@ -572,7 +558,7 @@ __global__ void __launch_bounds__(Thr<BN>::THREADS, (Cfg<BN, LIGHT>::MIN_CTAS))
       if (tr) tr[3] = clock64();
       uint32_t it = 0;
       TileFeed feed;
-      feed.init(dyn, blockIdx.x, gridDim.x, num_tiles, clc_base, 0, TileFeed::SCHEDULER);
+      feed.init(dyn, blockIdx.x, gridDim.x, num_tiles, clc_base, TileFeed::SCHEDULER);
       int tile;
       for (bool have = feed.next(tile); have; have = feed.next(tile)) {
         feed.request();
@@ -596,7 +582,7 @@ __global__ void __launch_bounds__(Thr<BN>::THREADS, (Cfg<BN, LIGHT>::MIN_CTAS))
       constexpr uint32_t idesc = make_idesc(Num<T>::dtype == RPO_BF16 ? 1 : 0, BM, BN);
       uint32_t it = 0, t = 0;
       TileFeed feed;
-      feed.init(dyn, blockIdx.x, gridDim.x, num_tiles, clc_base, 0, TileFeed::THREAD);
+      feed.init(dyn, blockIdx.x, gridDim.x, num_tiles, clc_base, TileFeed::THREAD);
       int tile;
       for (bool have = feed.next(tile); have; have = feed.next(tile), ++t) {
         const int a = t & 1;
@@ -630,7 +616,7 @@ __global__ void __launch_bounds__(Thr<BN>::THREADS, (Cfg<BN, LIGHT>::MIN_CTAS))
     uint32_t t = 0;
     pdl_wait();  // residual / aux rows come from upstream kernels; C may still be read by them
     TileFeed feed;
-    feed.init(dyn, blockIdx.x, gridDim.x, num_tiles, clc_base, 0, TileFeed::WARP);
+    feed.init(dyn, blockIdx.x, gridDim.x, num_tiles, clc_base, TileFeed::WARP);
     int tile;
     for (bool have = feed.next(tile); have; have = feed.next(tile), ++t) {
       const int a = t & 1;
@@ -716,26 +702,28 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, u
 }
 
 // ---- work decomposition of the CTA-pair kernel ---------------------------------------------------------
-// Data-parallel: cluster c owns whole tiles -- c, c + NC, ... (static) or whatever cluster launch control hands it
-// (TileFeed).  (A stream-K schedule -- the k-blocks of the whole problem cut into NC equal ranges, partial
+// Data-parallel, static: cluster c owns the whole tiles c, c + NC, ...  (The dynamic schedule of the single-CTA kernel
+// -- TileFeed -- was also built for pairs in round 1, multicast responses and all; measured 0.4 % slower on the step,
+// removed in round 2.  A stream-K schedule -- the k-blocks of the whole problem cut into NC equal ranges, partial
 // accumulators through a global workspace -- was built in round 1, measured +1.5 % on the K = 3072 GEMM and slower
 // at K = 768, made results depend on the row position, and was removed in round 2: DESIGN.md section 6.)
 struct Seg {
   int tile, k0, k1;
 };
 struct Sched {
-  int num_kb;
-  TileFeed feed;  // whole-tile schedules (static round-robin or cluster launch control)
-  __device__ __forceinline__ void init(int tiles, int kb, int c, int n_clusters, int dynamic, uint32_t clc_base,
-                                       int role) {
+  int num_kb, tile, stride, limit;
+  __device__ __forceinline__ void init(int tiles, int kb, int c, int n_clusters) {
     num_kb = kb;
-    feed.init(dynamic, c, n_clusters, tiles, clc_base, 1, role);
+    tile = c - n_clusters;
+    stride = n_clusters;
+    limit = tiles;
   }
   __device__ __forceinline__ bool next(Seg &s) {
-    if (!feed.next(s.tile)) return false;
+    tile += stride;
+    s.tile = tile;
     s.k0 = 0;
     s.k1 = num_kb;
-    return true;
+    return tile < limit;
   }
 };
 
@@ -750,7 +738,7 @@ struct Cfg2 {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int CSTAGE_BYTES = EpiGeo<BN>::CSTAGE_BYTES;
   static constexpr int BIAS_BYTES = BN * 4;
-  static constexpr int BAR_BYTES = 256 + CLC_BYTES;  // pipeline barriers + TMEM slot, then the CLC ring
+  static constexpr int BAR_BYTES = 256;  // pipeline barriers + TMEM slot
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + CSTAGE_BYTES + BIAS_BYTES + BAR_BYTES + 1024;
   static constexpr int TMEM_COLS = ACC_BUFS * BN <= 256 ? 256 : 512;
   static_assert(ACC_BUFS * BN <= 512, "accumulators must fit the tensor memory");
@@ -763,7 +751,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
     gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_c2,
                     T *__restrict__ C, long long ldc, long long M, int N, int Kd, Epilogue<T> ep, int num_n_tiles,
-                    int num_tiles, int dyn) {  // dyn: one pair per tile, cluster launch control (see TileFeed)
+                    int num_tiles) {
   using C_ = Cfg2<BN>;
   using T2 = typename Pk<T>::T2;
   extern __shared__ uint8_t smem_raw[];
@@ -784,7 +772,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
   auto empty_bar = [&](int s) { return bar_base + 8u * (C_::STAGES + s); };
   auto acc_full = [&](int a) { return bar_base + 8u * (2 * C_::STAGES + a); };
   auto acc_empty = [&](int a) { return bar_base + 8u * (2 * C_::STAGES + 2 + a); };
-  const uint32_t clc_base = bar_base + 256;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
@@ -798,8 +785,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
       mbar_init(acc_full(a), 1);
       mbar_init(acc_empty(a), 2 * Thr<BN>::EPI_WARPS);
     }
-    // slot releases: MMA thread + second producer + the epilogue warps of both CTAs
-    TileFeed::init_barriers(clc_base, 2 + 2 * Thr<BN>::EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -819,8 +804,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
     // ===== TMA producer (both CTAs; transaction bytes of both land on the leader's barrier) =====
     if (lane == 0) {
       Sched sch;
-      sch.init(num_tiles, num_kb, cluster_id, num_clusters, dyn, clc_base,
-               rank == 0 ? TileFeed::SCHEDULER : TileFeed::THREAD);
+      sch.init(num_tiles, num_kb, cluster_id, num_clusters);
       Seg sg;
       bool have = sch.next(sg);
       uint32_t pre = 0;
@@ -837,7 +821,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
       pdl_wait();
       uint32_t it = 0;
       for (; have; have = sch.next(sg)) {
-        if (rank == 0) sch.feed.request();
         const int m0 = (sg.tile / num_n_tiles) * (2 * BM) + (int)rank * BM;
         const int n0 = (sg.tile % num_n_tiles) * BN + (int)rank * (BN / 2);
         for (int kb = sg.k0; kb < sg.k1; ++kb, ++it) {
@@ -859,7 +842,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
     if (rank == 0 && elect_one()) {
       constexpr uint32_t idesc = make_idesc(Num<T>::dtype == RPO_BF16 ? 1 : 0, 2 * BM, C_::MMA_N);
       Sched sch;
-      sch.init(num_tiles, num_kb, cluster_id, num_clusters, dyn, clc_base, TileFeed::THREAD);
+      sch.init(num_tiles, num_kb, cluster_id, num_clusters);
       Seg sg;
       uint32_t it = 0, t = 0;
       for (; sch.next(sg); ++t) {
@@ -889,7 +872,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
     epi.map_c = &map_c;
     epi.map_c2 = &map_c2;
     Sched sch;
-    sch.init(num_tiles, num_kb, cluster_id, num_clusters, dyn, clc_base, TileFeed::WARP);
+    sch.init(num_tiles, num_kb, cluster_id, num_clusters);
     Seg sg;
     uint32_t t = 0;
     pdl_wait();
@@ -916,10 +899,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Thr<BN>::THREADS, 1)
 
 // ---- host side ---------------------------------------------------------------------------------
 
-// RPO_GEMM_DYNAMIC: bit 0 = CTA-pair kernel, bit 1 = single-CTA kernel (128 x BN tiles, one CTA per SM).
-// Measured on B200 (same box, whole step): static 3.383 ms, pair only 3.397, single only 3.361, both 3.369 -- alone,
-// a dynamically scheduled kernel is ~2 % slower (tools/ab_dynamic.sh), next to the text tower's stream the 128-wide
-// single-CTA GEMMs gain slightly.  Default 2.
+// RPO_GEMM_DYNAMIC: bit 1 = dynamic tile schedule of the single-CTA kernel (128 x BN tiles, one CTA per SM); default on.
+// Measured on B200 (same box, whole step, round 1): static 3.383 ms, dynamic 3.361 -- alone, a dynamically scheduled
+// kernel is ~2 % slower, next to the text tower's stream the 128-wide single-CTA GEMMs gain slightly.  The variable
+// exists for the test that holds the two schedules bit-identical.
 static int dynamic_tiles() {
   const char *e = getenv("RPO_GEMM_DYNAMIC");  // read per call: the parity tests compare both schedules
   return e ? (int)strtol(e, nullptr, 0) : 2;
@@ -989,18 +972,11 @@ static int launch_pair(const T *A, long long lda, const T *B, long long ldb, T *
   const int num_n_tiles = N / BN;
   const long long num_tiles = ((M + 2 * BM - 1) / (2 * BM)) * num_n_tiles;
   const int pairs = sm_count() / 2;
-  int grid = 2 * (int)(num_tiles < pairs ? num_tiles : pairs);
-  // more tiles than SM pairs: one pair per tile, taken over dynamically by the running pairs (see TileFeed)
-  int dyn = 0;
-  if (num_tiles > pairs && (dynamic_tiles() & 1)) {
-    dyn = 1;
-    grid = 2 * (int)num_tiles;
-  }
-  prof_tag("gemm2 M=%lld N=%d K=%d BN=%d%s%s%s%s", M, N, Kd, BN, ep.bias ? " +bias" : "",
-           ep.act == RPO_ACT_QUICKGELU ? " +gelu" : (ep.gelu_grad_aux ? " *gelu'" : ""), ep.residual ? " +res" : "",
-           dyn ? " dyn" : "");
+  const int grid = 2 * (int)(num_tiles < pairs ? num_tiles : pairs);
+  prof_tag("gemm2 M=%lld N=%d K=%d BN=%d%s%s%s", M, N, Kd, BN, ep.bias ? " +bias" : "",
+           ep.act == RPO_ACT_QUICKGELU ? " +gelu" : (ep.gelu_grad_aux ? " *gelu'" : ""), ep.residual ? " +res" : "");
   RPO_CHECK_CUDA(launch_pdl(gemm_tc2_kernel<T, BN>, dim3(grid), dim3(Thr<BN>::THREADS), C_::SMEM_BYTES, st, map_a, map_b, map_c, map_c2, C, ldc, M, N, Kd,
-                            ep, num_n_tiles, (int)num_tiles, dyn));
+                            ep, num_n_tiles, (int)num_tiles));
   RPO_LAUNCH_CHECK();
   return RPO_OK;
 }
