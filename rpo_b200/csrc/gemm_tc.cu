@@ -422,7 +422,9 @@ struct Epi {
       asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + (uint32_t)(i * 4)), "f"(bv) : "memory");
     }
     mbar_wait(acc_full_bar, acc_full_parity);
+#ifdef RPO_DIAG
     t_acc = clock64();
+#endif
     tc_fence_after();
     named_bar_sync<Thr<BN>::EPI_WARPS * 32>(1);  // bias visible to every epilogue warp
     static_assert(GROUPS == 1, "the alternating staging buffers assume one epilogue warp group");
@@ -483,7 +485,11 @@ __global__ void __launch_bounds__(Thr<BN>::THREADS, (Cfg<BN, LIGHT>::MIN_CTAS))
   using C_ = Cfg<BN, LIGHT>;
   // RPO_GEMM_TRACE (tuning aid): per CTA [globaltimer at entry, clock at entry, after setup, dependency wait passed,
   // first operands landed, accumulator of the first tile complete, first tile written, exit clock, globaltimer at exit]
+#ifdef RPO_DIAG  // phase timestamps (tools/gemm_trace.py): the release kernel carries none of it
   long long *tr = trace ? trace + (size_t)blockIdx.x * 16 : nullptr;
+#else
+  constexpr long long *tr = nullptr;
+#endif
   if (tr && threadIdx.x == 0) {
     unsigned long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
