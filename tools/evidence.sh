@@ -28,9 +28,11 @@ cap gemm_vout gemm_ $KB --only gemm --gemms v.out
 cap gemm_vproj gemm_ $KB --only gemm --gemms v.proj
 cap ln_fwd ln_fwd_kernel $KB --only ln
 cap ln_bwd ln_bwd_kernel $KB --only ln
-for c in 3 4 5; do
-  timeout 600 python bench.py --config $c --no-cpu-baseline > $OUT/bench_config$c.log 2>&1
-done
+if [ -z "$SKIP_BENCH" ]; then  # SKIP_BENCH=1: captures only
+  for c in 3 4 5; do
+    timeout 600 python bench.py --config $c --no-cpu-baseline > $OUT/bench_config$c.log 2>&1
+  done
+fi
 timeout 120 python tools/kernel_bench.py --cublas > $OUT/kernel_bench.txt 2>&1
 timeout 120 python tools/kernel_bench.py --arch ViT-L/14 --prec bf16 --batch 16 --cublas > $OUT/kernel_bench_vitl.txt 2>&1
 ls -la $OUT | tail -40
