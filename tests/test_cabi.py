@@ -26,6 +26,19 @@ def test_header_symbols_exported(lib):
         assert hasattr(lib, name), name
 
 
+def test_release_library_reads_three_environment_variables(lib):
+    """Tuning and fault-injection switches exist only in the diagnostics build (common.cuh::diag_env): the release
+    library must contain no other RPO_* variable names than the three documented ones."""
+    if os.environ.get("RPO_DIAG") == "1":
+        pytest.skip("diagnostics build")
+    blob = open(_lib.LIB_PATH, "rb").read()
+    names = set(m.decode() for m in re.findall(rb"RPO_[A-Z][A-Z0-9_]{3,}(?=\x00)", blob))
+    names -= {n for n in names if n.startswith(("RPO_ERR_", "RPO_OK", "RPO_F", "RPO_BF", "RPO_U8", "RPO_ACT_", "RPO_GEMM_AUTO",
+                                                 "RPO_GEMM_SIMT", "RPO_GEMM_TCGEN05", "RPO_PEER_", "RPO_REQUIRE", "RPO_CHECK_",
+                                                 "RPO_TRY", "RPO_LAUNCH_"))}
+    assert names == {"RPO_NO_PDL", "RPO_SINGLE_STREAM", "RPO_GEMM_DYNAMIC"}, names
+
+
 def test_version_and_errors(lib):
     assert lib.rpo_version() >= 100
     h = C.c_void_p()
