@@ -499,12 +499,14 @@ class Job:
             ticket = up.submit(pool_pin[0], labels_pin[0])
             last = 0.0
             for i in range(n):
-                nxt = up.submit(pool_pin[(i + 1) % self.pool_n], labels_pin[(i + 1) % self.pool_n]) if i + 1 < n else None
                 img, lab = up.acquire(ticket)
                 r.image.copy_(img, non_blocking=True)
                 r.label.copy_(lab, non_blocking=True)
                 up.release(ticket)
                 r.step()
+                # the next batch's upload is enqueued once this step is on its way (copy stream, other slot): it
+                # overlaps the step as before, and its host cost no longer sits between the sync and the launch
+                nxt = up.submit(pool_pin[(i + 1) % self.pool_n], labels_pin[(i + 1) % self.pool_n]) if i + 1 < n else None
                 loss_host.copy_(r.loss.view(1), non_blocking=True)
                 cur.synchronize()  # the reference reads loss.item() every step (trainers/rpo.py:311)
                 last = float(loss_host[0])
