@@ -1224,8 +1224,10 @@ static int pick_config(long long M, int N, int Kd) {
     // (N = 768 -- out-proj, c_proj, patch embedding: 84 tiles of 256 x 256 are 2 rounds on 74 SM pairs, the second 14 %
     // full.  256 x 384 tiles (ONE round, single accumulator) were built and measured slower -- out-proj 17.1 -> 18.9 us,
     // c_proj 39.1 -> 41.0, step 3.27 -> 3.51 ms -- and removed: profiles/r01_gemm_config_sweep.txt.)
-    // (graph-timed re-sweep of round 2, profiles/r02_gemm_config_sweep_vitb16.txt: c_proj -- N = 768, K = 3072 -- takes
-    // 32.4 us on 256 x 192 pair tiles, 112 tiles = 1.5 rounds, against 36.5 us on 256 x 256)
+    // (graph-timed re-sweeps of round 2, profiles/r02_gemm_config_sweep_vitb16.txt: N = 768 on 256 x 192 pair tiles is
+    // 112 tiles = 1.5 rounds -- c_proj (K = 3072) 32.3 us against 36.6 on 256 x 256.  Out-proj (K = 768) alone is also
+    // faster there, 14.5 us against 15.8 on 128 x 128, but inside the step, next to the text tower's stream, the
+    // dynamically scheduled 128 x 128 kernel wins: 2.915 ms against 2.92 - 2.94 on the same box -- so K >= 2048 only.)
     if (N % 192 == 0 && N < 2048 && Kd >= 2048) return CFG_P192;
     if (N % 256 == 0 && (N >= 2048 || Kd >= 2048)) return CFG_P256;
     if (N % 128 == 0) return CFG_S128;
