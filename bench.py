@@ -11,7 +11,8 @@ re-launches itself under torch.distributed.run.  Rank 0 prints ONE JSON line.
 
 What the line holds (N = 1): `value` = device-resident throughput of the step (inputs in HBM); `e2e` = the same
 through the host API with every batch uploaded from pinned host memory (uint8 pixels, rpo_b200.input_pipeline)
-and the loss read back every step; `trainer_path` = the same through rpo_b200.trainer.RPO.forward_backward (the
+and every step's loss copied back and read by the host while the next step runs (`e2e_sync_loss`: the host blocking on
+it in the same step); `trainer_path` = the same through rpo_b200.trainer.RPO.forward_backward (the
 drop-in the reference's train.py reaches); `roofline` (masked attention), `roofline_gemm`, `roofline_kernels`;
 `gpu_eager_baseline` (the oracle = the reference's op sequence, fp16 torch eager on this GPU; configs 2 and 4);
 `cpu_baseline`.  N > 1: `value` = plain data parallelism (the algorithm N = 1 runs: like with like),
@@ -423,6 +424,7 @@ class Job:
         self.pool = [synth.make_images(B, res, seed=1234 + 97 * rank + i) for i in range(self.pool_n)]
         self.labels = [((torch.arange(B) + i + rank) % C).to(torch.int64) for i in range(self.pool_n)]
         self.runner = self._runner(torch.float32)
+        self._runner_u8 = None
         self.tp0 = self.model.prompt_learner.text_prompt.data.clone()
         self.ip0 = self.model.prompt_learner.img_prompt.data.clone()
 
@@ -479,12 +481,20 @@ class Job:
         self.barrier()
         return e0.elapsed_time(e1) * 1e-3, float(r.loss.item())
 
-    def time_e2e(self, steps, warmup, image_dtype):
+    def time_e2e(self, steps, warmup, image_dtype, sync_loss=False):
         """end to end through the host API: pinned host -> device upload of every batch (BatchUploader: copy stream,
-        two slots) inside the timed region, loss read back to the host and synchronised every step"""
+        two slots) and a device -> host copy of every step's loss, both inside the timed region.  The host reads each
+        loss value when the NEXT step is on its way (what rpo_b200.trainer.RPO.forward_backward does by default: the
+        value feeds a running average for the log line, trainers/rpo.py:311-313); `sync_loss` = block on it in the
+        same step, as a literal `loss.item()` does."""
         torch = self.torch
         from rpo_b200.input_pipeline import BatchUploader
-        r = self.runner if image_dtype == torch.float32 else self._runner(image_dtype)
+        if image_dtype == torch.float32:
+            r = self.runner
+        else:
+            if self._runner_u8 is None:
+                self._runner_u8 = self._runner(image_dtype)
+            r = self._runner_u8
         self.reset(r)
         if image_dtype == torch.uint8:
             pool_pin = [self._u8(i).pin_memory() for i in range(self.pool_n)]
@@ -492,12 +502,13 @@ class Job:
             pool_pin = [p.pin_memory() for p in self.pool]
         labels_pin = [l.pin_memory() for l in self.labels]
         up = BatchUploader(self.dev, self.B, self.arch.image_resolution, image_dtype)
-        loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        landed = [torch.cuda.Event(), torch.cuda.Event()]
         cur = torch.cuda.current_stream()
 
         def run(n):
             ticket = up.submit(pool_pin[0], labels_pin[0])
-            last = 0.0
+            seen = []
             for i in range(n):
                 img, lab = up.acquire(ticket)
                 r.image.copy_(img, non_blocking=True)
@@ -507,11 +518,18 @@ class Job:
                 # the next batch's upload is enqueued once this step is on its way (copy stream, other slot): it
                 # overlaps the step as before, and its host cost no longer sits between the sync and the launch
                 nxt = up.submit(pool_pin[(i + 1) % self.pool_n], labels_pin[(i + 1) % self.pool_n]) if i + 1 < n else None
-                loss_host.copy_(r.loss.view(1), non_blocking=True)
-                cur.synchronize()  # the reference reads loss.item() every step (trainers/rpo.py:311)
-                last = float(loss_host[0])
+                loss_host[i & 1:(i & 1) + 1].copy_(r.loss.view(1), non_blocking=True)
+                landed[i & 1].record(cur)
+                j = i if sync_loss else i - 1  # the step whose loss the host reads now
+                if j >= 0:
+                    landed[j & 1].synchronize()
+                    seen.append(float(loss_host[j & 1]))
                 ticket = nxt
-            return last
+            if not sync_loss and n > 0:
+                landed[(n - 1) & 1].synchronize()
+                seen.append(float(loss_host[(n - 1) & 1]))
+            assert len(seen) == n  # every step's loss reached the host inside the timed region
+            return seen[-1] if seen else 0.0
 
         run(max(3, warmup))
         self.barrier()
@@ -555,7 +573,7 @@ class Job:
         return e0.elapsed_time(e1) * 1e-3
 
     def close(self):
-        self.runner = None
+        self.runner = self._runner_u8 = None
         self.model._engine = None
         self.model = None
         gc.collect()
@@ -576,14 +594,15 @@ def measure(workload, world, rank, dev, pg, shard_text, steps, warmup, e2e=True,
     import torch
     job = Job(workload, world, rank, dev, pg, shard_text, use_graph)
     t_dev, loss = job.time_device(steps, warmup)
-    t_e2e = t_e2e32 = t_tr = None
+    t_e2e = t_e2e_sync = t_e2e32 = t_tr = None
     h2d = 0
     if e2e:
         t_e2e, h2d = job.time_e2e(steps, warmup, torch.uint8)
+        t_e2e_sync, _ = job.time_e2e(steps, warmup, torch.uint8, sync_loss=True)
         t_e2e32, h2d32 = job.time_e2e(steps, warmup, torch.float32)
     if trainer:
         t_tr = job.time_trainer(steps, warmup)
-    t_dev, t_e2e, t_e2e32, t_tr = max_over_ranks([t_dev, t_e2e, t_e2e32, t_tr], world, dev)
+    t_dev, t_e2e, t_e2e_sync, t_e2e32, t_tr = max_over_ranks([t_dev, t_e2e, t_e2e_sync, t_e2e32, t_tr], world, dev)
     imgs = workload["batch_per_gpu"] * world * steps
     out = {"value": imgs / t_dev, "ms_per_step": t_dev / steps * 1e3, "images_per_sec_per_gpu": imgs / t_dev / world,
            "loss_after": loss, "collectives": job.runner.collectives,
@@ -595,11 +614,16 @@ def measure(workload, world, rank, dev, pg, shard_text, steps, warmup, e2e=True,
         out["e2e"] = {"value": imgs / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                       "ms_per_step": t_e2e / steps * 1e3,
                       "note": "pinned uint8 pixels + labels uploaded every step through rpo_b200.input_pipeline.BatchUploader "
-                              "(copy stream, two slots), ToTensor + Normalize inside the patch-extraction kernel, loss read "
-                              "back and synchronised every step"}
+                              "(copy stream, two slots), ToTensor + Normalize inside the patch-extraction kernel; every "
+                              "step's loss copied to pinned host memory and read by the host while the next step runs "
+                              "(the default of rpo_b200.trainer.RPO.forward_backward), the last one before the clock stops"}
+        out["e2e_sync_loss"] = {"value": imgs / t_e2e_sync, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                                "d2h_bytes_per_step": 4, "ms_per_step": t_e2e_sync / steps * 1e3,
+                                "note": "same, the host blocking on every step's loss before it enqueues the next step "
+                                        "(a literal loss.item(), trainers/rpo.py:311; RPO_B200_SYNC_LOSS=1 in the trainer)"}
         out["e2e_float32_upload"] = {"value": imgs / t_e2e32, "unit": UNIT, "h2d_bytes_per_step": h2d32,
                                      "d2h_bytes_per_step": 4, "ms_per_step": t_e2e32 / steps * 1e3,
-                                     "note": "same, with host-normalised float32 images (what the reference's transform "
+                                     "note": "as e2e, with host-normalised float32 images (what the reference's transform "
                                              "pipeline hands over)"}
     if t_tr is not None:
         out["trainer_path"] = {"value": imgs / t_tr, "unit": UNIT, "ms_per_step": t_tr / steps * 1e3,
@@ -660,7 +684,8 @@ def main_own(args):
             },
             "images_per_sec_per_gpu": main["images_per_sec_per_gpu"],
             "clocks": clocks,
-            "e2e": main["e2e"], "e2e_float32_upload": main["e2e_float32_upload"],
+            "e2e": main["e2e"], "e2e_sync_loss": main["e2e_sync_loss"],
+            "e2e_float32_upload": main["e2e_float32_upload"],
             "gpu_launches": main["gpu_launches_per_step"] * args.steps,
             "gpu_launches_per_step": main["gpu_launches_per_step"],
             "loss_after": main["loss_after"],

@@ -9,25 +9,23 @@ static constexpr int LN_WARPS = 8;
 static constexpr float LN_EPS = 1e-5f;
 
 // Loads one row (D elements of T) spread over a warp into registers as f32.
-// Lane l owns vectors l, l+32, ... ; MAXV vectors of VEC elements each (D <= 32*MAXV*VEC = 1024).
-template <typename T, int MAXV>
-__device__ __forceinline__ void load_row(const T *row, int nv, int lane, float (&vals)[MAXV * Vec16<T>::N]) {
+// Lane l owns vectors l, l+32, ... ; NV vectors of VEC elements each (D <= 32*NV*VEC).
+template <typename T, int NV>
+__device__ __forceinline__ void load_row(const T *row, int nv, int lane, float (&vals)[NV * Vec16<T>::N]) {
   constexpr int VEC = Vec16<T>::N;
+  Vec16<T> v[NV];
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    int vi = lane + 32 * i;
-    if (vi < nv) {
-      Vec16<T> v = ld16(row + (size_t)vi * VEC);
+  for (int i = 0; i < NV; ++i)  // all loads of the row in flight before the first conversion
+    if (lane + 32 * i < nv) v[i] = ld16(row + (size_t)(lane + 32 * i) * VEC);
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) vals[i * VEC + e] = tof<T>(v.v[e]);
-    } else {
+  for (int i = 0; i < NV; ++i) {
+    bool in = lane + 32 * i < nv;
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) vals[i * VEC + e] = 0.f;
-    }
+    for (int e = 0; e < VEC; ++e) vals[i * VEC + e] = in ? tof<T>(v[i].v[e]) : 0.f;
   }
 }
 
-// N consecutive f32 parameters (LayerNorm affine) with 16-byte loads; p is 16-byte aligned
+// N consecutive f32 parameters with 16-byte loads; p is 16-byte aligned
 template <int N>
 __device__ __forceinline__ void load_f32(const float *__restrict__ p, float (&out)[N]) {
 #pragma unroll
@@ -40,17 +38,42 @@ __device__ __forceinline__ void load_f32(const float *__restrict__ p, float (&ou
   }
 }
 
-template <typename T, int MAXV>
-__device__ __forceinline__ void row_stats(const float (&vals)[MAXV * Vec16<T>::N], int nv, int lane, int D,
+// LayerNorm affine parameters staged in shared memory, 16-byte piece j of vector vi at [j * nv + vi] (consecutive
+// lanes read consecutive float4: conflict-free).  They are frozen CLIP weights, written by no kernel of the step, so
+// the block copies them BEFORE pdl_wait(): the copy overlaps the tail of the upstream kernel, and afterwards nobody
+// holds them in registers across the row reductions (the f32 registers of w and b were what capped the old kernel
+// at 16 warps per SM).
+template <int VEC>
+__device__ __forceinline__ void stage_param(const float *__restrict__ p, float4 *sp, int nv) {
+  constexpr int Q = VEC / 4;
+  for (int i = threadIdx.x; i < nv * Q; i += blockDim.x) {
+    int vi = i / Q, j = i % Q;
+    sp[j * nv + vi] = __ldg(reinterpret_cast<const float4 *>(p) + i);
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void read_param(const float4 *sp, int nv, int vi, float (&out)[VEC]) {
+#pragma unroll
+  for (int j = 0; j < VEC / 4; ++j) {
+    float4 v = sp[j * nv + vi];
+    out[4 * j] = v.x;
+    out[4 * j + 1] = v.y;
+    out[4 * j + 2] = v.z;
+    out[4 * j + 3] = v.w;
+  }
+}
+
+template <typename T, int NV>
+__device__ __forceinline__ void row_stats(const float (&vals)[NV * Vec16<T>::N], int nv, int lane, int D,
                                           float &mean, float &rstd) {
   constexpr int VEC = Vec16<T>::N;
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXV * VEC; ++i) s += vals[i];  // padding entries are zero
+  for (int i = 0; i < NV * VEC; ++i) s += vals[i];  // padding entries are zero
   mean = warp_sum(s) / (float)D;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     if (lane + 32 * i < nv) {
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
@@ -63,85 +86,94 @@ __device__ __forceinline__ void row_stats(const float (&vals)[MAXV * Vec16<T>::N
   rstd = 1.0f / sqrtf(var + LN_EPS);
 }
 
-template <typename T>
-__global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const T *__restrict__ x, const float *__restrict__ w,
-                                                               const float *__restrict__ b, T *__restrict__ y,
-                                                               long long rows, int D) {
+// resident blocks per SM the register budget is held to: 4 x 8 warps while a lane owns at most 4 vectors of the row
+// (every width of the path: 512 / 768 / 1024 in 16-bit types), 2 for the wide f32 rows of the unit tests
+constexpr int ln_min_blocks(int NV) { return NV <= 4 ? 4 : 2; }
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(LN_WARPS * 32, ln_min_blocks(NV))
+    ln_fwd_kernel(const T *__restrict__ x, const float *__restrict__ w, const float *__restrict__ b, T *__restrict__ y,
+                  long long rows, int D) {
   constexpr int VEC = Vec16<T>::N;
-  constexpr int MAXV = 32 / VEC;
+  __shared__ float4 sw[1024 / 4], sb[1024 / 4];
   long long row = (long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
+  int nv = D / VEC;
+  stage_param<VEC>(w, sw, nv);
+  stage_param<VEC>(b, sb, nv);
   pdl_wait();
   pdl_trigger();
+  float vals[NV * VEC];
+  if (row < rows) load_row<T, NV>(x + row * D, nv, lane, vals);
+  __syncthreads();  // sw / sb complete (after the row loads are issued)
   if (row >= rows) return;
-  int nv = D / VEC;
-  float vals[MAXV * VEC];
-  load_row<T, MAXV>(x + row * D, nv, lane, vals);
-  // the affine parameters do not depend on the statistics: fetch them now, so that their latency overlaps the two
-  // warp reductions instead of following them (the kernel is one wave of one row per warp: a pure latency chain)
-  float wv[MAXV * VEC], bv[MAXV * VEC];
-#pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    int vi = lane + 32 * i;
-    if (vi < nv) {
-      load_f32<VEC>(w + vi * VEC, *reinterpret_cast<float(*)[VEC]>(&wv[i * VEC]));
-      load_f32<VEC>(b + vi * VEC, *reinterpret_cast<float(*)[VEC]>(&bv[i * VEC]));
-    }
-  }
   float mean, rstd;
-  row_stats<T, MAXV>(vals, nv, lane, D, mean, rstd);
+  row_stats<T, NV>(vals, nv, lane, D, mean, rstd);
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     int vi = lane + 32 * i;
     if (vi < nv) {
+      float wv[VEC], bv[VEC];
+      read_param<VEC>(sw, nv, vi, wv);
+      read_param<VEC>(sb, nv, vi, bv);
       Vec16<T> o;
 #pragma unroll
-      for (int e = 0; e < VEC; ++e)
-        o.v[e] = fromf<T>((vals[i * VEC + e] - mean) * rstd * wv[i * VEC + e] + bv[i * VEC + e]);
+      for (int e = 0; e < VEC; ++e) o.v[e] = fromf<T>((vals[i * VEC + e] - mean) * rstd * wv[e] + bv[e]);
       st16(y + row * D + (size_t)vi * VEC, o);
     }
   }
 }
 
 // dx = dres + rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy * w,  xhat = (x-mean)*rstd
-template <typename T>
-__global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const T *__restrict__ dy, const T *__restrict__ x,
-                                                               const float *__restrict__ w, const T *__restrict__ dres,
-                                                               T *__restrict__ dx, long long rows, int D) {
+template <typename T, int NV>
+__global__ void __launch_bounds__(LN_WARPS * 32, NV <= 3 ? 3 : (NV <= 4 ? 2 : 1))
+    ln_bwd_kernel(const T *__restrict__ dy, const T *__restrict__ x, const float *__restrict__ w,
+                  const T *__restrict__ dres, T *__restrict__ dx, long long rows, int D) {
   constexpr int VEC = Vec16<T>::N;
-  constexpr int MAXV = 32 / VEC;
+  __shared__ float4 sw[1024 / 4];
   long long row = (long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
+  int nv = D / VEC;
+  stage_param<VEC>(w, sw, nv);
   pdl_wait();
   pdl_trigger();
-  if (row >= rows) return;
-  int nv = D / VEC;
-  float xv[MAXV * VEC], gv[MAXV * VEC];
-  load_row<T, MAXV>(x + row * D, nv, lane, xv);
-  load_row<T, MAXV>(dy + row * D, nv, lane, gv);
-  // g = dy * w does not depend on the statistics: form it while the row loads / reductions are in flight
+  float xv[NV * VEC], gv[NV * VEC];
+  Vec16<T> r[NV];
+  if (row < rows) {
+    load_row<T, NV>(x + row * D, nv, lane, xv);
+    load_row<T, NV>(dy + row * D, nv, lane, gv);
+    // the residual gradient is needed last but depends on nothing: its load goes out with the others instead of
+    // adding one more memory round trip after the four reductions (the prompt-row launches are latency chains)
+    if (dres) {
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
+      for (int i = 0; i < NV; ++i)
+        if (lane + 32 * i < nv) r[i] = ld16(dres + row * D + (size_t)(lane + 32 * i) * VEC);
+    }
+  }
+  __syncthreads();
+  if (row >= rows) return;
+  // g = dy * w does not depend on the statistics
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
     int vi = lane + 32 * i;
     if (vi < nv) {
       float wv[VEC];
-      load_f32<VEC>(w + vi * VEC, wv);
+      read_param<VEC>(sw, nv, vi, wv);
 #pragma unroll
       for (int e = 0; e < VEC; ++e) gv[i * VEC + e] *= wv[e];
     }
   }
   float mean, rstd;
-  row_stats<T, MAXV>(xv, nv, lane, D, mean, rstd);
+  row_stats<T, NV>(xv, nv, lane, D, mean, rstd);
   float sg = 0.f, sgx = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     int vi = lane + 32 * i;
     if (vi < nv) {
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
         float g = gv[i * VEC + e];
         float xh = (xv[i * VEC + e] - mean) * rstd;
-        gv[i * VEC + e] = g;
         xv[i * VEC + e] = xh;
         sg += g;
         sgx += g * xh;
@@ -151,15 +183,14 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const T *__restri
   sg = warp_sum(sg) / (float)D;
   sgx = warp_sum(sgx) / (float)D;
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     int vi = lane + 32 * i;
     if (vi < nv) {
-      Vec16<T> o, r;
-      if (dres) r = ld16(dres + row * D + (size_t)vi * VEC);
+      Vec16<T> o;
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
         float v = rstd * (gv[i * VEC + e] - sg - xv[i * VEC + e] * sgx);
-        if (dres) v += tof<T>(r.v[e]);
+        if (dres) v += tof<T>(r[i].v[e]);
         o.v[e] = fromf<T>(v);
       }
       st16(dx + row * D + (size_t)vi * VEC, o);
@@ -169,14 +200,30 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const T *__restri
 
 static bool ln_shape_ok(int D, size_t esz) { return D > 0 && D <= 1024 && (D * esz) % 16 == 0; }
 
+// vectors of the row per lane, rounded up to an instantiated count
+template <typename T>
+static int ln_vectors_per_lane(int D) {
+  int nv = D / Vec16<T>::N, per = (nv + 31) / 32;
+  return per <= 4 ? per : 8;
+}
+
 template <typename T>
 int layernorm_fwd(const T *x, const float *w, const float *b, T *y, long long rows, int D, cudaStream_t st) {
   RPO_REQUIRE(ln_shape_ok(D, sizeof(T)), "LayerNorm width must be <= 1024 and a multiple of 16 bytes");
   RPO_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)w | (uintptr_t)b) & 15) == 0, "LayerNorm buffers must be 16-byte aligned");
   if (rows <= 0) return RPO_OK;
-  unsigned grid = (unsigned)((rows + LN_WARPS - 1) / LN_WARPS);
+  dim3 grid((unsigned)((rows + LN_WARPS - 1) / LN_WARPS)), block(LN_WARPS * 32);
   prof_tag("ln_fwd rows=%lld D=%d", rows, D);
-  RPO_CHECK_CUDA(launch_pdl(ln_fwd_kernel<T>, dim3(grid), dim3(LN_WARPS * 32), 0, st, x, w, b, y, rows, D));
+  cudaError_t e = cudaErrorInvalidValue;
+  switch (ln_vectors_per_lane<T>(D)) {
+    case 1: e = launch_pdl(ln_fwd_kernel<T, 1>, grid, block, 0, st, x, w, b, y, rows, D); break;
+    case 2: e = launch_pdl(ln_fwd_kernel<T, 2>, grid, block, 0, st, x, w, b, y, rows, D); break;
+    case 3: e = launch_pdl(ln_fwd_kernel<T, 3>, grid, block, 0, st, x, w, b, y, rows, D); break;
+    case 4: e = launch_pdl(ln_fwd_kernel<T, 4>, grid, block, 0, st, x, w, b, y, rows, D); break;
+    default:
+      if constexpr (sizeof(T) == 4) e = launch_pdl(ln_fwd_kernel<T, 8>, grid, block, 0, st, x, w, b, y, rows, D);
+  }
+  RPO_CHECK_CUDA(e);
   RPO_LAUNCH_CHECK();
   return RPO_OK;
 }
@@ -186,9 +233,18 @@ int layernorm_bwd(const T *dy, const T *x, const float *w, const T *dres, T *dx,
   RPO_REQUIRE(ln_shape_ok(D, sizeof(T)), "LayerNorm width must be <= 1024 and a multiple of 16 bytes");
   RPO_REQUIRE((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)dres | (uintptr_t)w) & 15) == 0, "LayerNorm buffers must be 16-byte aligned");
   if (rows <= 0) return RPO_OK;
-  unsigned grid = (unsigned)((rows + LN_WARPS - 1) / LN_WARPS);
+  dim3 grid((unsigned)((rows + LN_WARPS - 1) / LN_WARPS)), block(LN_WARPS * 32);
   prof_tag("ln_bwd rows=%lld D=%d", rows, D);
-  RPO_CHECK_CUDA(launch_pdl(ln_bwd_kernel<T>, dim3(grid), dim3(LN_WARPS * 32), 0, st, dy, x, w, dres, dx, rows, D));
+  cudaError_t e = cudaErrorInvalidValue;
+  switch (ln_vectors_per_lane<T>(D)) {
+    case 1: e = launch_pdl(ln_bwd_kernel<T, 1>, grid, block, 0, st, dy, x, w, dres, dx, rows, D); break;
+    case 2: e = launch_pdl(ln_bwd_kernel<T, 2>, grid, block, 0, st, dy, x, w, dres, dx, rows, D); break;
+    case 3: e = launch_pdl(ln_bwd_kernel<T, 3>, grid, block, 0, st, dy, x, w, dres, dx, rows, D); break;
+    case 4: e = launch_pdl(ln_bwd_kernel<T, 4>, grid, block, 0, st, dy, x, w, dres, dx, rows, D); break;
+    default:
+      if constexpr (sizeof(T) == 4) e = launch_pdl(ln_bwd_kernel<T, 8>, grid, block, 0, st, dy, x, w, dres, dx, rows, D);
+  }
+  RPO_CHECK_CUDA(e);
   RPO_LAUNCH_CHECK();
   return RPO_OK;
 }
