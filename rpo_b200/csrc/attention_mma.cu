@@ -624,12 +624,17 @@ static int launch_fwd_flash(const T *qkv_ctx, const T *q_prompt, T *out_ctx, T *
 template <typename T, int NG>  // NG: 16-key groups per warp (compile-time bound of the fragment arrays)
 __global__ void __launch_bounds__(THREADS)
     ro_attn_bwd_ks(const T *__restrict__ qkv_ctx, const T *__restrict__ q_prompt, const T *__restrict__ o_prompt,
-                   const T *__restrict__ d_out, T *__restrict__ dq, const int *__restrict__ ctx_off, int K, int H) {
+                   const T *__restrict__ d_out, T *__restrict__ dq, const int *__restrict__ ctx_off, int K, int H,
+                   int settled) {
+  // settled (common.cuh, SettledOperands): keys, values and prompt queries date from the forward pass, so their copies
+  // are issued before the dependency wait and land while the upstream GEMM (which produces d_out) is still running
   extern __shared__ __align__(128) uint8_t sm[];
   const int g = blockIdx.y, h = blockIdx.x;
   const int D = H * HD;
-  pdl_wait();
-  pdl_trigger();
+  if (!settled) {
+    pdl_wait();
+    pdl_trigger();
+  }
   const int row0 = ctx_off[g];
   const int n = ctx_off[g + 1] - row0;
   const int n16 = (n + 15) & ~15;
@@ -649,27 +654,69 @@ __global__ void __launch_bounds__(THREADS)
   const uint32_t Ks = smem_u32(sm), Vs = Ks + n16 * ROW_BYTES, Qs = Ks + q_off, dOs = Qs + QT * ROW_BYTES;
   float *red = reinterpret_cast<float *>(sm + q_off + 2 * QT * ROW_BYTES);  // [2][4 shares][QT] max, sum
   const T *kbase = qkv_ctx + (long long)row0 * 3 * D + D + h * HD;
+  // two copy groups: K and Q feed the score pass; V (half of the bytes) is first read by the dP pass two barriers
+  // further down, so its copy stays in flight behind the score pass and the row-maximum / row-sum exchanges
   stage_rows<T>(Ks, kbase, 3LL * D, n, n16);
-  stage_rows<T>(Vs, kbase + D, 3LL * D, n, n16);
   const long long pbase = ((long long)g * K + q_begin) * D + h * HD;
   stage_rows<T>(Qs, q_prompt + pbase, D, rows_here, QT);
-  stage_rows<T>(dOs, d_out + pbase, D, rows_here, QT);
-  cp_async_wait_all();
-  __syncthreads();
+  cp_async_commit();
+  stage_rows<T>(Vs, kbase + D, 3LL * D, n, n16);
+  cp_async_commit();
   const int r_base = mt * 16;
   const bool active = mt < mt_n;  // warp-uniform; inactive warps only take part in the barriers
+  // the attention output rows of delta_r = sum_d dO[r,d] * O[r,d] (two lanes per row, 32 columns each) also date from
+  // the forward pass: fetched here, next to the copies, instead of in a round trip of their own after the barrier
+  const int dr = r_base + (lane >> 1);
+  uint4 ov[4];
+#pragma unroll
+  for (int v = 0; v < 4; ++v) ov[v] = make_uint4(0u, 0u, 0u, 0u);
+  if (settled && active && dr < rows_here) {
+    const T *po = o_prompt + pbase + (long long)dr * D + (lane & 1) * 32;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) ov[v] = __ldg(reinterpret_cast<const uint4 *>(po + v * 8));
+  }
+  if (settled) {
+    pdl_wait();
+    pdl_trigger();
+  } else if (active && dr < rows_here) {
+    const T *po = o_prompt + pbase + (long long)dr * D + (lane & 1) * 32;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) ov[v] = *reinterpret_cast<const uint4 *>(po + v * 8);
+  }
+  // dO (a few KB, the one operand the upstream kernel wrote) through registers: it must not queue behind V's group
+  {
+    constexpr int PER = QT * 8 / THREADS;
+    uint4 dv[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {  // all loads first: one round trip, not PER
+      const int idx = threadIdx.x + i * THREADS, r = idx >> 3, c = idx & 7;
+      dv[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (r < rows_here) dv[i] = *reinterpret_cast<const uint4 *>(d_out + pbase + (long long)r * D + c * 8);
+    }
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int idx = threadIdx.x + i * THREADS, r = idx >> 3, c = idx & 7;
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dOs + swz(r, c)), "r"(dv[i].x), "r"(dv[i].y),
+                   "r"(dv[i].z), "r"(dv[i].w)
+                   : "memory");
+    }
+  }
+  cp_async_wait_pending(1);
+  __syncthreads();
   const int ra = r_base + (lane >> 2), rb = ra + 8;  // this lane's two rows inside the CTA's row block
-  // delta_r = sum_d dO[r,d] * O[r,d]; two lanes per row, 32 columns each
   float delta_a = 0.f, delta_b = 0.f;
   if (active) {
-    const int r = r_base + (lane >> 1);
     float sdl = 0.f;
-    if (r < rows_here) {
-      const T *po = o_prompt + pbase + (long long)r * D + (lane & 1) * 32;
-      const T *pd = d_out + pbase + (long long)r * D + (lane & 1) * 32;
+    if (dr < rows_here) {
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
-        Vec16<T> a = ld16(po + v * 8), b = ld16(pd + v * 8);
+        Vec16<T> a, b;  // dO from the staged tile (the same values the MMA fragments read)
+        *reinterpret_cast<uint4 *>(&a) = ov[v];
+        uint4 bq;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(bq.x), "=r"(bq.y), "=r"(bq.z), "=r"(bq.w)
+                     : "r"(dOs + swz(dr, (lane & 1) * 4 + v)));
+        *reinterpret_cast<uint4 *>(&b) = bq;
 #pragma unroll
         for (int e = 0; e < 8; ++e) sdl += tof<T>(a.v[e]) * tof<T>(b.v[e]);
       }
@@ -755,6 +802,7 @@ __global__ void __launch_bounds__(THREADS)
       red[(4 + ks) * QT + rb] = sb;
     }
   }
+  cp_async_wait_pending(0);  // this thread's share of V has landed; the barrier publishes everybody's
   __syncthreads();
   // dS is handed to the tensor core in the 16-bit dtype; for fp16 it is pre-scaled by 2^8 (exact) so
   // that products of small probabilities and small gradients stay out of the subnormal range
@@ -855,7 +903,7 @@ static int launch_bwd_ks(const T *qkv_ctx, const T *q_prompt, const T *o_prompt,
   dim3 grid(H, G, (K + QT - 1) / QT);
   prof_tag("attn_bwd G=%d H=%d K=%d max_ctx=%d", G, H, K, max_ctx);
   RPO_CHECK_CUDA(launch_pdl(ro_attn_bwd_ks<T, NG>, grid, dim3(THREADS), smem, st, qkv_ctx, q_prompt, o_prompt, d_out, dq,
-                            ctx_off, K, H));
+                            ctx_off, K, H, g_operands_settled ? 1 : 0));
   RPO_LAUNCH_CHECK();
   return RPO_OK;
 }

@@ -78,6 +78,20 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 bool pdl_enabled();
 
+// "Settled operands": the prompt-row backward re-reads tensors the FORWARD pass left behind (context keys / values,
+// prompt queries, the residual stream a LayerNorm normalised).  Inside a step those were written hundreds of launches
+// earlier, with kernels in between that trigger their dependents only after their own dependency wait -- so they are
+// complete before any kernel of the backward chain can even be scheduled, and a backward kernel may fetch them AHEAD of
+// its pdl_wait(), while the upstream kernel is still running (what the GEMMs do with the frozen weights).  Only the
+// engine's backward chain makes that promise (SettledOperands scope around its launches); the unit entry points of the
+// C ABI cannot know who produced their arguments and keep the wait first.
+extern thread_local bool g_operands_settled;
+struct SettledOperands {
+  bool prev;
+  SettledOperands() : prev(g_operands_settled) { g_operands_settled = pdl_enabled(); }
+  ~SettledOperands() { g_operands_settled = prev; }
+};
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                               Args &&...args) {

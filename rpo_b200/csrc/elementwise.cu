@@ -125,33 +125,47 @@ __global__ void __launch_bounds__(LN_WARPS * 32, ln_min_blocks(NV))
 }
 
 // dx = dres + rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy * w,  xhat = (x-mean)*rstd
+// settled (common.cuh, SettledOperands): x is a row the forward pass left behind, so it is loaded and its statistics
+// are reduced BEFORE the dependency wait, while the upstream GEMM still produces dy -- same arithmetic, two of the four
+// reductions and one memory round trip off the chain.
 template <typename T, int NV>
 __global__ void __launch_bounds__(LN_WARPS * 32, NV <= 3 ? 3 : (NV <= 4 ? 2 : 1))
     ln_bwd_kernel(const T *__restrict__ dy, const T *__restrict__ x, const float *__restrict__ w,
-                  const T *__restrict__ dres, T *__restrict__ dx, long long rows, int D) {
+                  const T *__restrict__ dres, T *__restrict__ dx, long long rows, int D, int settled) {
   constexpr int VEC = Vec16<T>::N;
   __shared__ float4 sw[1024 / 4];
-  long long row = (long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
-  int lane = threadIdx.x & 31;
-  int nv = D / VEC;
+  const long long row = (long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int nv = D / VEC;
+  const bool live = row < rows;  // warp-uniform
   stage_param<VEC>(w, sw, nv);
-  pdl_wait();
-  pdl_trigger();
   float xv[NV * VEC], gv[NV * VEC];
+  float mean = 0.f, rstd = 0.f;
+  if (settled) {
+    if (live) {
+      load_row<T, NV>(x + row * D, nv, lane, xv);
+      row_stats<T, NV>(xv, nv, lane, D, mean, rstd);
+    }
+    pdl_wait();
+    pdl_trigger();
+  } else {
+    pdl_wait();
+    pdl_trigger();
+    if (live) load_row<T, NV>(x + row * D, nv, lane, xv);
+  }
   Vec16<T> r[NV];
-  if (row < rows) {
-    load_row<T, NV>(x + row * D, nv, lane, xv);
+  if (live) {
     load_row<T, NV>(dy + row * D, nv, lane, gv);
     // the residual gradient is needed last but depends on nothing: its load goes out with the others instead of
-    // adding one more memory round trip after the four reductions (the prompt-row launches are latency chains)
+    // adding one more memory round trip after the reductions (the prompt-row launches are latency chains)
     if (dres) {
 #pragma unroll
       for (int i = 0; i < NV; ++i)
         if (lane + 32 * i < nv) r[i] = ld16(dres + row * D + (size_t)(lane + 32 * i) * VEC);
     }
   }
-  __syncthreads();
-  if (row >= rows) return;
+  __syncthreads();  // sw complete
+  if (!live) return;
   // g = dy * w does not depend on the statistics
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -163,8 +177,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, NV <= 3 ? 3 : (NV <= 4 ? 2 : 1)
       for (int e = 0; e < VEC; ++e) gv[i * VEC + e] *= wv[e];
     }
   }
-  float mean, rstd;
-  row_stats<T, NV>(xv, nv, lane, D, mean, rstd);
+  if (!settled) row_stats<T, NV>(xv, nv, lane, D, mean, rstd);
   float sg = 0.f, sgx = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -236,13 +249,15 @@ int layernorm_bwd(const T *dy, const T *x, const float *w, const T *dres, T *dx,
   dim3 grid((unsigned)((rows + LN_WARPS - 1) / LN_WARPS)), block(LN_WARPS * 32);
   prof_tag("ln_bwd rows=%lld D=%d", rows, D);
   cudaError_t e = cudaErrorInvalidValue;
+  const int settled = g_operands_settled ? 1 : 0;
   switch (ln_vectors_per_lane<T>(D)) {
-    case 1: e = launch_pdl(ln_bwd_kernel<T, 1>, grid, block, 0, st, dy, x, w, dres, dx, rows, D); break;
-    case 2: e = launch_pdl(ln_bwd_kernel<T, 2>, grid, block, 0, st, dy, x, w, dres, dx, rows, D); break;
-    case 3: e = launch_pdl(ln_bwd_kernel<T, 3>, grid, block, 0, st, dy, x, w, dres, dx, rows, D); break;
-    case 4: e = launch_pdl(ln_bwd_kernel<T, 4>, grid, block, 0, st, dy, x, w, dres, dx, rows, D); break;
+    case 1: e = launch_pdl(ln_bwd_kernel<T, 1>, grid, block, 0, st, dy, x, w, dres, dx, rows, D, settled); break;
+    case 2: e = launch_pdl(ln_bwd_kernel<T, 2>, grid, block, 0, st, dy, x, w, dres, dx, rows, D, settled); break;
+    case 3: e = launch_pdl(ln_bwd_kernel<T, 3>, grid, block, 0, st, dy, x, w, dres, dx, rows, D, settled); break;
+    case 4: e = launch_pdl(ln_bwd_kernel<T, 4>, grid, block, 0, st, dy, x, w, dres, dx, rows, D, settled); break;
     default:
-      if constexpr (sizeof(T) == 4) e = launch_pdl(ln_bwd_kernel<T, 8>, grid, block, 0, st, dy, x, w, dres, dx, rows, D);
+      if constexpr (sizeof(T) == 4)
+        e = launch_pdl(ln_bwd_kernel<T, 8>, grid, block, 0, st, dy, x, w, dres, dx, rows, D, settled);
   }
   RPO_CHECK_CUDA(e);
   RPO_LAUNCH_CHECK();

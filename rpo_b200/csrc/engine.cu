@@ -24,6 +24,7 @@ namespace rpo {
 
 thread_local std::string g_last_error;
 thread_local int64_t g_launch_count = 0;
+thread_local bool g_operands_settled = false;
 void set_error(const std::string &msg) { g_last_error = msg; }
 bool pdl_enabled() {
   static const bool on = [] {
@@ -244,6 +245,8 @@ static int tower_backward(RpoHandle *hd, Tower &tw, cudaStream_t st) {
   const long long xs = tw.Mtot_max * D;
   T *dx = (T *)tw.dx, *dx_mid = (T *)tw.dx_mid, *dh = (T *)tw.dh, *dpre = (T *)tw.dpre, *dao = (T *)tw.dao,
     *dq = (T *)tw.dq;
+  // x_in / x_mid / qkv / qp / o of every block date from the forward pass (the logit stage lies in between)
+  SettledOperands settled;
   for (int l = tw.layers - 1; l >= 0; --l) {
     const RpoBlockWeights &bw = tw.blocks[l];
     T *x_in = at<T>(tw.x_in, l * xs) + Mc * D, *x_mid = at<T>(tw.x_mid, l * xs) + Mc * D;
