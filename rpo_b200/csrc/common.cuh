@@ -80,7 +80,8 @@ bool pdl_enabled();
 
 // "Settled operands": the prompt-row backward re-reads tensors the FORWARD pass left behind (context keys / values,
 // prompt queries, the residual stream a LayerNorm normalised).  Inside a step those were written hundreds of launches
-// earlier, with kernels in between that trigger their dependents only after their own dependency wait -- so they are
+// earlier, with the logit stage in between -- plain launches (full stream-order dependencies), joined with the text
+// stream by events -- so they are
 // complete before any kernel of the backward chain can even be scheduled, and a backward kernel may fetch them AHEAD of
 // its pdl_wait(), while the upstream kernel is still running (what the GEMMs do with the frozen weights).  Only the
 // engine's backward chain makes that promise (SettledOperands scope around its launches); the unit entry points of the
