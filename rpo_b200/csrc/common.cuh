@@ -80,9 +80,10 @@ bool pdl_enabled();
 
 // "Settled operands": the prompt-row backward re-reads tensors the FORWARD pass left behind (context keys / values,
 // prompt queries, the residual stream a LayerNorm normalised).  Inside a step those were written hundreds of launches
-// earlier, with the logit stage in between -- plain launches (full stream-order dependencies), joined with the text
-// stream by events -- so they are
-// complete before any kernel of the backward chain can even be scheduled, and a backward kernel may fetch them AHEAD of
+// earlier; every backward stage opens with a head GEMM and a LayerNorm backward that triggers its dependents only
+// after its own wait (so nothing behind it is scheduled before the head GEMM -- and with it everything older on the
+// stream -- has completed), and the logit stage in between consists of plain launches.  The tensors are therefore
+// complete before any kernel of tower_backward can even be scheduled, and such a kernel may fetch them AHEAD of
 // its pdl_wait(), while the upstream kernel is still running (what the GEMMs do with the frozen weights).  Only the
 // engine's backward chain makes that promise (SettledOperands scope around its launches); the unit entry points of the
 // C ABI cannot know who produced their arguments and keep the wait first.
