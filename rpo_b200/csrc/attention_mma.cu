@@ -274,12 +274,16 @@ __global__ void __launch_bounds__(THREADS)
 template <typename T, int NT>
 __global__ void __launch_bounds__(THREADS)
     ro_attn_bwd_mma(const T *__restrict__ qkv_ctx, const T *__restrict__ q_prompt, const T *__restrict__ o_prompt,
-                    const T *__restrict__ d_out, T *__restrict__ dq, const int *__restrict__ ctx_off, int K, int H) {
+                    const T *__restrict__ d_out, T *__restrict__ dq, const int *__restrict__ ctx_off, int K, int H,
+                    int settled) {
+  // settled: see ro_attn_bwd_ks -- K, V, Q and the attention output rows are fetched ahead of the dependency wait
   extern __shared__ __align__(128) uint8_t sm[];
   const int g = blockIdx.y, h = blockIdx.x;
   const int D = H * HD;
-  pdl_wait();
-  pdl_trigger();
+  if (!settled) {
+    pdl_wait();
+    pdl_trigger();
+  }
   const int row0 = ctx_off[g];
   const int n = ctx_off[g + 1] - row0;
   const int n16 = (n + 15) & ~15;
@@ -292,23 +296,43 @@ __global__ void __launch_bounds__(THREADS)
   const long long pbase = ((long long)g * K + q_begin) * D + h * HD;
   const int rows_here = min(QT, K - q_begin);
   stage_rows<T>(Qs, q_prompt + pbase, D, rows_here, QT);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r_base = warp * 16;
+  // attention output rows of delta_r = sum_d dO[r,d] * O[r,d] (two lanes per row, 32 columns each): loaded next to the
+  // copies instead of in a round trip of their own after the barrier
+  const int dr = r_base + (lane >> 1);
+  uint4 ov[4];
+#pragma unroll
+  for (int v = 0; v < 4; ++v) ov[v] = make_uint4(0u, 0u, 0u, 0u);
+  const T *po = o_prompt + pbase + (long long)dr * D + (lane & 1) * 32;
+  if (settled) {
+    if (dr < rows_here) {
+#pragma unroll
+      for (int v = 0; v < 4; ++v) ov[v] = __ldg(reinterpret_cast<const uint4 *>(po + v * 8));
+    }
+    pdl_wait();
+    pdl_trigger();
+  } else if (dr < rows_here) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v) ov[v] = *reinterpret_cast<const uint4 *>(po + v * 8);
+  }
   stage_rows<T>(dOs, d_out + pbase, D, rows_here, QT);
   cp_async_wait_all();
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r_base = warp * 16;
   if (r_base >= rows_here) return;
-  // delta_r = sum_d dO[r,d] * O[r,d]; two lanes per row, 32 columns each
   float delta_a, delta_b;
   {
-    const int r = r_base + (lane >> 1);
     float s = 0.f;
-    if (r < rows_here) {
-      const T *po = o_prompt + pbase + (long long)r * D + (lane & 1) * 32;
-      const T *pd = d_out + pbase + (long long)r * D + (lane & 1) * 32;
+    if (dr < rows_here) {
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
-        Vec16<T> a = ld16(po + v * 8), b = ld16(pd + v * 8);
+        Vec16<T> a, b;  // dO from the staged tile (the same values the MMA fragments read)
+        *reinterpret_cast<uint4 *>(&a) = ov[v];
+        uint4 bq;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(bq.x), "=r"(bq.y), "=r"(bq.z), "=r"(bq.w)
+                     : "r"(dOs + swz(dr, (lane & 1) * 4 + v)));
+        *reinterpret_cast<uint4 *>(&b) = bq;
 #pragma unroll
         for (int e = 0; e < 8; ++e) s += tof<T>(a.v[e]) * tof<T>(b.v[e]);
       }
@@ -940,7 +964,7 @@ static int launch_bwd(const T *qkv_ctx, const T *q_prompt, const T *o_prompt, co
   dim3 grid(H, G, (K + QT - 1) / QT);
   prof_tag("attn_bwd G=%d H=%d K=%d max_ctx=%d", G, H, K, max_ctx);
   RPO_CHECK_CUDA(launch_pdl(ro_attn_bwd_mma<T, NT>, grid, dim3(THREADS), smem, st, qkv_ctx, q_prompt, o_prompt, d_out, dq,
-                            ctx_off, K, H));
+                            ctx_off, K, H, g_operands_settled ? 1 : 0));
   RPO_LAUNCH_CHECK();
   return RPO_OK;
 }
