@@ -60,8 +60,23 @@ def metric_name(cfg_id):
 
 
 def workload_config(cfg_id, workload):
-    """The `config` object both arms print (same keys, so the driver can compare them)."""
+    """The workload keys of a `config` object."""
     return {"workload": f"{CONFIG_TEXT[cfg_id]}; {STEP_TEXT}", **workload}
+
+
+L2_POLICY = ("inputs rotate through 8 distinct batches (154 MB > 126 MB L2 at batch 32); a step touches "
+             "~1.5 GB of activations")
+TEXT_REPLICATED = "replicated on every rank (as the reference)"
+
+
+def line_config(cfg_id, workload, world, cuda_graph=True, text_tower=TEXT_REPLICATED, collectives=None):
+    """The `config` object of the JSON line -- the SAME object in both arms (the reference arm is timed on this arm's
+    workload; what its bounded CPU sample departs from is in its `cpu_baseline.sample`)."""
+    if collectives is None:
+        collectives = "none" if world == 1 else "peer"
+    return {**workload_config(cfg_id, workload), "global_batch": workload["batch_per_gpu"] * world,
+            "parallelism": f"dp{world}", "l2_policy": L2_POLICY, "cuda_graph": bool(cuda_graph),
+            "text_tower": text_tower, "collectives": collectives}
 
 
 def load_peaks():
@@ -236,7 +251,7 @@ def main_reference(args):
         "impl": "reference", "metric": metric_name(cfg_id), "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(cfg_id, WORKLOAD),
+        "config": line_config(cfg_id, WORKLOAD, max(1, int(args.gpus))),
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -607,7 +622,7 @@ def measure(workload, world, rank, dev, pg, shard_text, steps, warmup, e2e=True,
     out = {"value": imgs / t_dev, "ms_per_step": t_dev / steps * 1e3, "images_per_sec_per_gpu": imgs / t_dev / world,
            "loss_after": loss, "collectives": job.runner.collectives,
            "text_tower": (f"class-sharded over {world} ranks (all-gather of text features + reduce-scatter of their "
-                          f"gradient)") if job.shard_text else "replicated on every rank (as the reference)",
+                          f"gradient)") if job.shard_text else TEXT_REPLICATED,
            "gpu_launches_per_step": job.runner.launches_per_step,
            "device_workspace_bytes": job.runner.eng.device_bytes()}
     if t_e2e is not None:
@@ -675,13 +690,7 @@ def main_own(args):
             "metric": metric_name(cfg_id), "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_NAME[prec], "data": "synthetic",
-            "config": {
-                **workload_config(cfg_id, W), "global_batch": B * world, "parallelism": f"dp{world}",
-                "l2_policy": "inputs rotate through 8 distinct batches (154 MB > 126 MB L2 at batch 32); a step touches "
-                             "~1.5 GB of activations",
-                "cuda_graph": not args.no_graph,
-                "text_tower": main["text_tower"], "collectives": main["collectives"],
-            },
+            "config": line_config(cfg_id, W, world, not args.no_graph, main["text_tower"], main["collectives"]),
             "images_per_sec_per_gpu": main["images_per_sec_per_gpu"],
             "clocks": clocks,
             "e2e": main["e2e"], "e2e_sync_loss": main["e2e_sync_loss"],

@@ -58,6 +58,9 @@ def test_reference_arm_prints_the_contract_line(monkeypatch, capsys):
     assert line["higher_is_better"] is True and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": bench.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # the `config` object is the own arm's, key for key (bench.line_config builds it for both)
+    assert line["config"] == bench.line_config(2, bench.WORKLOAD, 1)
+    assert line["config"]["global_batch"] == 2 and line["config"]["parallelism"] == "dp1"
     # ranks other than 0 exit without work
     monkeypatch.setenv("RANK", "1")
     bench.main_reference(SimpleNamespace(steps=1, warmup=1, gpus=2))
