@@ -216,7 +216,9 @@ int rpo_peer_reduce_scatter(const RpoPeerComm *comm, void *const *bufs, int32_t 
 
 /* unit kernels (one per hot-path op; used by the parity tests) -------------------------------- */
 
-/* clip/model.py:153-159 LayerNorm.forward: y = LN_f32(x; w, b, eps=1e-5) cast to dtype. x,y [rows,D]. */
+/* clip/model.py:153-159 LayerNorm.forward: y = LN_f32(x; w, b, eps=1e-5) cast to dtype. x,y [rows,D].
+ * w / b are parameters, not activations: the kernels copy them before they wait for the work enqueued ahead of them
+ * on `stream`, so their contents must be final when the call is made (in the path they are frozen CLIP weights). */
 int rpo_layernorm_fwd(const void *x, const float *w, const float *b, void *y, int64_t rows, int32_t D, int32_t dtype,
                       void *stream);
 /* its input-gradient: dx = dres (nullable) + dLN/dx(dy; x, w).  All [rows,D] dtype. */
